@@ -1,0 +1,174 @@
+/*
+ * mmalign.h -- C ABI of the B200-native alignment-scoring and retrieval path.
+ *
+ * The reference (guille-gil/Multimodal-Alignment-of-Noisy-Image-Text-Pairs-using-
+ * Weak-Supervision) has no FFI of its own: its scoring path is Python that sends
+ * SQL to PostgreSQL/pgvector.  The entry points below are what a binding for
+ * that path replaces; each cites the reference site (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative MMALIGN_E* code and never
+ *     throws; mmalign_last_error() gives the text.
+ *   - all array arguments may be HOST or DEVICE pointers (detected with
+ *     cudaPointerGetAttributes).  Host inputs are uploaded into buffers owned by
+ *     the context; device inputs are BORROWED and must stay valid until the next
+ *     set_* call or mmalign_destroy.  Host outputs are filled with a
+ *     device-to-host copy before the call returns.
+ *   - one context per (process, device); calls are ordered on the stream passed
+ *     to mmalign_run (a cudaStream_t, NULL = default stream); not thread-safe per
+ *     context.
+ *   - there is NO CPU fallback: a device that is not sm_100 is an error.
+ *   - ids never cross the ABI: the caller maps image_id / chunk_id to dense row
+ *     indices ("lower index wins a tie") and (manual_id, page) to a 64-bit page
+ *     key; MMALIGN_NULL_KEY is SQL NULL and never joins.
+ */
+#ifndef MMALIGN_H
+#define MMALIGN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMALIGN_ABI_VERSION 1
+#define MMALIGN_NULL_KEY 0xFFFFFFFFFFFFFFFFull
+
+enum {
+    MMALIGN_OK = 0,
+    MMALIGN_EINVAL = -1,   /* bad argument */
+    MMALIGN_ECUDA = -2,    /* CUDA runtime / driver error */
+    MMALIGN_EDEVICE = -3,  /* not an sm_100 device */
+    MMALIGN_ESTATE = -4,   /* call order (run before set_*) */
+    MMALIGN_ELIMIT = -5    /* a documented capacity limit was exceeded */
+};
+
+/* schema bits: src/insert_clip_embeddings.py:446-453 (use_lexical, use_positional) */
+enum {
+    MMALIGN_VANILLA = 1u,    /* vanilla_clip    (F, F) */
+    MMALIGN_LEXICAL = 2u,    /* clip_lexical    (T, F) */
+    MMALIGN_POSITIONAL = 4u, /* clip_positional (F, T) */
+    MMALIGN_COMBINED = 8u,   /* clip_combined   (T, T) */
+    MMALIGN_RAW_SCORES = 0x100u /* mmalign_alignments only: rec = {lexical, positional, 0} before
+                                   the 0.05 / 0.1 thresholds of :387, :393, :400 */
+};
+
+enum {
+    MMALIGN_CAND_SAME_PAGE = 0, /* the reference's join: src/evaluate_alignments.py:128-131 */
+    MMALIGN_CAND_ALL = 1        /* full N x M ranking (BASELINE.json north_star) */
+};
+
+enum {
+    MMALIGN_PATH_AUTO = 0,  /* tcgen05 fused kernel + exact rescoring, exact scan for uncertified rows */
+    MMALIGN_PATH_EXACT = 1, /* exact fp32 scan of every row (slow; validation) */
+    MMALIGN_PATH_FUSED = 2  /* like AUTO but an uncertified row is an error instead of a rescan */
+};
+
+typedef struct mmalign_ctx mmalign_ctx;
+
+typedef struct {
+    uint32_t schema_mask;  /* which of the four schemas to rank, in bit order */
+    int32_t candidates;    /* MMALIGN_CAND_* */
+    int32_t n_k;           /* number of K values, 1..8 */
+    int32_t k_list[8];     /* src/evaluate_alignments.py:388 [1,5,10]; :275 [1,5,10,20] */
+    int32_t mrr_cutoff;    /* src/evaluate_alignments.py:206: 100 */
+    double lam_lex;        /* weight of a 'lexical' alignment record in the ranking score */
+    double lam_pos;        /* weight of a 'positional' record */
+    double lam_comb;       /* weight of a 'combined' record; all 0 = reference ranking */
+    int32_t path;          /* MMALIGN_PATH_* */
+    int32_t kprime;        /* candidates kept per row by the fused kernel; 0 = auto */
+    int32_t reserved[6];
+} mmalign_params;
+
+/* Any pointer may be NULL (output not wanted).  S = popcount(schema_mask),
+ * Kmax = max(k_list), P = mmalign_num_pairs(). */
+typedef struct {
+    int64_t *topk_idx;    /* [S][N][Kmax] global chunk index, -1 padded          (:109-143) */
+    double *topk_score;   /* [S][N][Kmax] ranking score, -inf padded                        */
+    int32_t *pair_rank;   /* [S][P] 1-based rank of each true pair within
+                             max(Kmax, mrr_cutoff), else 0                       (:188-190, :208-214) */
+    double *pair_sim;     /* [P] exact cosine of each true pair                  (:72-106)  */
+    int64_t *hits;        /* [S][n_k] pairs with rank <= k                       (:182-192) */
+    double *rr_sum;       /* [S] sum of 1/rank over pairs with rank <= mrr_cutoff (:203-216) */
+    double *sim_sum;      /* [1] sum of pair_sim                                 (:226-231) */
+    int64_t *num_pairs;   /* [1] P                                               (:393-395) */
+    double *pair_score;   /* [S][P] ranking score of each true pair (multi-GPU rank step)   */
+    int64_t *deep_idx;    /* [S][N][max(Kmax, mrr_cutoff)] lists to the full exact depth    */
+    double *deep_score;   /*        (multi-GPU rank step; see mmalign_count_beating)        */
+    int64_t *stats;       /* [8] 0: rows rescanned exactly, 1: candidates rescored,
+                             2: fused-kernel launches, 3: kernels launched in total,
+                             4: K' used, 5..7 reserved */
+} mmalign_out;
+
+int mmalign_abi_version(void);
+
+/* replaces connect_db(): src/evaluate_alignments.py:37-45 (one context instead of
+ * one TCP connection per call) */
+int mmalign_create(mmalign_ctx **ctx, int device);
+void mmalign_destroy(mmalign_ctx *ctx);
+const char *mmalign_last_error(const mmalign_ctx *ctx); /* ctx may be NULL */
+
+/* replaces the `images` / `text_chunks` tables: src/setup_vector_db.py:102-131.
+ *   emb       [n][D] fp32 clip_embedding (any norm; cosine re-normalises like `<=>`)
+ *   page_key  [n]    (manual_id, page) packed by the caller, MMALIGN_NULL_KEY = NULL
+ *   bbox      [n][4] x0,y0,x1,y1 as doubles (JSON floats); all-zero = missing
+ *   terms     [n][term_words] bit t = lexical term t occurs in the item
+ *             (src/insert_clip_embeddings.py:149-150); NULL = every term (the
+ *             reference's images carry no term set)
+ * set_chunks takes this rank's shard: rows [col_offset, col_offset + m_local)
+ * of the global chunk table. */
+int mmalign_set_images(mmalign_ctx *ctx, const float *emb, const uint64_t *page_key,
+                       const double *bbox, const uint64_t *terms, int64_t n, int32_t D,
+                       int32_t term_words);
+int mmalign_set_chunks(mmalign_ctx *ctx, const float *emb, const uint64_t *page_key,
+                       const double *bbox, const uint64_t *terms, int64_t m_local, int32_t D,
+                       int32_t term_words, int64_t n_terms, int64_t col_offset);
+
+/* replaces get_image_text_pairs(): src/evaluate_alignments.py:48-69.  Pairs are
+ * ordered by (image index, chunk index).  pair_offsets [N+1], pair_chunk [P]
+ * (global chunk index); either may be NULL. */
+int mmalign_num_pairs(mmalign_ctx *ctx, int64_t *num_pairs);
+int mmalign_get_pairs(mmalign_ctx *ctx, int64_t *pair_offsets, int64_t *pair_chunk);
+
+/* replaces get_top_k_similar_chunks / compute_similarity / compute_top_k_accuracy /
+ * compute_mrr / compute_average_similarity: src/evaluate_alignments.py:72-231 */
+int mmalign_run(mmalign_ctx *ctx, const mmalign_params *params, mmalign_out *out, void *stream);
+
+/* replaces the alignment loop of insert_embeddings():
+ * src/insert_clip_embeddings.py:369-414.  rec [P][3] = weak_score of the
+ * 'lexical' / 'positional' / 'combined' record of each true pair in `schema`
+ * (one MMALIGN_* bit), 0.0 where the reference inserts none. */
+int mmalign_alignments(mmalign_ctx *ctx, uint32_t schema, double *rec, void *stream);
+
+/* cross-rank merge after an all-gather of every rank's mmalign_run lists
+ * (chunks are sharded over ranks):
+ *   in_idx/in_score [G][S*N][K]  ->  out_idx/out_score [S*N][K]
+ * ordered by (score desc, index asc). */
+int mmalign_merge_topk(mmalign_ctx *ctx, const int64_t *in_idx, const double *in_score,
+                       int32_t n_ranks, int64_t n_lists, int32_t K, int64_t *out_idx,
+                       double *out_score, void *stream);
+
+/* multi-GPU rank step: how many entries of THIS rank's exact lists (deep_idx /
+ * deep_score [S][N][K] from mmalign_run, K = max(Kmax, mrr_cutoff)) beat each
+ * query pair (q_image, q_chunk global index, q_score [S][n_q]).  counts [S][n_q];
+ * summed over ranks, rank = 1 + sum if sum < cutoff, else 0.  Device pointers. */
+int mmalign_count_beating(mmalign_ctx *ctx, const int64_t *deep_idx, const double *deep_score,
+                          int64_t N, int32_t S, int32_t K, int64_t n_q, const int64_t *q_image,
+                          const int64_t *q_chunk, const double *q_score, int32_t *counts,
+                          void *stream);
+
+/* metric sums from per-pair arrays (deterministic order): hits [S][n_k], rr_sum [S], sim_sum [1] */
+int mmalign_reduce_metrics(mmalign_ctx *ctx, const int32_t *pair_rank, const double *pair_sim,
+                           int32_t S, int64_t P, const int32_t *k_list, int32_t n_k,
+                           int32_t mrr_cutoff, int64_t *hits, double *rr_sum, double *sim_sum,
+                           void *stream);
+
+/* validation hook: the raw bf16 x bf16 -> fp32 score tile matrix of the fused
+ * kernel, out [N][m_local] fp32 (small sizes only). */
+int mmalign_debug_scores(mmalign_ctx *ctx, float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMALIGN_H */

@@ -1,0 +1,88 @@
+"""ctypes binding of csrc/libmmalign.so (the C ABI declared in include/mmalign.h).
+
+There is no fallback: if the shared library is missing or fails to load, import
+of the engine raises.  The library is built in-tree by `build()` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+CSRC = Path(__file__).resolve().parent / "csrc"
+LIB_PATH = CSRC / "libmmalign.so"
+SOURCES = ["api.cu", "prep.cu", "rescore.cu", "fused_tc.cu", "common.cuh"]
+
+NULL_KEY = 0xFFFFFFFFFFFFFFFF
+SCHEMA_BITS = {"vanilla_clip": 1, "clip_lexical": 2, "clip_positional": 4, "clip_combined": 8}
+CAND = {"same_page": 0, "all": 1}
+PATHS = {"auto": 0, "exact": 1, "fused": 2}
+
+
+class Params(C.Structure):
+    _fields_ = [("schema_mask", C.c_uint32), ("candidates", C.c_int32), ("n_k", C.c_int32),
+                ("k_list", C.c_int32 * 8), ("mrr_cutoff", C.c_int32), ("lam_lex", C.c_double),
+                ("lam_pos", C.c_double), ("lam_comb", C.c_double), ("path", C.c_int32),
+                ("kprime", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class Out(C.Structure):
+    _fields_ = [("topk_idx", C.c_void_p), ("topk_score", C.c_void_p), ("pair_rank", C.c_void_p),
+                ("pair_sim", C.c_void_p), ("hits", C.c_void_p), ("rr_sum", C.c_void_p),
+                ("sim_sum", C.c_void_p), ("num_pairs", C.c_void_p), ("pair_score", C.c_void_p),
+                ("deep_idx", C.c_void_p), ("deep_score", C.c_void_p), ("stats", C.c_void_p)]
+
+
+EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_last_error",
+           "mmalign_set_images", "mmalign_set_chunks", "mmalign_num_pairs", "mmalign_get_pairs",
+           "mmalign_run", "mmalign_alignments", "mmalign_merge_topk", "mmalign_count_beating",
+           "mmalign_reduce_metrics", "mmalign_debug_scores"]
+
+_lib = None
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile the CUDA sources for sm_100a into csrc/libmmalign.so (nvcc cross-compiles without a GPU)."""
+    newest = max((CSRC / s).stat().st_mtime for s in SOURCES)
+    hdr = CSRC.parent.parent / "include" / "mmalign.h"
+    newest = max(newest, hdr.stat().st_mtime)
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
+        cmd = ["make", "-C", str(CSRC), "-j4"] + (["-B"] if force else [])
+        r = subprocess.run(cmd, capture_output=not verbose, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("building libmmalign.so failed:\n" + (r.stdout or "") + (r.stderr or ""))
+    return LIB_PATH
+
+
+def load():
+    """Loads libmmalign.so; raises (loudly) when it is absent -- there is no CPU path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+                           "(the scoring path is CUDA-only and has no fallback)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, i64, i32, u32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_double
+    L.mmalign_abi_version.restype = C.c_int
+    L.mmalign_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.mmalign_destroy.argtypes = [vp]
+    L.mmalign_destroy.restype = None
+    L.mmalign_last_error.argtypes = [vp]
+    L.mmalign_last_error.restype = C.c_char_p
+    L.mmalign_set_images.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32]
+    L.mmalign_set_chunks.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i64, i64]
+    L.mmalign_num_pairs.argtypes = [vp, C.POINTER(i64)]
+    L.mmalign_get_pairs.argtypes = [vp, vp, vp]
+    L.mmalign_run.argtypes = [vp, C.POINTER(Params), C.POINTER(Out), vp]
+    L.mmalign_alignments.argtypes = [vp, u32, vp, vp]
+    L.mmalign_merge_topk.argtypes = [vp, vp, vp, i32, i64, i32, vp, vp, vp]
+    L.mmalign_count_beating.argtypes = [vp, vp, vp, i64, i32, i32, i64, vp, vp, vp, vp, vp]
+    L.mmalign_reduce_metrics.argtypes = [vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, vp]
+    L.mmalign_debug_scores.argtypes = [vp, vp, vp]
+    for name in EXPORTS:
+        getattr(L, name)
+        if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L

@@ -1,0 +1,89 @@
+"""Host-side ingest: the reference's record formats -> the dense arrays of the C ABI.
+
+Record formats: data/processed/image_metadata.json (src/pdf_processor.py:406-415),
+text_chunks.json (:686-692) and filtered_lexical_components.json (:1013-1019, read at
+src/insert_clip_embeddings.py:232-248).  String ids never cross the ABI: items keep
+their list order as dense indices ("lower index wins a tie" = table insertion order).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+NULL_KEY = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def page_keys(records: Sequence[dict], page_ids: Dict[tuple, int]) -> np.ndarray:
+    """(manual_id, page) -> dense 64-bit key; page None is SQL NULL and never joins
+    (the join of src/evaluate_alignments.py:61)."""
+    out = np.empty(len(records), np.uint64)
+    for i, r in enumerate(records):
+        page = r.get("page")
+        if page is None or r.get("manual_id") is None:
+            out[i] = NULL_KEY
+        else:
+            out[i] = page_ids.setdefault((r["manual_id"], page), len(page_ids))
+    return out
+
+
+def bbox_array(records: Sequence[dict]) -> np.ndarray:
+    """Missing / wrong-length boxes become all-zero rows, which score 0.0 exactly like
+    src/insert_clip_embeddings.py:161-169 (the zero-width test :172 catches them)."""
+    out = np.zeros((len(records), 4), np.float64)
+    for i, r in enumerate(records):
+        b = r.get("bbox")
+        if b and len(b) == 4:
+            out[i] = b
+    return out
+
+
+def term_bitsets(chunks: Sequence[dict], terms: Sequence[str]) -> np.ndarray:
+    """bit t of row j = terms[t] occurs as a substring of chunk j's lower-cased text
+    (src/insert_clip_embeddings.py:149-150)."""
+    T = len(terms)
+    W = max(1, (T + 63) // 64)
+    out = np.zeros((len(chunks), W), np.uint64)
+    for j, c in enumerate(chunks):
+        text = c["text"].lower()
+        for t, term in enumerate(terms):
+            if term in text:
+                out[j, t >> 6] |= np.uint64(1) << np.uint64(t & 63)
+    return out
+
+
+@dataclass
+class Corpus:
+    image_ids: List[str]
+    chunk_ids: List[str]
+    image_manual: List[str]
+    image_page: list
+    img: dict                 # emb, key, bbox, terms(None)
+    chk: dict                 # emb, key, bbox, terms
+    terms: List[str] = field(default_factory=list)
+    image_index: Dict[str, int] = field(default_factory=dict)
+    chunk_index: Dict[str, int] = field(default_factory=dict)
+
+    @property
+    def n_terms(self) -> int:
+        return len(self.terms)
+
+
+def build_corpus(images: Sequence[dict], chunks: Sequence[dict], image_emb, chunk_emb,
+                 lexical_components: Optional[dict | Sequence[str]] = None) -> Corpus:
+    if isinstance(lexical_components, dict):  # insert_clip_embeddings.py:237-239
+        terms = [c["term"] for c in lexical_components.get("components", [])]
+    else:
+        terms = list(lexical_components or [])
+    page_ids: Dict[tuple, int] = {}
+    img = dict(emb=np.ascontiguousarray(image_emb, np.float32), key=page_keys(images, page_ids),
+               bbox=bbox_array(images), terms=None)
+    chk = dict(emb=np.ascontiguousarray(chunk_emb, np.float32), key=page_keys(chunks, page_ids),
+               bbox=bbox_array(chunks), terms=term_bitsets(chunks, terms))
+    c = Corpus(image_ids=[r["image_id"] for r in images], chunk_ids=[r["chunk_id"] for r in chunks],
+               image_manual=[r.get("manual_id") for r in images], image_page=[r.get("page") for r in images],
+               img=img, chk=chk, terms=terms)
+    c.image_index = {s: i for i, s in enumerate(c.image_ids)}
+    c.chunk_index = {s: j for j, s in enumerate(c.chunk_ids)}
+    return c

@@ -1,0 +1,531 @@
+// api.cu -- the C ABI of include/mmalign.h: context, uploads, and the
+// K0 -> K1 -> K2 -> exact scan -> K4 pipeline.  No CPU fallback anywhere: every
+// result is produced by the kernels in prep.cu / fused_tc.cu / rescore.cu.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+
+using namespace mma;
+
+static thread_local char g_err[512] = "";
+
+struct DevBuf {  // growable device scratch
+    void *p = nullptr;
+    size_t bytes = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct SideStore {
+    Side s;
+    std::vector<void *> owned;  // uploads + derived buffers
+    float *err_max = nullptr;   // [1] max rounding-error norm over the rows
+    alignas(64) CUtensorMap tmap;
+    bool ready = false;
+    void release()
+    {
+        for (void *p : owned) cudaFree(p);
+        owned.clear();
+        s = Side();
+        err_max = nullptr;
+        ready = false;
+    }
+};
+
+struct mmalign_ctx {
+    int device = 0;
+    int sm_count = 148;
+    char err[512] = "";
+    SideStore img, chk;
+    int64_t n_terms = 0, col_offset = 0;
+    PairIndex px;
+    bool px_ready = false;
+    DevBuf px_offsets, px_sorted, px_start;
+    DevBuf list_keys, list_tau, list_count;
+    DevBuf fail_rows, small;      // small: fail_count, cand_counter, error_flag, k_list, stats
+    DevBuf metrics_scratch, stage; // stage: device copies of host outputs
+};
+
+static int fail(mmalign_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    snprintf(g_err, sizeof g_err, "%s", buf);
+    if (c) snprintf(c->err, sizeof c->err, "%s", buf);
+    return code;
+}
+
+#define CU(c, x)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (x);                                                                      \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail((c), MMALIGN_ECUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+static bool is_device_ptr(const void *p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+extern "C" int mmalign_abi_version(void) { return MMALIGN_ABI_VERSION; }
+
+extern "C" const char *mmalign_last_error(const mmalign_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" int mmalign_create(mmalign_ctx **out, int device)
+{
+    if (!out) return fail(nullptr, MMALIGN_EINVAL, "mmalign_create: ctx is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, MMALIGN_EDEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(nullptr, MMALIGN_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CU(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(nullptr, MMALIGN_EDEVICE, "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)",
+                    device, prop.major, prop.minor);
+    CU(nullptr, cudaSetDevice(device));
+    mmalign_ctx *c = new mmalign_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (c->small.reserve(4096) != cudaSuccess) { delete c; return fail(nullptr, MMALIGN_ECUDA, "cudaMalloc failed"); }
+    *out = c;
+    return MMALIGN_OK;
+}
+
+extern "C" void mmalign_destroy(mmalign_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->img.release();
+    c->chk.release();
+    DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->list_keys, &c->list_tau, &c->list_count,
+                      &c->fail_rows, &c->small, &c->metrics_scratch, &c->stage};
+    for (DevBuf *b : bufs) b->release();
+    delete c;
+}
+
+template <typename T>
+static int adopt(mmalign_ctx *c, SideStore &ss, const T *src, size_t count, const T **dst, cudaStream_t st)
+{
+    *dst = nullptr;
+    if (!src || count == 0) return MMALIGN_OK;
+    if (is_device_ptr(src)) { *dst = src; return MMALIGN_OK; }  // borrowed
+    void *d = nullptr;
+    CU(c, cudaMalloc(&d, count * sizeof(T)));
+    ss.owned.push_back(d);
+    CU(c, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *dst = static_cast<const T *>(d);
+    return MMALIGN_OK;
+}
+
+static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint64_t *key, const double *bbox,
+                    const uint64_t *terms, int64_t n, int D, int term_words, int box_rows, const char *what)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "%s: ctx is NULL", what);
+    CU(c, cudaSetDevice(c->device));
+    if (n < 0 || n > 0x7FFFFFF0ll) return fail(c, MMALIGN_EINVAL, "%s: row count %lld out of range", what, (long long)n);
+    if (D <= 0 || D % 4 != 0 || D > 4096) return fail(c, MMALIGN_EINVAL, "%s: D=%d must be a multiple of 4 in 4..4096", what, D);
+    if (n > 0 && (!emb || !key)) return fail(c, MMALIGN_EINVAL, "%s: emb and page_key are required", what);
+    if (term_words < 0 || (terms && term_words == 0)) return fail(c, MMALIGN_EINVAL, "%s: bad term_words", what);
+    cudaStream_t st = 0;
+    CU(c, cudaStreamSynchronize(st));
+    ss.release();
+    c->px_ready = false;
+    Side &s = ss.s;
+    s.n = n; s.D = D; s.term_words = term_words;
+    int rc;
+    if ((rc = adopt(c, ss, emb, (size_t)n * D, &s.emb, st))) return rc;
+    if ((rc = adopt(c, ss, key, (size_t)n, &s.key, st))) return rc;
+    if ((rc = adopt(c, ss, terms, (size_t)n * term_words, &s.terms, st))) return rc;
+    if (bbox) {
+        if ((rc = adopt(c, ss, bbox, (size_t)n * 4, &s.bbox, st))) return rc;
+    } else if (n > 0) {  // missing boxes: all zero -> positional score 0 (insert_clip_embeddings.py:161)
+        void *d = nullptr;
+        CU(c, cudaMalloc(&d, (size_t)n * 4 * sizeof(double)));
+        ss.owned.push_back(d);
+        CU(c, cudaMemsetAsync(d, 0, (size_t)n * 4 * sizeof(double), st));
+        s.bbox = static_cast<const double *>(d);
+    }
+    const size_t nn = n > 0 ? (size_t)n : 1;
+    void *p = nullptr;
+    CU(c, cudaMalloc(&p, nn * D * sizeof(__nv_bfloat16))); ss.owned.push_back(p); s.emb_bf16 = (__nv_bfloat16 *)p;
+    CU(c, cudaMalloc(&p, nn * sizeof(float))); ss.owned.push_back(p); s.norm2 = (float *)p;
+    CU(c, cudaMalloc(&p, nn * sizeof(float))); ss.owned.push_back(p); s.err = (float *)p;
+    CU(c, cudaMalloc(&p, sizeof(float))); ss.owned.push_back(p); ss.err_max = (float *)p;
+    CU(c, launch_prep(s, st));
+    CU(c, reduce_max_float(s.err, n, ss.err_max, st));
+    if (n > 0 && D % 64 == 0) {
+        char msg[256];
+        if (encode_tensor_map(&ss.tmap, s.emb_bf16, n, D, box_rows, msg, sizeof msg))
+            return fail(c, MMALIGN_ECUDA, "%s: %s", what, msg);
+    }
+    CU(c, cudaStreamSynchronize(st));
+    ss.ready = true;
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_set_images(mmalign_ctx *c, const float *emb, const uint64_t *key, const double *bbox,
+                                  const uint64_t *terms, int64_t n, int32_t D, int32_t term_words)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_set_images: ctx is NULL");
+    return set_side(c, c->img, emb, key, bbox, terms, n, D, term_words, 128, "mmalign_set_images");
+}
+
+extern "C" int mmalign_set_chunks(mmalign_ctx *c, const float *emb, const uint64_t *key, const double *bbox,
+                                  const uint64_t *terms, int64_t m, int32_t D, int32_t term_words,
+                                  int64_t n_terms, int64_t col_offset)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_set_chunks: ctx is NULL");
+    if (n_terms < 0 || n_terms > (int64_t)term_words * 64)
+        return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks: n_terms=%lld does not fit %d term words", (long long)n_terms, term_words);
+    if (col_offset < 0) return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks: negative col_offset");
+    int rc = set_side(c, c->chk, emb, key, bbox, terms, m, D, term_words, 256, "mmalign_set_chunks");
+    if (rc) return rc;
+    c->n_terms = n_terms;
+    c->col_offset = col_offset;
+    return MMALIGN_OK;
+}
+
+static int ensure_index(mmalign_ctx *c)
+{
+    if (!c->img.ready || !c->chk.ready) return fail(c, MMALIGN_ESTATE, "set_images and set_chunks must be called first");
+    if (c->img.s.D != c->chk.s.D) return fail(c, MMALIGN_EINVAL, "image D=%d differs from chunk D=%d", c->img.s.D, c->chk.s.D);
+    if (c->img.s.terms && c->img.s.term_words != c->chk.s.term_words)
+        return fail(c, MMALIGN_EINVAL, "image term_words=%d differs from chunk term_words=%d", c->img.s.term_words, c->chk.s.term_words);
+    if (c->px_ready) return MMALIGN_OK;
+    CU(c, cudaSetDevice(c->device));
+    const int64_t N = c->img.s.n, M = c->chk.s.n;
+    CU(c, c->px_offsets.reserve(sizeof(int64_t) * (N + 1)));
+    CU(c, c->px_sorted.reserve(sizeof(int32_t) * (M > 0 ? M : 1)));
+    CU(c, c->px_start.reserve(sizeof(int64_t) * (N > 0 ? N : 1)));
+    c->px.offsets = (int64_t *)c->px_offsets.p;
+    c->px.sorted_chunk = (int32_t *)c->px_sorted.p;
+    c->px.sp_start = (int64_t *)c->px_start.p;
+    CU(c, build_pair_index(c->img.s, c->chk.s, c->px, 0));
+    c->px_ready = true;
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_num_pairs(mmalign_ctx *c, int64_t *num_pairs)
+{
+    if (!c || !num_pairs) return fail(c, MMALIGN_EINVAL, "mmalign_num_pairs: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    *num_pairs = c->px.P;
+    return MMALIGN_OK;
+}
+
+// ---- output staging: host pointers get a device twin that is copied back --------------------
+struct Stager {
+    mmalign_ctx *c;
+    cudaStream_t st;
+    struct Item { void *host; void *dev; size_t bytes; };
+    std::vector<Item> items;
+    size_t used = 0;
+    std::vector<std::pair<void **, size_t>> pending;  // (slot to patch, offset)
+    template <typename T> int map(T *user, size_t count, T **dev)
+    {
+        *dev = nullptr;
+        if (!user || count == 0) return 0;
+        if (is_device_ptr(user)) { *dev = user; return 0; }
+        const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+        items.push_back({user, nullptr, count * sizeof(T)});
+        pending.push_back({(void **)dev, used});
+        used += bytes;
+        return 0;
+    }
+    int commit()
+    {
+        if (!used) return 0;
+        if (c->stage.reserve(used) != cudaSuccess) return fail(c, MMALIGN_ECUDA, "cudaMalloc of %zu staging bytes failed", used);
+        for (size_t i = 0; i < pending.size(); ++i) {
+            void *d = (char *)c->stage.p + pending[i].second;
+            *pending[i].first = d;
+            items[i].dev = d;
+        }
+        return 0;
+    }
+    int copy_back()
+    {
+        for (auto &it : items) CU(c, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, st));
+        return 0;
+    }
+};
+
+extern "C" int mmalign_get_pairs(mmalign_ctx *c, int64_t *pair_offsets, int64_t *pair_chunk)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_get_pairs: ctx is NULL");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    const int64_t N = c->img.s.n;
+    if (pair_offsets)
+        CU(c, cudaMemcpyAsync(pair_offsets, c->px.offsets, sizeof(int64_t) * (N + 1), cudaMemcpyDefault, st));
+    if (pair_chunk && c->px.P > 0) {
+        Stager sg{c, st};
+        int64_t *d = nullptr;
+        sg.map(pair_chunk, (size_t)c->px.P, &d);
+        if ((rc = sg.commit())) return rc;
+        CU(c, launch_pair_chunk(c->px, N, c->col_offset, d, st));
+        if ((rc = sg.copy_back())) return rc;
+    }
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+static int schema_index(uint32_t bit)
+{
+    switch (bit) { case 1: return 0; case 2: return 1; case 4: return 2; case 8: return 3; }
+    return -1;
+}
+
+extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream)
+{
+    if (!c || !prm || !uo) return fail(c, MMALIGN_EINVAL, "mmalign_run: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const Side &img = c->img.s, &chk = c->chk.s;
+    const int64_t N = img.n, M = chk.n, P = c->px.P;
+    // ---- parameters
+    RunParams rp = {};
+    for (int s = 0; s < 4; ++s)
+        if (prm->schema_mask & (1u << s)) rp.schema[rp.S++] = s;
+    if (rp.S == 0 || (prm->schema_mask & ~15u)) return fail(c, MMALIGN_EINVAL, "schema_mask=0x%x selects no valid schema", prm->schema_mask);
+    if (prm->candidates != MMALIGN_CAND_SAME_PAGE && prm->candidates != MMALIGN_CAND_ALL)
+        return fail(c, MMALIGN_EINVAL, "candidates=%d is not MMALIGN_CAND_SAME_PAGE/ALL", prm->candidates);
+    if (prm->n_k < 1 || prm->n_k > kMaxK) return fail(c, MMALIGN_EINVAL, "n_k=%d must be in 1..8", prm->n_k);
+    rp.n_k = prm->n_k;
+    for (int q = 0; q < rp.n_k; ++q) {
+        if (prm->k_list[q] < 1 || prm->k_list[q] > 256) return fail(c, MMALIGN_EINVAL, "k_list[%d]=%d must be in 1..256", q, prm->k_list[q]);
+        rp.k_list[q] = prm->k_list[q];
+        if (rp.k_list[q] > rp.kmax) rp.kmax = rp.k_list[q];
+    }
+    if (prm->mrr_cutoff < 0 || prm->mrr_cutoff > 256) return fail(c, MMALIGN_EINVAL, "mrr_cutoff=%d must be in 0..256", prm->mrr_cutoff);
+    rp.mrr_cutoff = prm->mrr_cutoff;
+    rp.kneed = rp.kmax > rp.mrr_cutoff ? rp.kmax : rp.mrr_cutoff;
+    rp.candidates = prm->candidates;
+    rp.lam_lex = prm->lam_lex; rp.lam_pos = prm->lam_pos; rp.lam_comb = prm->lam_comb;
+    rp.n_terms = c->n_terms;
+    rp.col_offset = c->col_offset;
+    const bool needs_terms = (prm->schema_mask & (MMALIGN_LEXICAL | MMALIGN_COMBINED)) != 0;
+    if (needs_terms && !chk.terms && M > 0) return fail(c, MMALIGN_EINVAL, "lexical schema requested but the chunks have no term sets");
+    if (prm->path < 0 || prm->path > 2) return fail(c, MMALIGN_EINVAL, "path=%d unknown", prm->path);
+    CU(c, cudaSetDevice(c->device));
+    // ---- outputs
+    Stager sg{c, st};
+    Outputs out = {};
+    int64_t *d_hits = nullptr, *d_np = nullptr, *d_stats = nullptr;
+    double *d_rr = nullptr, *d_sim = nullptr;
+    const size_t SNK = (size_t)rp.S * N * rp.kmax, SP = (size_t)rp.S * P;
+    if ((uo->topk_idx == nullptr) != (uo->topk_score == nullptr)) return fail(c, MMALIGN_EINVAL, "topk_idx and topk_score go together");
+    sg.map(uo->topk_idx, SNK, &out.topk_idx);
+    sg.map(uo->topk_score, SNK, &out.topk_score);
+    sg.map(uo->pair_rank, SP, &out.pair_rank);
+    sg.map(uo->pair_sim, (size_t)P, &out.pair_sim);
+    sg.map(uo->hits, (size_t)rp.S * rp.n_k, &d_hits);
+    sg.map(uo->rr_sum, (size_t)rp.S, &d_rr);
+    sg.map(uo->sim_sum, 1, &d_sim);
+    sg.map(uo->num_pairs, 1, &d_np);
+    sg.map(uo->stats, 8, &d_stats);
+    sg.map(uo->pair_score, SP, &out.pair_score);
+    if ((uo->deep_idx == nullptr) != (uo->deep_score == nullptr)) return fail(c, MMALIGN_EINVAL, "deep_idx and deep_score go together");
+    sg.map(uo->deep_idx, (size_t)rp.S * N * rp.kneed, &out.deep_idx);
+    sg.map(uo->deep_score, (size_t)rp.S * N * rp.kneed, &out.deep_score);
+    // metric sums need the per-pair arrays even if the caller did not ask for them
+    const bool want_sums = uo->hits || uo->rr_sum || uo->sim_sum;
+    if ((rc = sg.commit())) return rc;
+    DevBuf extra;  // scratch per-pair arrays when only the sums were requested
+    if (want_sums && (!out.pair_rank || !out.pair_sim) && P > 0) {
+        CU(c, extra.reserve(SP * sizeof(int32_t) + 256 + (size_t)P * sizeof(double)));
+        if (!out.pair_rank) out.pair_rank = (int32_t *)extra.p;
+        if (!out.pair_sim) out.pair_sim = (double *)((char *)extra.p + ((SP * sizeof(int32_t) + 255) & ~(size_t)255));
+    }
+    // ---- small device state
+    int32_t *fail_count = (int32_t *)c->small.p;
+    unsigned long long *cand_counter = (unsigned long long *)((char *)c->small.p + 8);
+    int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
+    int32_t *k_list_dev = (int32_t *)((char *)c->small.p + 64);
+    CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
+    CU(c, cudaMemcpyAsync(k_list_dev, rp.k_list, sizeof(int32_t) * kMaxK, cudaMemcpyHostToDevice, st));
+    if (out.pair_rank && SP) CU(c, cudaMemsetAsync(out.pair_rank, 0, SP * sizeof(int32_t), st));
+    long long launches = 2, fused_launches = 0, kprime_used = 0;
+    // ---- scoring
+    if (N > 0) {
+        if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
+            CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, cand_counter,
+                                 error_flag, st));
+            launches += 1;
+        } else if (prm->path == MMALIGN_PATH_EXACT || M == 0) {
+            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, st));
+            launches += 1;
+        } else {
+            if (img.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", img.D);
+            if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
+            FusedPlan plan;
+            const int prc = fused_plan(N, M, img.D, rp.kneed, prm->kprime, c->sm_count, &plan);
+            if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)N, (long long)M, img.D, prm->kprime, prc);
+            CU(c, c->list_keys.reserve((size_t)plan.n_lists * plan.cap * sizeof(uint64_t)));
+            CU(c, c->list_tau.reserve((size_t)plan.n_lists * sizeof(float)));
+            CU(c, c->list_count.reserve((size_t)plan.n_lists * sizeof(int32_t)));
+            CU(c, c->fail_rows.reserve((size_t)N * sizeof(int32_t)));
+            CandLists L;
+            L.keys = (uint64_t *)c->list_keys.p; L.tau = (float *)c->list_tau.p; L.count = (int32_t *)c->list_count.p;
+            CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, L, nullptr, st));
+            CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, (int32_t *)c->fail_rows.p, fail_count,
+                                 cand_counter, error_flag, st));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, st));
+            launches += 3;
+            fused_launches = 1;
+            kprime_used = plan.kprime;
+        }
+    }
+    // ---- metric sums
+    if (want_sums) {
+        CU(c, c->metrics_scratch.reserve(metrics_scratch_bytes(rp.S, rp.n_k)));
+        CU(c, launch_reduce_metrics(out.pair_rank, out.pair_sim, rp.S, P, k_list_dev, rp.n_k, rp.mrr_cutoff, d_hits,
+                                    d_rr, d_sim, c->metrics_scratch.p, st));
+        launches += 2;
+    }
+    // ---- status, stats
+    struct { int32_t fail; int32_t pad; unsigned long long cand; int32_t err; } h = {};
+    CU(c, cudaMemcpyAsync(&h, c->small.p, 24, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    if (h.err) { extra.release(); return fail(c, MMALIGN_ELIMIT, "an image has more than 512 same-page chunks (capacity limit of this build)"); }
+    if (prm->path == MMALIGN_PATH_FUSED && h.fail > 0) {
+        extra.release();
+        return fail(c, MMALIGN_ELIMIT, "%d rows were not certified by the fused path (MMALIGN_PATH_FUSED forbids the exact rescan)", h.fail);
+    }
+    if (d_np) CU(c, cudaMemcpyAsync(d_np, &P, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    if (d_stats) {
+        const int64_t stats[8] = {h.fail, (int64_t)h.cand, fused_launches, launches, kprime_used, 0, 0, 0};
+        CU(c, cudaMemcpyAsync(d_stats, stats, sizeof stats, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = sg.copy_back())) { extra.release(); return rc; }
+    CU(c, cudaStreamSynchronize(st));
+    extra.release();
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_alignments(mmalign_ctx *c, uint32_t schema, double *rec, void *stream)
+{
+    if (!c || !rec) return fail(c, MMALIGN_EINVAL, "mmalign_alignments: NULL argument");
+    const bool raw = (schema & MMALIGN_RAW_SCORES) != 0;
+    const int s = schema_index(schema & ~MMALIGN_RAW_SCORES);
+    if (s < 0) return fail(c, MMALIGN_EINVAL, "schema=0x%x must be exactly one MMALIGN_* schema bit", schema);
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    if ((s == 1 || s == 3) && !c->chk.s.terms && c->chk.s.n > 0)
+        return fail(c, MMALIGN_EINVAL, "lexical schema requested but the chunks have no term sets");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    Stager sg{c, st};
+    double *d = nullptr;
+    sg.map(rec, (size_t)c->px.P * 3, &d);
+    if ((rc = sg.commit())) return rc;
+    if (c->px.P > 0) CU(c, launch_alignments(c->img.s, c->chk.s, c->px, s, c->n_terms, raw, d, st));
+    if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_merge_topk(mmalign_ctx *c, const int64_t *in_idx, const double *in_score, int32_t G,
+                                  int64_t n_lists, int32_t K, int64_t *out_idx, double *out_score, void *stream)
+{
+    if (!c || !in_idx || !in_score || !out_idx || !out_score) return fail(c, MMALIGN_EINVAL, "mmalign_merge_topk: NULL argument");
+    if (G < 1 || G > 16 || K < 1 || n_lists < 0) return fail(c, MMALIGN_EINVAL, "mmalign_merge_topk: bad G/K/n_lists");
+    if (!is_device_ptr(in_idx) || !is_device_ptr(in_score) || !is_device_ptr(out_idx) || !is_device_ptr(out_score))
+        return fail(c, MMALIGN_EINVAL, "mmalign_merge_topk takes device pointers (it runs between two collectives)");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, launch_merge_topk(in_idx, in_score, G, n_lists, K, out_idx, out_score, (cudaStream_t)stream));
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_count_beating(mmalign_ctx *c, const int64_t *deep_idx, const double *deep_score, int64_t N,
+                                     int32_t S, int32_t K, int64_t n_q, const int64_t *q_image,
+                                     const int64_t *q_chunk, const double *q_score, int32_t *counts, void *stream)
+{
+    if (!c || !deep_idx || !deep_score || (n_q > 0 && (!q_image || !q_chunk || !q_score || !counts)))
+        return fail(c, MMALIGN_EINVAL, "mmalign_count_beating: NULL argument");
+    if (S < 1 || S > 4 || K < 1 || N < 0 || n_q < 0) return fail(c, MMALIGN_EINVAL, "mmalign_count_beating: bad S/K/N/n_q");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, launch_count_beating(deep_idx, deep_score, N, S, K, n_q, q_image, q_chunk, q_score, counts, (cudaStream_t)stream));
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_reduce_metrics(mmalign_ctx *c, const int32_t *pair_rank, const double *pair_sim, int32_t S,
+                                      int64_t P, const int32_t *k_list, int32_t n_k, int32_t mrr_cutoff,
+                                      int64_t *hits, double *rr_sum, double *sim_sum, void *stream)
+{
+    if (!c || !pair_rank || !k_list) return fail(c, MMALIGN_EINVAL, "mmalign_reduce_metrics: NULL argument");
+    if (S < 1 || S > 4 || n_k < 1 || n_k > kMaxK || P < 0) return fail(c, MMALIGN_EINVAL, "mmalign_reduce_metrics: bad S/n_k/P");
+    if (!is_device_ptr(pair_rank) || (pair_sim && !is_device_ptr(pair_sim)))
+        return fail(c, MMALIGN_EINVAL, "mmalign_reduce_metrics: pair arrays must be device pointers");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    Stager sg{c, st};
+    int64_t *d_hits = nullptr;
+    double *d_rr = nullptr, *d_sim = nullptr;
+    sg.map(hits, (size_t)S * n_k, &d_hits);
+    sg.map(rr_sum, (size_t)S, &d_rr);
+    sg.map(sim_sum, 1, &d_sim);
+    int rc;
+    if ((rc = sg.commit())) return rc;
+    int32_t *k_list_dev = (int32_t *)((char *)c->small.p + 64);
+    CU(c, cudaMemcpyAsync(k_list_dev, k_list, sizeof(int32_t) * n_k, cudaMemcpyDefault, st));
+    CU(c, c->metrics_scratch.reserve(metrics_scratch_bytes(S, n_k)));
+    CU(c, launch_reduce_metrics(pair_rank, pair_sim, S, P, k_list_dev, n_k, mrr_cutoff, d_hits, d_rr, d_sim,
+                                c->metrics_scratch.p, st));
+    if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_debug_scores(mmalign_ctx *c, float *out, void *stream)
+{
+    if (!c || !out) return fail(c, MMALIGN_EINVAL, "mmalign_debug_scores: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    const Side &img = c->img.s, &chk = c->chk.s;
+    if (img.n == 0 || chk.n == 0) return MMALIGN_OK;
+    if (img.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused kernel needs D %% 64 == 0");
+    if ((double)img.n * (double)chk.n > 2.7e8) return fail(c, MMALIGN_ELIMIT, "mmalign_debug_scores is for small problems (N*M <= 2.7e8)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    FusedPlan plan;
+    if (fused_plan(img.n, chk.n, img.D, 10, 0, c->sm_count, &plan)) return fail(c, MMALIGN_ELIMIT, "no fused plan");
+    Stager sg{c, st};
+    float *d = nullptr;
+    sg.map(out, (size_t)img.n * chk.n, &d);
+    if ((rc = sg.commit())) return rc;
+    CandLists L;
+    CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, L, d, st));
+    if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}

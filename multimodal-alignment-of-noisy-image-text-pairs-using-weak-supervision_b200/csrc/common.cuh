@@ -1,0 +1,247 @@
+// common.cuh -- shared device helpers of the alignment-scoring path (sm_100a only).
+//
+// Build flag contract: the whole library is compiled with -fmad=false, so the
+// only fused multiply-adds are the explicit fmaf() calls of the canonical dot
+// product; the fp64 weak-supervision terms round exactly like the reference's
+// Python float arithmetic (src/insert_clip_embeddings.py:144-210).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/mmalign.h"
+
+namespace mma {
+
+constexpr int kMaxSchemas = 4;
+constexpr int kMaxK = 8;
+
+// ---------------------------------------------------------------------------
+// Shared state between the launchers (api.cu owns the buffers).
+// ---------------------------------------------------------------------------
+struct Side {                 // images or this rank's chunk shard
+    int64_t n = 0;
+    int D = 0;
+    int term_words = 0;
+    const float *emb = nullptr;       // [n][D] fp32 master rows
+    const uint64_t *key = nullptr;    // [n] page keys
+    const double *bbox = nullptr;     // [n][4]
+    const uint64_t *terms = nullptr;  // [n][term_words] or null (= all terms)
+    __nv_bfloat16 *emb_bf16 = nullptr; // [n][D] L2-normalised rows, bf16 (fused-kernel operand)
+    float *norm2 = nullptr;           // [n] sum x^2 in the canonical order
+    float *err = nullptr;             // [n] |normalised row - its bf16 rounding|_2
+};
+
+struct PairIndex {            // CSR of same-page chunks per image (evaluate_alignments.py:48-69)
+    int64_t P = 0;
+    int64_t *offsets = nullptr;      // [N+1] pair offsets, pairs ordered (image, chunk)
+    int32_t *sorted_chunk = nullptr; // [M] local chunk indices sorted by (page key, index)
+    int64_t *sp_start = nullptr;     // [N] first position in sorted_chunk of the image's page
+};
+
+struct RunParams {
+    int S;                 // schemas ranked
+    int schema[kMaxSchemas];
+    int candidates;
+    int n_k;
+    int k_list[kMaxK];
+    int kmax;              // max(k_list): width of the top-K lists
+    int mrr_cutoff;
+    int kneed;             // max(kmax, mrr_cutoff): depth the ranking must be exact to
+    double lam_lex, lam_pos, lam_comb;
+    int64_t n_terms;       // T = len(lexical_components)
+    int64_t col_offset;    // global index of local chunk 0
+};
+
+struct Outputs {           // device pointers (api.cu stages host outputs)
+    int64_t *topk_idx;
+    double *topk_score;
+    int32_t *pair_rank;
+    double *pair_sim;
+    double *pair_score;    // [S][P] ranking score of each true pair (multi-GPU rank step)
+    int64_t *deep_idx;     // [S][N][kneed] lists to the full exact depth (multi-GPU rank step)
+    double *deep_score;
+};
+
+// candidate lists written by the fused kernel (fused_tc.cu), read by rescore.cu
+struct CandLists {
+    uint64_t *keys = nullptr;  // [n_lists][cap]  (ordered fp32 score << 32) | ~column
+    float *tau = nullptr;      // [n_lists] list is complete above tau
+    int32_t *count = nullptr;  // [n_lists]
+    int cap = 0;               // entries per list
+    int n_splits = 0;          // column splits per row block
+    int64_t n_row_blocks = 0;
+    int kprime = 0;
+};
+
+// ---------------------------------------------------------------------------
+// Ordered keys
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t f32_ordered(float f)
+{
+#ifdef __CUDA_ARCH__
+    uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t k)
+{
+    uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ uint64_t cand_pack(float score, uint32_t col)
+{
+    return ((uint64_t)f32_ordered(score) << 32) | (uint64_t)(0xFFFFFFFFu - col);
+}
+__device__ __forceinline__ float cand_score(uint64_t k) { return f32_unordered((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t cand_col(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+// ---------------------------------------------------------------------------
+// Canonical fp32 dot product (bit-identical to oracle/mmalign_oracle.c: orc_dot):
+// lane l owns float4 chunks l, l+32, ... ; four fmaf chains per lane; folded
+// (0+1)+(2+3); xor butterfly 16,8,4,2,1.  Rows must be 16-byte aligned, D % 4 == 0.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_dot(const float4 *__restrict__ a, const float4 *__restrict__ b,
+                                          int d4, int lane)
+{
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    for (int c = lane; c < d4; c += 32) {
+        const float4 x = a[c];
+        const float4 y = __ldg(b + c);
+        c0 = fmaf(x.x, y.x, c0);
+        c1 = fmaf(x.y, y.y, c1);
+        c2 = fmaf(x.z, y.z, c2);
+        c3 = fmaf(x.w, y.w, c3);
+    }
+    float s = (c0 + c1) + (c2 + c3);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xFFFFFFFFu, s, off);
+    return s;
+}
+
+// pgvector cosine as SQL sees it, 1 - (a <=> b): evaluate_alignments.py:97, :128
+__device__ __forceinline__ double sim_from_sums(float dot, float na, float nb)
+{
+    double sim = (double)dot / sqrt((double)na * (double)nb);
+    if (sim > 1.0) sim = 1.0;
+    else if (sim < -1.0) sim = -1.0;
+    const double dist = 1.0 - sim;
+    return 1.0 - dist;
+}
+
+// ---------------------------------------------------------------------------
+// Weak-supervision terms in fp64
+// ---------------------------------------------------------------------------
+// src/insert_clip_embeddings.py:144-156
+__device__ __forceinline__ double lexical_score(long long hits, long long T)
+{
+    if (T <= 0) return 0.0;
+    double denom = (double)T * 0.1;
+    if (!(denom > 1.0)) denom = 1.0;
+    const double s = (double)hits / denom;
+    return s < 1.0 ? s : 1.0;
+}
+
+// src/insert_clip_embeddings.py:159-210 (all-zero bbox = missing, caught by :172/:174)
+__device__ __forceinline__ double positional_score(const double *ib, const double *cb)
+{
+    if ((ib[2] - ib[0] == 0.0) || (ib[3] - ib[1] == 0.0)) return 0.0;
+    if ((cb[2] - cb[0] == 0.0) || (cb[3] - cb[1] == 0.0)) return 0.0;
+    const double x1 = ib[0] > cb[0] ? ib[0] : cb[0];
+    const double y1 = ib[1] > cb[1] ? ib[1] : cb[1];
+    const double x2 = ib[2] < cb[2] ? ib[2] : cb[2];
+    const double y2 = ib[3] < cb[3] ? ib[3] : cb[3];
+    if (x2 <= x1 || y2 <= y1) {
+        const double icx = (ib[0] + ib[2]) / 2, icy = (ib[1] + ib[3]) / 2;
+        const double ccx = (cb[0] + cb[2]) / 2, ccy = (cb[1] + cb[3]) / 2;
+        const double dx = icx - ccx, dy = icy - ccy;
+        const double dist = sqrt(dx * dx + dy * dy);
+        const double s = 1.0 - (dist / 1000.0);
+        return s > 0.0 ? s : 0.0;
+    }
+    const double w = x2 - x1, h = y2 - y1;
+    const double inter = (w > 0 ? w : 0) * (h > 0 ? h : 0);
+    const double ia = (ib[2] - ib[0]) * (ib[3] - ib[1]);
+    const double ca = (cb[2] - cb[0]) * (cb[3] - cb[1]);
+    const double uni = ia + ca - inter;
+    if (uni == 0.0) return 0.0;
+    return inter / uni;
+}
+
+// src/insert_clip_embeddings.py:385-414; rec = {lexical, positional, combined}
+__device__ __forceinline__ void weak_records(bool use_lex, bool use_pos, double lex, double pos,
+                                             double *rec)
+{
+    const bool have_lex = use_lex && lex > 0.05;
+    const bool have_pos = use_pos && pos > 0.05;
+    rec[0] = rec[1] = rec[2] = 0.0;
+    if (use_lex && use_pos && have_lex && have_pos) {
+        const double c = (lex + pos) / 2;
+        if (c > 0.1) rec[2] = c;
+    } else {
+        if (have_lex) rec[0] = lex;
+        if (have_pos) rec[1] = pos;
+    }
+}
+
+__device__ __forceinline__ bool schema_uses_lex(int s) { return s == 1 || s == 3; }
+__device__ __forceinline__ bool schema_uses_pos(int s) { return s == 2 || s == 3; }
+
+__device__ __forceinline__ long long term_hits(const uint64_t *chunk_terms, const uint64_t *img_terms,
+                                               int words)
+{
+    long long h = 0;
+    for (int w = 0; w < words; ++w)
+        h += __popcll(img_terms ? (chunk_terms[w] & img_terms[w]) : chunk_terms[w]);
+    return h;
+}
+
+// ---------------------------------------------------------------------------
+// Launchers (each returns the cudaError_t of its launch)
+// ---------------------------------------------------------------------------
+// prep.cu
+cudaError_t launch_prep(Side &side, cudaStream_t st);
+cudaError_t reduce_max_float(const float *x, int64_t n, float *out, cudaStream_t st);
+cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, cudaStream_t st);
+// rescore.cu
+cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
+                           const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
+                           int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
+                           int32_t *error_flag, cudaStream_t st);
+cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
+                              const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
+                              const Outputs &out, int32_t *error_flag, cudaStream_t st);
+cudaError_t launch_alignments(const Side &img, const Side &chk, const PairIndex &px, int schema,
+                              int64_t n_terms, bool raw, double *rec, cudaStream_t st);
+cudaError_t launch_pair_chunk(const PairIndex &px, int64_t N, int64_t col_offset, int64_t *pair_chunk,
+                              cudaStream_t st);
+size_t metrics_scratch_bytes(int S, int n_k);
+cudaError_t launch_reduce_metrics(const int32_t *pair_rank, const double *pair_sim, int S, int64_t P,
+                                  const int32_t *k_list_dev, int n_k, int mrr_cutoff, int64_t *hits,
+                                  double *rr_sum, double *sim_sum, void *scratch, cudaStream_t st);
+cudaError_t launch_merge_topk(const int64_t *in_idx, const double *in_score, int G, int64_t n_lists,
+                              int K, int64_t *out_idx, double *out_score, cudaStream_t st);
+cudaError_t launch_count_beating(const int64_t *deep_idx, const double *deep_score, int64_t N, int S, int K,
+                                 int64_t n_q, const int64_t *q_image, const int64_t *q_chunk,
+                                 const double *q_score, int32_t *counts, cudaStream_t st);
+// fused_tc.cu
+struct FusedPlan {
+    int64_t n_row_blocks;
+    int n_splits;
+    int tiles_per_split;
+    int64_t n_lists;
+    int cap;               // list capacity (entries)
+    int kprime;
+    int grid;
+    size_t smem_bytes;
+    int stages;
+    bool a_resident;
+};
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, FusedPlan *plan);
+cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan, const void *tmap_a,
+                         const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st);
+int encode_tensor_map(void *tmap_out, const void *base, int64_t rows, int D, int box_rows,
+                      char *err, size_t errlen);
+
+} // namespace mma

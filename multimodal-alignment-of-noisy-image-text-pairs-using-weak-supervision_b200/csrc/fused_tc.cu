@@ -1,0 +1,481 @@
+// fused_tc.cu -- K1: the image x chunk similarity contraction on the 5th-gen
+// tensor cores, with a streaming per-row top-K' in the epilogue, so the N x M
+// score matrix never reaches HBM.  (The reference ranks with one SQL statement
+// per image: src/evaluate_alignments.py:126-136.)
+//
+// One persistent CTA per SM, 12 warps, warp-specialised:
+//   warp 0      TMA producer: A row block (128 images x D, bf16, resident in shared
+//               memory for the whole sweep when D <= 512) and B k-slices (256 chunks
+//               x 64) through a ring of mbarrier-guarded stages, SWIZZLE_128B.
+//   warp 1      MMA issuer: tcgen05.mma cta_group::1 kind::f16, M=128 N=256 K=16,
+//               fp32 accumulators in TMEM, double-buffered (2 x 256 columns).
+//   warp 2      TMEM allocator.
+//   warps 4-11  epilogue: tcgen05.ld 32 columns at a time (one thread = one image
+//               row of one accumulator half), compare against the row's running
+//               threshold tau, append survivors to the row's candidate list in
+//               global memory; a full list is compacted by the whole warp to its
+//               best K' entries (ballot / popc / redux selection), which raises tau.
+// A list is complete above its final tau: every column the thread saw with score >
+// tau is in it.  rescore.cu re-scores the lists exactly and certifies each row.
+#include "common.cuh"
+#include <cuda.h>
+#include <math_constants.h>
+#include <stdio.h>
+
+namespace mma {
+
+constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int kFusedThreads = 384;
+constexpr uint32_t kABlockBytes = BM * BK * 2;   // 16 KiB: one 64-wide k block of the A tile
+constexpr uint32_t kBStageBytes = BN * BK * 2;   // 32 KiB
+constexpr int kMaxStages = 8;
+constexpr size_t kSmemLimit = 232448;            // 227 KiB opt-in maximum per CTA
+
+// ---------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 "version 1"):
+// rows are 128 bytes, 8-row swizzle atoms are 1024 bytes apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;            // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=256
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                            ((uint32_t)(BM >> 4) << 24);
+
+struct FusedArgs {
+    int64_t N, M;
+    int num_kb;            // D / 64
+    int64_t n_row_blocks, n_tiles;
+    int n_splits, tiles_per_split;
+    int stages;
+    uint64_t *keys;
+    float *tau;
+    int32_t *count;
+    int kprime;
+    float *dump;           // debug: write raw scores [N][M] instead of lists
+};
+
+// ---------------------------------------------------------------------------
+// Warp-cooperative compaction of full candidate lists (see header comment).
+// ---------------------------------------------------------------------------
+template <int KPL>
+__device__ __noinline__ void compact_lists(uint64_t *my_list, int &n, float &tau, int kprime, bool need)
+{
+    constexpr int CAP = 32 * KPL;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned pending = __ballot_sync(0xFFFFFFFFu, need);
+    while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1;
+        uint64_t *L = reinterpret_cast<uint64_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)my_list, src));
+        const int cnt = __shfl_sync(0xFFFFFFFFu, n, src);
+        __syncwarp();
+        uint64_t k[KPL];
+        uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int idx = q * 32 + lane;
+            k[q] = idx < cnt ? __ldcg(L + idx) : 0ull;
+            if (idx < cnt) {
+                const uint32_t h = (uint32_t)(k[q] >> 32);
+                hmin = min(hmin, h);
+                hmax = max(hmax, h);
+            }
+        }
+        uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, hmin);
+        uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, hmax);
+        // largest t with #{score >= t} >= kprime  (#{score >= lo} = cnt >= kprime)
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+            int c = 0;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) c += (q * 32 + lane < cnt) && ((uint32_t)(k[q] >> 32) >= mid);
+            c = __reduce_add_sync(0xFFFFFFFFu, c);
+            if (c >= kprime) lo = mid; else hi = mid - 1u;
+        }
+        const uint32_t t = lo;
+        int ge = 0;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) ge += (q * 32 + lane < cnt) && ((uint32_t)(k[q] >> 32) >= t);
+        ge = __reduce_add_sync(0xFFFFFFFFu, ge);
+        const bool drop_ties = ge > CAP - 64;  // a wall of equal scores: keep only what is above it
+        int base = 0;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const uint32_t h = (uint32_t)(k[q] >> 32);
+            const bool keep = (q * 32 + lane < cnt) && (drop_ties ? h > t : h >= t);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) L[base + __popc(m & lt_mask)] = k[q];
+            base += __popc(m);
+        }
+        __syncwarp();
+        if (lane == src) { n = base; tau = f32_unordered(t); }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------
+template <int KPL, bool A_RES>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const FusedArgs P)
+{
+    constexpr int CAP = 32 * KPL;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1 KiB alignment
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = P.num_kb;
+    const uint32_t a_bytes = A_RES ? (uint32_t)num_kb * kABlockBytes : 0u;
+    const uint32_t stage_bytes = kBStageBytes + (A_RES ? 0u : kABlockBytes);
+    const uint32_t sA = smem_base;
+    const uint32_t sStage = smem_base + a_bytes;
+    const uint32_t sBar = sStage + (uint32_t)P.stages * stage_bytes;
+    // barriers (8 bytes each): full[stages], empty[stages], tmem_full[2], tmem_empty[2], a_full, a_empty
+    const uint32_t bar_full = sBar, bar_empty = sBar + 8u * kMaxStages;
+    const uint32_t bar_tfull = sBar + 16u * kMaxStages, bar_tempty = bar_tfull + 16u;
+    const uint32_t bar_afull = bar_tempty + 16u, bar_aempty = bar_afull + 8u;
+    const uint32_t tmem_slot = bar_aempty + 8u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 256); }
+        mbar_init(bar_afull, 1);
+        mbar_init(bar_aempty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int64_t n_units = P.n_row_blocks * P.n_splits;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+            int stage = 0;
+            uint32_t phase = 0, uphase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int64_t rb = u % P.n_row_blocks;
+                const int sp = (int)(u / P.n_row_blocks);
+                const int64_t t0 = (int64_t)sp * P.tiles_per_split;
+                const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
+                if (A_RES) {
+                    mbar_wait(bar_aempty, uphase ^ 1u);  // previous unit's MMAs have drained A
+                    mbar_expect_tx(bar_afull, a_bytes);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        tma_load_2d(sA + kb * kABlockBytes, &tmap_a, bar_afull, kb * BK, (int)(rb * BM));
+                    uphase ^= 1u;
+                }
+                for (int64_t t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+                        const uint32_t dst = sStage + stage * stage_bytes;
+                        mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
+                        tma_load_2d(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN));
+                        if (!A_RES)
+                            tma_load_2d(dst + kBStageBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
+                        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, uphase = 0;
+            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int sp = (int)(u / P.n_row_blocks);
+                const int64_t t0 = (int64_t)sp * P.tiles_per_split;
+                const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
+                if (A_RES) { mbar_wait(bar_afull, uphase); uphase ^= 1u; }
+                for (int64_t t = t0; t < t1; ++t) {
+                    mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(bar_full + 8u * stage, phase);
+                        tc_fence_after();
+                        const uint32_t b_addr = sStage + stage * stage_bytes;
+                        const uint32_t a_addr = A_RES ? sA + kb * kABlockBytes : b_addr + kBStageBytes;
+                        const uint64_t adesc = umma_desc_sw128(a_addr);
+                        const uint64_t bdesc = umma_desc_sw128(b_addr);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K=16 step inside the swizzle atom
+                            tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
+                                        (uint32_t)((kb | k) != 0));
+                        tc_commit(bar_empty + 8u * stage);  // frees the stage when these MMAs retire
+                        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(bar_tfull + 8u * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+                if (A_RES) tc_commit(bar_aempty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+        const int half = (warp - 4) >> 2;   // which 128 accumulator columns
+        const int r = quad * 32 + lane;     // image row within the block
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int64_t rb = u % P.n_row_blocks;
+            const int sp = (int)(u / P.n_row_blocks);
+            const int64_t t0 = (int64_t)sp * P.tiles_per_split;
+            const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
+            const int64_t list_id = (((int64_t)sp * P.n_row_blocks + rb) * 2 + half) * 128 + r;
+            uint64_t *list = P.keys + list_id * CAP;
+            float tau = -CUDART_INF_F;
+            int n = 0;
+            const int64_t row = rb * BM + r;
+            for (int64_t t = t0; t < t1; ++t) {
+                mbar_wait(bar_tfull + 8u * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + ch * 32, v);
+                    tmem_ld_wait();
+                    if (ch == 3) {  // this thread's last read of the accumulator: hand it back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(bar_tempty + 8u * acc);
+                    }
+                    const int64_t col0 = t * BN + half * 128 + ch * 32;
+                    if (P.dump) {
+                        if (row < P.N)
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (col0 + k < P.M) P.dump[row * P.M + col0 + k] = __uint_as_float(v[k]);
+                        continue;
+                    }
+                    if (col0 + 32 > P.M) {  // ragged last tile: TMA zero-filled these columns
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            if (col0 + k >= P.M) v[k] = 0xFF800000u;  // -inf
+                    }
+                    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - 32);
+                    float m = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(v[k]));
+                    if (m > tau) {
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const float s = __uint_as_float(v[k]);
+                            if (s > tau) { list[n] = cand_pack(s, (uint32_t)(col0 + k)); ++n; }
+                        }
+                    }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+            if (!P.dump) {
+                P.tau[list_id] = tau;
+                P.count[list_id] = n;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, FusedPlan *plan)
+{
+    if (D % BK != 0 || D < BK || N <= 0 || M <= 0) return -1;
+    FusedPlan p = {};
+    p.n_row_blocks = (N + BM - 1) / BM;
+    const int64_t n_tiles = (M + BN - 1) / BN;
+    // column splits: the fewest that keep the last wave of persistent CTAs >= 95 % full
+    int best = 1;
+    double best_eff = 0.0;
+    for (int s = 1; s <= 64 && s <= n_tiles; ++s) {
+        const int64_t units = p.n_row_blocks * s;
+        const int64_t waves = (units + sm_count - 1) / sm_count;
+        const double eff = (double)units / (double)(waves * sm_count);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+        if (eff >= 0.95) { best = s; break; }
+    }
+    p.n_splits = best;
+    const int64_t tps = (n_tiles + p.n_splits - 1) / p.n_splits;
+    p.n_splits = (int)((n_tiles + tps - 1) / tps);
+    p.tiles_per_split = (int)tps;
+    p.kprime = kprime_req > 0 ? kprime_req : kneed + (kneed * 6 / 10 > 28 ? kneed * 6 / 10 : 28);
+    if (p.kprime < kneed) p.kprime = kneed;
+    if (p.kprime <= 64) p.cap = 128;
+    else if (p.kprime <= 192) p.cap = 256;
+    else if (p.kprime <= 448) p.cap = 512;
+    else return -2;
+    p.n_lists = p.n_row_blocks * p.n_splits * 256;
+    p.a_resident = D <= 512;
+    const size_t a_bytes = p.a_resident ? (size_t)(D / BK) * kABlockBytes : 0;
+    const size_t stage_bytes = kBStageBytes + (p.a_resident ? 0 : kABlockBytes);
+    const size_t fixed = 1024 /*alignment slack*/ + a_bytes + 256 /*barriers*/;
+    int stages = (int)((kSmemLimit - fixed) / stage_bytes);
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return -3;
+    p.stages = stages;
+    p.smem_bytes = fixed + (size_t)stages * stage_bytes;
+    const int64_t units = p.n_row_blocks * p.n_splits;
+    p.grid = (int)(units < sm_count ? units : sm_count);
+    *plan = p;
+    return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int encode_tensor_map(void *tmap_out, const void *base, int64_t rows, int D, int box_rows, char *err,
+                      size_t errlen)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+            snprintf(err, errlen, "cuTensorMapEncodeTiled entry point unavailable");
+            return -1;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(reinterpret_cast<CUtensorMap *>(tmap_out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                          const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(err, errlen, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return -1;
+    }
+    return 0;
+}
+
+template <int KPL, bool A_RES>
+static cudaError_t launch_variant(const CUtensorMap &ta, const CUtensorMap &tb, const FusedArgs &args,
+                                  const FusedPlan &plan, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(fused_score_topk_kernel<KPL, A_RES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    fused_score_topk_kernel<KPL, A_RES><<<plan.grid, kFusedThreads, plan.smem_bytes, st>>>(ta, tb, args);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan, const void *tmap_a,
+                         const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st)
+{
+    FusedArgs a = {};
+    a.N = img.n; a.M = chk.n; a.num_kb = img.D / BK;
+    a.n_row_blocks = plan.n_row_blocks;
+    a.n_tiles = (chk.n + BN - 1) / BN;
+    a.n_splits = plan.n_splits;
+    a.tiles_per_split = plan.tiles_per_split;
+    a.stages = plan.stages;
+    a.keys = lists.keys; a.tau = lists.tau; a.count = lists.count;
+    a.kprime = plan.kprime;
+    a.dump = dump;
+    const CUtensorMap &ta = *reinterpret_cast<const CUtensorMap *>(tmap_a);
+    const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);
+    lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;
+    lists.kprime = plan.kprime;
+#define VARIANT(KPL) (plan.a_resident ? launch_variant<KPL, true>(ta, tb, a, plan, st) \
+                                      : launch_variant<KPL, false>(ta, tb, a, plan, st))
+    switch (plan.cap) {
+    case 128: return VARIANT(4);
+    case 256: return VARIANT(8);
+    case 512: return VARIANT(16);
+    }
+#undef VARIANT
+    return cudaErrorInvalidValue;
+}
+
+} // namespace mma

@@ -1,0 +1,244 @@
+"""AlignmentEngine: thin Python owner of one mmalign context (one per process and GPU).
+
+Arrays may be numpy arrays (host) or torch tensors (host, pinned host or CUDA);
+only their addresses cross the ABI.  Results come back as numpy arrays unless
+`device_outputs=True`, in which case they are CUDA torch tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from ._native import CAND, PATHS, SCHEMA_BITS
+
+SCHEMAS = ["vanilla_clip", "clip_lexical", "clip_positional", "clip_combined"]
+
+
+class MMAlignError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mmalign error {code}: {msg}")
+        self.code = code
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _prep(x, np_dtype, torch_dtype_name):
+    """Returns (keepalive, address) of a contiguous array of the wanted dtype."""
+    if x is None:
+        return None, None
+    if _is_torch(x):
+        import torch
+        td = getattr(torch, torch_dtype_name)
+        if x.dtype != td:
+            if torch_dtype_name == "int64" and x.dtype == torch.uint64:
+                x = x.view(torch.int64)
+            else:
+                x = x.to(td)
+        x = x.contiguous()
+        return x, x.data_ptr()
+    a = np.ascontiguousarray(x, dtype=np_dtype)
+    return a, a.ctypes.data
+
+
+def schema_mask(schemas: Iterable[str] | str | int) -> int:
+    if isinstance(schemas, int):
+        return schemas
+    if isinstance(schemas, str):
+        schemas = [schemas]
+    m = 0
+    for s in schemas:
+        if s not in SCHEMA_BITS:
+            raise ValueError(f"unknown schema {s!r}; expected one of {SCHEMAS}")
+        m |= SCHEMA_BITS[s]
+    return m
+
+
+class AlignmentEngine:
+    def __init__(self, device: int = 0):
+        self._L = _native.load()
+        self._ctx = C.c_void_p()
+        rc = self._L.mmalign_create(C.byref(self._ctx), int(device))
+        if rc != 0:
+            raise MMAlignError(rc, self._L.mmalign_last_error(None).decode())
+        self.device = int(device)
+        self._keep = {}
+        self.N = self.M = self.D = 0
+        self.col_offset = 0
+
+    # -- lifetime ---------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.mmalign_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+            self._keep = {}
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise MMAlignError(rc, self._L.mmalign_last_error(self._ctx).decode())
+
+    # -- corpus -----------------------------------------------------------------
+    def _set(self, which, emb, key, bbox, terms, n_terms=0, col_offset=0):
+        e, pe = _prep(emb, np.float32, "float32")
+        k, pk = _prep(key, np.uint64, "int64")
+        b, pb = _prep(bbox, np.float64, "float64")
+        t, pt = _prep(terms, np.uint64, "int64")
+        n, D = int(e.shape[0]), int(e.shape[1])
+        if k.shape[0] != n:
+            raise ValueError("page_key length differs from the number of embedding rows")
+        W = 0 if t is None else int(t.shape[1])
+        if which == "images":
+            rc = self._L.mmalign_set_images(self._ctx, pe, pk, pb, pt, n, D, W)
+            self.N, self.D = n, D
+        else:
+            rc = self._L.mmalign_set_chunks(self._ctx, pe, pk, pb, pt, n, D, W, int(n_terms), int(col_offset))
+            self.M, self.col_offset = n, int(col_offset)
+        self._keep[which] = (e, k, b, t)  # device inputs are borrowed by the library
+        self._check(rc)
+
+    def set_images(self, emb, page_key, bbox=None, terms=None):
+        self._set("images", emb, page_key, bbox, terms)
+
+    def set_chunks(self, emb, page_key, bbox=None, terms=None, n_terms: int = 0, col_offset: int = 0):
+        self._set("chunks", emb, page_key, bbox, terms, n_terms, col_offset)
+
+    def num_pairs(self) -> int:
+        p = C.c_int64()
+        self._check(self._L.mmalign_num_pairs(self._ctx, C.byref(p)))
+        return p.value
+
+    def pairs(self):
+        """(pair_offsets [N+1], pair_chunk [P]) -- evaluate_alignments.py:48-69 in (image, chunk) order."""
+        P = self.num_pairs()
+        off = np.zeros(self.N + 1, np.int64)
+        pc = np.zeros(max(P, 1), np.int64)
+        self._check(self._L.mmalign_get_pairs(self._ctx, off.ctypes.data, pc.ctypes.data if P else None))
+        return off, pc[:P]
+
+    # -- scoring ----------------------------------------------------------------
+    def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
+            mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
+            path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
+            deep=False, stream=None):
+        mask = schema_mask(schemas)
+        S = bin(mask).count("1")
+        ks = [int(k) for k in k_values]
+        prm = _native.Params()
+        prm.schema_mask = mask
+        prm.candidates = CAND[candidates] if isinstance(candidates, str) else int(candidates)
+        prm.n_k = len(ks)
+        for i, k in enumerate(ks[:8]):
+            prm.k_list[i] = k
+        prm.mrr_cutoff = int(mrr_cutoff)
+        prm.lam_lex, prm.lam_pos = float(weak_weight[0]), float(weak_weight[1])
+        prm.lam_comb = float(weak_weight[0] + weak_weight[1]) if lam_comb is None else float(lam_comb)
+        prm.path = PATHS[path] if isinstance(path, str) else int(path)
+        prm.kprime = int(kprime)
+        kmax = max(ks) if ks else 0
+        kneed = max(kmax, int(mrr_cutoff))
+        P = self.num_pairs()
+        N = self.N
+        res, out = {}, _native.Out()
+        if device_outputs:
+            import torch
+            dev = torch.device("cuda", self.device)
+
+            def alloc(name, shape, dt):
+                t = torch.empty(shape, dtype={"i64": torch.int64, "f64": torch.float64, "i32": torch.int32}[dt], device=dev)
+                res[name] = t
+                return t.data_ptr()
+        else:
+            def alloc(name, shape, dt):
+                a = np.empty(shape, dtype={"i64": np.int64, "f64": np.float64, "i32": np.int32}[dt])
+                res[name] = a
+                return a.ctypes.data
+        if "topk" in want:
+            out.topk_idx = alloc("topk_idx", (S, N, kmax), "i64")
+            out.topk_score = alloc("topk_score", (S, N, kmax), "f64")
+        if "pairs" in want:
+            out.pair_rank = alloc("pair_rank", (S, P), "i32")
+            out.pair_sim = alloc("pair_sim", (P,), "f64")
+        if deep:
+            out.pair_score = alloc("pair_score", (S, P), "f64")
+            out.deep_idx = alloc("deep_idx", (S, N, kneed), "i64")
+            out.deep_score = alloc("deep_score", (S, N, kneed), "f64")
+        hits = np.zeros((S, len(ks)), np.int64)
+        rr = np.zeros(S, np.float64)
+        sim = np.zeros(1, np.float64)
+        npairs = np.zeros(1, np.int64)
+        stats = np.zeros(8, np.int64)
+        if "sums" in want:
+            out.hits, out.rr_sum, out.sim_sum = hits.ctypes.data, rr.ctypes.data, sim.ctypes.data
+        out.num_pairs, out.stats = npairs.ctypes.data, stats.ctypes.data
+        st = None if stream is None else C.c_void_p(int(stream))
+        self._check(self._L.mmalign_run(self._ctx, C.byref(prm), C.byref(out), st))
+        res.update(hits=hits, rr_sum=rr, sim_sum=float(sim[0]), num_pairs=int(npairs[0]),
+                   stats=dict(rows_rescanned=int(stats[0]), candidates_rescored=int(stats[1]),
+                              fused_launches=int(stats[2]), kernel_launches=int(stats[3]),
+                              kprime=int(stats[4])),
+                   schemas=[s for s in SCHEMAS if SCHEMA_BITS[s] & mask], k_values=ks)
+        return res
+
+    def alignments(self, schema: str, raw: bool = False):
+        """Records of the `alignments` table (insert_clip_embeddings.py:369-414): rec [P,3];
+        raw=True gives the un-thresholded (lexical, positional, 0) scores."""
+        P = self.num_pairs()
+        rec = np.zeros((max(P, 1), 3), np.float64)
+        self._check(self._L.mmalign_alignments(self._ctx, SCHEMA_BITS[schema] | (0x100 if raw else 0),
+                                               rec.ctypes.data, None))
+        return rec[:P]
+
+    def debug_scores(self):
+        out = np.zeros((self.N, self.M), np.float32)
+        self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))
+        return out
+
+    # -- multi-GPU helpers (device tensors) ---------------------------------------
+    def merge_topk(self, gathered_idx, gathered_score):
+        """[G, L, K] gathered lists -> merged [L, K] (torch CUDA tensors)."""
+        import torch
+        G, L, K = gathered_idx.shape
+        oi = torch.empty((L, K), dtype=torch.int64, device=gathered_idx.device)
+        os_ = torch.empty((L, K), dtype=torch.float64, device=gathered_idx.device)
+        self._check(self._L.mmalign_merge_topk(self._ctx, gathered_idx.data_ptr(), gathered_score.data_ptr(),
+                                               G, L, K, oi.data_ptr(), os_.data_ptr(), None))
+        return oi, os_
+
+    def count_beating(self, deep_idx, deep_score, q_image, q_chunk, q_score):
+        import torch
+        S, N, K = deep_idx.shape
+        n_q = int(q_image.shape[0])
+        counts = torch.zeros((S, n_q), dtype=torch.int32, device=deep_idx.device)
+        if n_q:
+            self._check(self._L.mmalign_count_beating(self._ctx, deep_idx.data_ptr(), deep_score.data_ptr(), N, S, K,
+                                                      n_q, q_image.data_ptr(), q_chunk.data_ptr(),
+                                                      q_score.data_ptr(), counts.data_ptr(), None))
+        return counts
+
+    def reduce_metrics(self, pair_rank, pair_sim, k_values, mrr_cutoff=100):
+        S, P = pair_rank.shape
+        ks = np.asarray(list(k_values), np.int32)
+        hits = np.zeros((S, len(ks)), np.int64)
+        rr = np.zeros(S, np.float64)
+        sim = np.zeros(1, np.float64)
+        self._check(self._L.mmalign_reduce_metrics(self._ctx, pair_rank.data_ptr(),
+                                                   pair_sim.data_ptr() if pair_sim is not None else None, S, P,
+                                                   ks.ctypes.data, len(ks), int(mrr_cutoff), hits.ctypes.data,
+                                                   rr.ctypes.data, sim.ctypes.data, None))
+        return hits, rr, float(sim[0])
