@@ -30,14 +30,15 @@ struct DevBuf {  // growable device scratch
 
 struct SideStore {
     Side s;
-    std::vector<void *> owned;  // uploads + derived buffers
+    DevBuf up[4];               // uploads of host inputs: emb, key, bbox, terms (reused across set_* calls)
+    DevBuf bf16, norm2, err, errmax;
     float *err_max = nullptr;   // [1] max rounding-error norm over the rows
     alignas(64) CUtensorMap tmap;
     bool ready = false;
     void release()
     {
-        for (void *p : owned) cudaFree(p);
-        owned.clear();
+        for (DevBuf &b : up) b.release();
+        bf16.release(); norm2.release(); err.release(); errmax.release();
         s = Side();
         err_max = nullptr;
         ready = false;
@@ -134,16 +135,14 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
 }
 
 template <typename T>
-static int adopt(mmalign_ctx *c, SideStore &ss, const T *src, size_t count, const T **dst, cudaStream_t st)
+static int adopt(mmalign_ctx *c, DevBuf &buf, const T *src, size_t count, const T **dst, cudaStream_t st)
 {
     *dst = nullptr;
     if (!src || count == 0) return MMALIGN_OK;
     if (is_device_ptr(src)) { *dst = src; return MMALIGN_OK; }  // borrowed
-    void *d = nullptr;
-    CU(c, cudaMalloc(&d, count * sizeof(T)));
-    ss.owned.push_back(d);
-    CU(c, cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
-    *dst = static_cast<const T *>(d);
+    CU(c, buf.reserve(count * sizeof(T)));
+    CU(c, cudaMemcpyAsync(buf.p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    *dst = static_cast<const T *>(buf.p);
     return MMALIGN_OK;
 }
 
@@ -158,29 +157,27 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
     if (term_words < 0 || (terms && term_words == 0)) return fail(c, MMALIGN_EINVAL, "%s: bad term_words", what);
     cudaStream_t st = 0;
     CU(c, cudaStreamSynchronize(st));
-    ss.release();
+    ss.ready = false;
     c->px_ready = false;
+    ss.s = Side();
     Side &s = ss.s;
     s.n = n; s.D = D; s.term_words = term_words;
     int rc;
-    if ((rc = adopt(c, ss, emb, (size_t)n * D, &s.emb, st))) return rc;
-    if ((rc = adopt(c, ss, key, (size_t)n, &s.key, st))) return rc;
-    if ((rc = adopt(c, ss, terms, (size_t)n * term_words, &s.terms, st))) return rc;
+    if ((rc = adopt(c, ss.up[0], emb, (size_t)n * D, &s.emb, st))) return rc;
+    if ((rc = adopt(c, ss.up[1], key, (size_t)n, &s.key, st))) return rc;
+    if ((rc = adopt(c, ss.up[3], terms, (size_t)n * term_words, &s.terms, st))) return rc;
     if (bbox) {
-        if ((rc = adopt(c, ss, bbox, (size_t)n * 4, &s.bbox, st))) return rc;
+        if ((rc = adopt(c, ss.up[2], bbox, (size_t)n * 4, &s.bbox, st))) return rc;
     } else if (n > 0) {  // missing boxes: all zero -> positional score 0 (insert_clip_embeddings.py:161)
-        void *d = nullptr;
-        CU(c, cudaMalloc(&d, (size_t)n * 4 * sizeof(double)));
-        ss.owned.push_back(d);
-        CU(c, cudaMemsetAsync(d, 0, (size_t)n * 4 * sizeof(double), st));
-        s.bbox = static_cast<const double *>(d);
+        CU(c, ss.up[2].reserve((size_t)n * 4 * sizeof(double)));
+        CU(c, cudaMemsetAsync(ss.up[2].p, 0, (size_t)n * 4 * sizeof(double), st));
+        s.bbox = static_cast<const double *>(ss.up[2].p);
     }
     const size_t nn = n > 0 ? (size_t)n : 1;
-    void *p = nullptr;
-    CU(c, cudaMalloc(&p, nn * D * sizeof(__nv_bfloat16))); ss.owned.push_back(p); s.emb_bf16 = (__nv_bfloat16 *)p;
-    CU(c, cudaMalloc(&p, nn * sizeof(float))); ss.owned.push_back(p); s.norm2 = (float *)p;
-    CU(c, cudaMalloc(&p, nn * sizeof(float))); ss.owned.push_back(p); s.err = (float *)p;
-    CU(c, cudaMalloc(&p, sizeof(float))); ss.owned.push_back(p); ss.err_max = (float *)p;
+    CU(c, ss.bf16.reserve(nn * D * sizeof(__nv_bfloat16))); s.emb_bf16 = (__nv_bfloat16 *)ss.bf16.p;
+    CU(c, ss.norm2.reserve(nn * sizeof(float))); s.norm2 = (float *)ss.norm2.p;
+    CU(c, ss.err.reserve(nn * sizeof(float))); s.err = (float *)ss.err.p;
+    CU(c, ss.errmax.reserve(sizeof(float))); ss.err_max = (float *)ss.errmax.p;
     CU(c, launch_prep(s, st));
     CU(c, reduce_max_float(s.err, n, ss.err_max, st));
     if (n > 0 && D % 64 == 0) {

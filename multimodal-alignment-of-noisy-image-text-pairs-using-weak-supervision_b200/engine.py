@@ -131,6 +131,16 @@ class AlignmentEngine:
         self._check(self._L.mmalign_get_pairs(self._ctx, off.ctypes.data, pc.ctypes.data if P else None))
         return off, pc[:P]
 
+    def pairs_device(self):
+        """Same as pairs() but as CUDA tensors (no host copy)."""
+        import torch
+        P = self.num_pairs()
+        dev = torch.device("cuda", self.device)
+        off = torch.empty(self.N + 1, dtype=torch.int64, device=dev)
+        pc = torch.empty(max(P, 1), dtype=torch.int64, device=dev)
+        self._check(self._L.mmalign_get_pairs(self._ctx, off.data_ptr(), pc.data_ptr() if P else None))
+        return off, pc[:P]
+
     # -- scoring ----------------------------------------------------------------
     def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
             mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,

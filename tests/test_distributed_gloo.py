@@ -1,0 +1,137 @@
+"""world_size-2 gloo run of the multi-GPU plumbing (distributed.ShardedScorer) on the CPU.
+
+The CUDA kernels cannot run here, so a stand-in engine answers the four library calls
+(run / merge_topk / count_beating / reduce_metrics) from the CPU oracle; what is under test is
+the host logic: shard ranges, the three exchanges, padding of ragged pair lists, global ranks,
+metric reduction.  The merged result must equal the oracle's single-process result."""
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG_NAME
+
+MASK = 15
+LAM = (0.3, 0.2, 0.5)
+KS = (1, 5, 10, 20)
+CUTOFF = 30
+
+
+class OracleEngine:
+    def __init__(self, oracle, img, chk_shard, T, col_offset):
+        self.o, self.img, self.chk, self.T, self.off0 = oracle, img, chk_shard, T, col_offset
+        self.N = len(img["key"])
+
+    def run(self, schemas, *, want, device_outputs, deep=False, candidates, k_values, mrr_cutoff, weak_weight,
+            kprime, path):
+        kmax, kneed = max(k_values), max(max(k_values), mrr_cutoff)
+        lam = (weak_weight[0], weak_weight[1], weak_weight[0] + weak_weight[1])
+        a = self.o.evaluate(self.img, self.chk, T=self.T, schema_mask=MASK, candidates="all", lam=lam, kmax=kneed, cutoff=kneed)
+        s = self.o.evaluate(self.img, self.chk, T=self.T, schema_mask=MASK, candidates="same_page", lam=lam, kmax=64, cutoff=64)
+        off, pc = a["pair_offsets"], a["pair_chunk"]
+        P = len(pc)
+        score = np.zeros((4, P))
+        for si in range(4):
+            for i in range(self.N):
+                lut = dict(zip(s["topk_idx"][si, i].tolist(), s["topk_score"][si, i].tolist()))
+                for p in range(off[i], off[i + 1]):
+                    score[si, p] = lut[pc[p]]
+        g = lambda x: np.where(x >= 0, x + self.off0, -1)
+        t = torch.from_numpy
+        self._pairs = (t(off), t(pc + self.off0))
+        return dict(topk_idx=t(g(a["topk_idx"][:, :, :kmax]).copy()), topk_score=t(a["topk_score"][:, :, :kmax].copy()),
+                    pair_rank=t(a["pair_rank"]), pair_sim=t(a["pair_sim"]), pair_score=t(score),
+                    deep_idx=t(g(a["topk_idx"])), deep_score=t(a["topk_score"]), stats={})
+
+    def pairs_device(self):
+        return self._pairs
+
+    def merge_topk(self, gi, gs):
+        G, L, K = gi.shape
+        i, s = gi.numpy().transpose(1, 0, 2).reshape(L, G * K), gs.numpy().transpose(1, 0, 2).reshape(L, G * K)
+        oi, os_ = np.full((L, K), -1, np.int64), np.full((L, K), -np.inf)
+        for l in range(L):
+            ok = i[l] >= 0
+            o = np.lexsort((i[l][ok], -s[l][ok]))[:K]
+            oi[l, :len(o)], os_[l, :len(o)] = i[l][ok][o], s[l][ok][o]
+        return torch.from_numpy(oi), torch.from_numpy(os_)
+
+    def count_beating(self, deep_idx, deep_score, q_img, q_chk, q_sc):
+        di, ds = deep_idx.numpy(), deep_score.numpy()
+        S, nq = q_sc.shape
+        out = np.zeros((S, nq), np.int32)
+        for s in range(S):
+            for q in range(nq):
+                i, j, sc = int(q_img[q]), int(q_chk[q]), float(q_sc[s, q])
+                beats = (di[s, i] >= 0) & ((ds[s, i] > sc) | ((ds[s, i] == sc) & (di[s, i] < j)))
+                out[s, q] = int(beats.sum())
+        return torch.from_numpy(out)
+
+    def reduce_metrics(self, pair_rank, pair_sim, k_values, mrr_cutoff):
+        r = pair_rank.numpy()
+        hits = np.array([[np.count_nonzero((r[s] >= 1) & (r[s] <= k)) for k in k_values] for s in range(r.shape[0])], np.int64)
+        rr = np.array([sum(1.0 / x for x in r[s].tolist() if 1 <= x <= mrr_cutoff) for s in range(r.shape[0])])
+        return hits, rr, float(pair_sim.numpy().sum())
+
+
+def worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    synthetic = importlib.import_module(PKG_NAME + ".synthetic")
+    distributed = importlib.import_module(PKG_NAME + ".distributed")
+    img, chk, _ = synthetic.make_numpy(24, 203, 64, T=64, seed=31)
+    lo, hi = distributed.shard_range(203, world, rank)
+    shard = {k: (v[lo:hi] if v is not None else None) for k, v in chk.items()}
+    eng = OracleEngine(oracle, img, shard, 64, lo)
+    sc = distributed.ShardedScorer(eng, world, rank, None, dist=dist)
+    r = sc.run(schemas=None, k_values=KS, mrr_cutoff=CUTOFF, weak_weight=LAM[:2], host_outputs=True)
+    # gather each rank's pair ranks for the global check
+    q.put((rank, lo, r["topk_idx"], r["topk_score"], r["pair_rank"], r["hits"], r["rr_sum"], r["sim_sum"],
+           r["num_pairs"], r["metrics"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_merge_equals_single_process(oracle, synthetic):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=180) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    img, chk, _ = synthetic.make_numpy(24, 203, 64, T=64, seed=31)
+    o = oracle.evaluate(img, chk, T=64, schema_mask=MASK, candidates="all", lam=LAM, kmax=max(KS), cutoff=CUTOFF)
+    for rank, lo, ti, ts, pr, hits, rr, sim, P, metrics in got:
+        assert np.array_equal(ti, o["topk_idx"]) and np.array_equal(ts, o["topk_score"])
+        assert P == len(o["pair_chunk"])
+        for si in range(4):
+            for qi, k in enumerate(KS):
+                assert hits[si, qi] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
+            want_rr = sum(1.0 / x for x in o["pair_rank"][si].tolist() if 1 <= x <= CUTOFF)
+            assert rr[si] == pytest.approx(want_rr, rel=1e-12)
+        assert sim == pytest.approx(float(o["pair_sim"].sum()), rel=1e-12)
+        assert metrics["num_pairs"] == P
+    # each rank's slice of the true pairs carries the GLOBAL rank
+    hi0 = got[1][1]
+    mine0 = o["pair_chunk"] < hi0
+    assert np.array_equal(got[0][4], o["pair_rank"][:, mine0]) and np.array_equal(got[1][4], o["pair_rank"][:, ~mine0])
+
+
+def test_shard_range(pkg):
+    d = importlib.import_module(PKG_NAME + ".distributed")
+    for M in (0, 1, 7, 8, 1000003):
+        for G in (1, 2, 4, 8):
+            r = [d.shard_range(M, G, k) for k in range(G)]
+            assert r[0][0] == 0 and r[-1][1] == M and all(a[1] == b[0] for a, b in zip(r, r[1:]))
