@@ -200,10 +200,19 @@ def run_ours(args):
     sharded = distributed.ShardedScorer(eng, world, rank, dev)
     run_kw = dict(schemas=SCHEMAS, k_values=K_VALUES, mrr_cutoff=MRR_CUTOFF, weak_weight=WEAK, kprime=args.kprime)
 
+    phase_ms = {}
+
     def step(im, ck, host_out):
+        t0 = time.perf_counter()
         eng.set_images(im["emb"], im["key"], im["bbox"], im["terms"])
+        t1 = time.perf_counter()
         eng.set_chunks(ck["emb"], ck["key"], ck["bbox"], ck["terms"], n_terms=T_TERMS, col_offset=r0)
-        return sharded.run(host_outputs=host_out, **run_kw)
+        t2 = time.perf_counter()
+        out = sharded.run(host_outputs=host_out, **run_kw)
+        t3 = time.perf_counter()
+        phase_ms["host" if host_out else "device"] = dict(set_images=1e3 * (t1 - t0), set_chunks=1e3 * (t2 - t1),
+                                                          run=1e3 * (t3 - t2), **{k: v for k, v in out["stats"].items() if k.endswith("_us")})
+        return out
 
     def barrier():
         if world > 1:
@@ -280,7 +289,8 @@ def run_ours(args):
         "e2e": e2e, "gpu_launches": int(np.sum(launches)), "roofline": roof,
         "quality": {"top1_vanilla": m["top_k"][0][0], "top10_vanilla": m["top_k"][0][2], "mrr_vanilla": m["mrr"][0],
                     "mrr_combined": m["mrr"][-1], "num_pairs": m["num_pairs"],
-                    "rows_rescanned": res["stats"]["rows_rescanned"], "kprime": res["stats"]["kprime"]},
+                    "rows_rescanned": res["stats"]["rows_rescanned"], "kprime": res["stats"]["kprime"],
+                    "candidates_rescored_per_row": res["stats"]["candidates_rescored"] / max(N, 1)},
     }
     if world == 1 and not args.no_cpu_baseline:
         to_np = lambda d: {k: (v.cpu().numpy() if v is not None else None) for k, v in d.items()}
@@ -299,6 +309,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{n2} query rows x all {M} chunks in {dt:.1f} s (oracle/numpy_port.py: numpy sgemm "
                                           f"[{numpy_port.blas_info()}] + argpartition/lexsort, same workload)"}
+    print("phase wall times of the last step (ms; *_us from CUDA events):", json.dumps(phase_ms), file=sys.stderr)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

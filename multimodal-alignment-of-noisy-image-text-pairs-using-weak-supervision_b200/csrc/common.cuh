@@ -64,7 +64,7 @@ struct Outputs {           // device pointers (api.cu stages host outputs)
 
 // candidate lists written by the fused kernel (fused_tc.cu), read by rescore.cu
 struct CandLists {
-    uint64_t *keys = nullptr;  // [n_lists][cap]  (ordered fp32 score << 32) | ~column
+    uint64_t *keys = nullptr;  // [n_lists][cap]  lo = column, hi = fp32 score bits
     float *tau = nullptr;      // [n_lists] list is complete above tau
     int32_t *count = nullptr;  // [n_lists]
     int cap = 0;               // entries per list
@@ -90,12 +90,9 @@ __device__ __forceinline__ float f32_unordered(uint32_t k)
     uint32_t u = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
     return __uint_as_float(u);
 }
-__device__ __forceinline__ uint64_t cand_pack(float score, uint32_t col)
-{
-    return ((uint64_t)f32_ordered(score) << 32) | (uint64_t)(0xFFFFFFFFu - col);
-}
-__device__ __forceinline__ float cand_score(uint64_t k) { return f32_unordered((uint32_t)(k >> 32)); }
-__device__ __forceinline__ uint32_t cand_col(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+// candidate-list entry: lo = chunk column, hi = fp32 score bits
+__device__ __forceinline__ float cand_score(uint64_t k) { return __uint_as_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t cand_col(uint64_t k) { return (uint32_t)k; }
 
 // ---------------------------------------------------------------------------
 // Canonical fp32 dot product (bit-identical to oracle/mmalign_oracle.c: orc_dot):
@@ -232,7 +229,8 @@ struct FusedPlan {
     int tiles_per_split;
     int64_t n_lists;
     int cap;               // list capacity (entries)
-    int kprime;
+    int kprime;            // depth the union of a row's lists is complete to
+    int kprime_list;       // entries each list keeps
     int grid;
     size_t smem_bytes;
     int stages;

@@ -48,15 +48,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
+    uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) { }
+}
+// For the single-thread roles: their spin loops would otherwise steal issue slots from the
+// epilogue warps that share their scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1)
 {
@@ -91,7 +100,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *v)
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// The registers of the pending load are in/out operands, so no use of them can be scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t *v)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory operand descriptor (sm_100 "version 1"):
 // rows are 128 bytes, 8-row swizzle atoms are 1024 bytes apart (SBO), LBO unused.
@@ -114,7 +132,7 @@ struct FusedArgs {
     int64_t n_row_blocks, n_tiles;
     int n_splits, tiles_per_split;
     int stages;
-    uint64_t *keys;
+    uint64_t *keys;        // [n_lists][cap] entries: lo = column, hi = fp32 score bits
     float *tau;
     int32_t *count;
     int kprime;
@@ -122,10 +140,16 @@ struct FusedArgs {
 };
 
 // ---------------------------------------------------------------------------
-// Warp-cooperative compaction of full candidate lists (see header comment).
+// Candidate lists.  An entry is 8 bytes: lo = chunk column, hi = fp32 score bits.
+// Thread (row, half) owns list `ubase + off0`; `n` entries are live.
 // ---------------------------------------------------------------------------
+constexpr int kSlack = 8;  // a compaction may keep up to K' + kSlack entries (saves bisection steps)
+
+// Warp-cooperative compaction of the lists of the lanes that ask for it: keeps the best ~K'
+// entries and raises the lane's threshold tau to the smallest kept score.
 template <int KPL>
-__device__ __noinline__ void compact_lists(uint64_t *my_list, int &n, float &tau, int kprime, bool need)
+__device__ __noinline__ void compact_lists(const char *ubase, uint32_t my_off0, int &n, float &tau, int kprime,
+                                           bool need)
 {
     constexpr int CAP = 32 * KPL;
     const int lane = threadIdx.x & 31;
@@ -134,49 +158,90 @@ __device__ __noinline__ void compact_lists(uint64_t *my_list, int &n, float &tau
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        uint64_t *L = reinterpret_cast<uint64_t *>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)my_list, src));
+        const uint32_t off0 = __shfl_sync(0xFFFFFFFFu, my_off0, src);
         const int cnt = __shfl_sync(0xFFFFFFFFu, n, src);
+        uint2 *L = reinterpret_cast<uint2 *>(const_cast<char *>(ubase) + off0);
         __syncwarp();
-        uint64_t k[KPL];
+        uint32_t h[KPL], c[KPL];  // ordered score key, column
         uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
             const int idx = q * 32 + lane;
-            k[q] = idx < cnt ? __ldcg(L + idx) : 0ull;
+            h[q] = 0u; c[q] = 0u;
             if (idx < cnt) {
-                const uint32_t h = (uint32_t)(k[q] >> 32);
-                hmin = min(hmin, h);
-                hmax = max(hmax, h);
+                const uint2 e = __ldcg(L + idx);
+                c[q] = e.x;
+                h[q] = f32_ordered(__uint_as_float(e.y));  // >= 1 for every real score
+                hmin = min(hmin, h[q]);
+                hmax = max(hmax, h[q]);
             }
         }
         uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, hmin);
         uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, hmax);
-        // largest t with #{score >= t} >= kprime  (#{score >= lo} = cnt >= kprime)
-        while (lo < hi) {
+        int c_lo = cnt;  // #{key >= lo}
+        // largest t with #{key >= t} >= kprime, stopping early once the count is within the slack
+        while (lo < hi && c_lo > kprime + kSlack) {
             const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
-            int c = 0;
+            int cc = 0;
 #pragma unroll
-            for (int q = 0; q < KPL; ++q) c += (q * 32 + lane < cnt) && ((uint32_t)(k[q] >> 32) >= mid);
-            c = __reduce_add_sync(0xFFFFFFFFu, c);
-            if (c >= kprime) lo = mid; else hi = mid - 1u;
+            for (int q = 0; q < KPL; ++q) cc += (h[q] >= mid);
+            cc = __reduce_add_sync(0xFFFFFFFFu, cc);
+            if (cc >= kprime) { lo = mid; c_lo = cc; } else hi = mid - 1u;
         }
         const uint32_t t = lo;
-        int ge = 0;
-#pragma unroll
-        for (int q = 0; q < KPL; ++q) ge += (q * 32 + lane < cnt) && ((uint32_t)(k[q] >> 32) >= t);
-        ge = __reduce_add_sync(0xFFFFFFFFu, ge);
-        const bool drop_ties = ge > CAP - 64;  // a wall of equal scores: keep only what is above it
+        const bool drop_ties = c_lo > CAP - 64;  // a wall of equal scores: keep only what is above it
         int base = 0;
 #pragma unroll
         for (int q = 0; q < KPL; ++q) {
-            const uint32_t h = (uint32_t)(k[q] >> 32);
-            const bool keep = (q * 32 + lane < cnt) && (drop_ties ? h > t : h >= t);
+            const bool keep = drop_ties ? h[q] > t : h[q] >= t;
             const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-            if (keep) L[base + __popc(m & lt_mask)] = k[q];
+            if (keep) L[base + __popc(m & lt_mask)] = make_uint2(c[q], __float_as_uint(f32_unordered(h[q])));
             base += __popc(m);
         }
         __syncwarp();
-        if (lane == src) { n = base; tau = f32_unordered(t); }
+        if (lane == src) { n = base; tau = fmaxf(tau, f32_unordered(t)); }
+    }
+}
+
+__device__ __forceinline__ float max8(const uint32_t *v)
+{
+    const float a = fmaxf(fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1])), __uint_as_float(v[2]));
+    const float b = fmaxf(fmaxf(__uint_as_float(v[3]), __uint_as_float(v[4])), __uint_as_float(v[5]));
+    return fmaxf(fmaxf(a, b), fmaxf(__uint_as_float(v[6]), __uint_as_float(v[7])));
+}
+
+// One 32-column chunk of one accumulator row: append every score above tau to the row's list.
+template <int KPL>
+__device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t M, const char *ubase,
+                                              uint32_t off0, int &n, float &tau, int kprime)
+{
+    constexpr int CAP = 32 * KPL;
+    if (col0 + 32 > M) {  // ragged last tile: TMA zero-filled these columns
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+            if (col0 + k >= M) v[k] = 0xFF800000u;  // -inf
+    }
+    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) compact_lists<KPL>(ubase, off0, n, tau, kprime, n > CAP - 32);
+    float g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] = max8(v + 8 * q);
+    const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+    if (__any_sync(0xFFFFFFFFu, m > tau)) {
+        uint32_t woff = off0 + 8u * (uint32_t)n;
+        const uint32_t c0 = (uint32_t)col0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (__any_sync(0xFFFFFFFFu, g[q] > tau)) {
+#pragma unroll
+                for (int k = 8 * q; k < 8 * q + 8; ++k) {
+                    if (__uint_as_float(v[k]) > tau) {
+                        *reinterpret_cast<uint2 *>(const_cast<char *>(ubase) + woff) = make_uint2(c0 + k, v[k]);
+                        woff += 8u;
+                    }
+                }
+            }
+        }
+        n = (int)((woff - off0) >> 3);
     }
 }
 
@@ -236,7 +301,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const int64_t t0 = (int64_t)sp * P.tiles_per_split;
                 const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
                 if (A_RES) {
-                    mbar_wait(bar_aempty, uphase ^ 1u);  // previous unit's MMAs have drained A
+                    mbar_wait_relaxed(bar_aempty, uphase ^ 1u);  // previous unit's MMAs have drained A
                     mbar_expect_tx(bar_afull, a_bytes);
                     for (int kb = 0; kb < num_kb; ++kb)
                         tma_load_2d(sA + kb * kABlockBytes, &tmap_a, bar_afull, kb * BK, (int)(rb * BM));
@@ -244,7 +309,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 }
                 for (int64_t t = t0; t < t1; ++t) {
                     for (int kb = 0; kb < num_kb; ++kb) {
-                        mbar_wait(bar_empty + 8u * stage, phase ^ 1u);
+                        mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1u);
                         const uint32_t dst = sStage + stage * stage_bytes;
                         mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
                         tma_load_2d(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN));
@@ -266,7 +331,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
                 if (A_RES) { mbar_wait(bar_afull, uphase); uphase ^= 1u; }
                 for (int64_t t = t0; t < t1; ++t) {
-                    mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
+                    mbar_wait_relaxed(bar_tempty + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
                     for (int kb = 0; kb < num_kb; ++kb) {
@@ -302,7 +367,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             const int64_t t0 = (int64_t)sp * P.tiles_per_split;
             const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
             const int64_t list_id = (((int64_t)sp * P.n_row_blocks + rb) * 2 + half) * 128 + r;
-            uint64_t *list = P.keys + list_id * CAP;
+            // uniform base of this unit's 256 lists + a 32-bit per-thread offset
+            const char *ubase = reinterpret_cast<const char *>(P.keys + (list_id - (half * 128 + r)) * CAP);
+            const uint32_t off0 = (uint32_t)(half * 128 + r) * (uint32_t)(CAP * 8);
             float tau = -CUDART_INF_F;
             int n = 0;
             const int64_t row = rb * BM + r;
@@ -310,42 +377,49 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 mbar_wait(bar_tfull + 8u * acc, acc_phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+                const int64_t col0 = t * BN + half * 128;
+                if (P.dump) {
 #pragma unroll 1
-                for (int ch = 0; ch < 4; ++ch) {
-                    uint32_t v[32];
-                    __syncwarp();  // tcgen05.ld / ballots below are warp-aligned: reconverge after the append branch
-                    tmem_ld32(taddr + ch * 32, v);
-                    tmem_ld_wait();
-                    if (ch == 3) {  // this thread's last read of the accumulator: hand it back to the MMA warp
-                        tc_fence_before();
-                        mbar_arrive(bar_tempty + 8u * acc);
-                    }
-                    const int64_t col0 = t * BN + half * 128 + ch * 32;
-                    if (P.dump) {
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t v[32];
+                        __syncwarp();
+                        tmem_ld32(taddr + ch * 32, v);
+                        tmem_ld_wait(v);
                         if (row < P.N)
 #pragma unroll
                             for (int k = 0; k < 32; ++k)
-                                if (col0 + k < P.M) P.dump[row * P.M + col0 + k] = __uint_as_float(v[k]);
-                        continue;
+                                if (col0 + ch * 32 + k < P.M) P.dump[row * P.M + col0 + ch * 32 + k] = __uint_as_float(v[k]);
                     }
-                    if (col0 + 32 > P.M) {  // ragged last tile: TMA zero-filled these columns
-#pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            if (col0 + k >= P.M) v[k] = 0xFF800000u;  // -inf
-                    }
-                    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - 32);
-                    float m = __uint_as_float(v[0]);
-#pragma unroll
-                    for (int k = 1; k < 32; ++k) m = fmaxf(m, __uint_as_float(v[k]));
-                    if (m > tau) {
-#pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const float s = __uint_as_float(v[k]);
-                            if (s > tau) { list[n] = cand_pack(s, (uint32_t)(col0 + k)); ++n; }
-                        }
-                    }
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + 8u * acc);
+                } else {
+                    // ping-pong: the load of chunk c+1 is in flight while chunk c is filtered
+                    uint32_t va[32], vb[32];
+                    __syncwarp();
+                    tmem_ld32(taddr, va);
+                    tmem_ld_wait(va);
+                    tmem_ld32(taddr + 32, vb);
+                    process_chunk<KPL>(va, col0, P.M, ubase, off0, n, tau, P.kprime);
+                    __syncwarp();
+                    tmem_ld_wait(vb);
+                    tmem_ld32(taddr + 64, va);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, ubase, off0, n, tau, P.kprime);
+                    __syncwarp();
+                    tmem_ld_wait(va);
+                    tmem_ld32(taddr + 96, vb);
+                    process_chunk<KPL>(va, col0 + 64, P.M, ubase, off0, n, tau, P.kprime);
+                    __syncwarp();
+                    tmem_ld_wait(vb);
+                    tc_fence_before();  // last read of this accumulator: hand it back to the MMA warp
+                    mbar_arrive(bar_tempty + 8u * acc);
+                    process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+            if (!P.dump) {  // leave at most K' + slack entries per list for the rescoring kernel
+                __syncwarp();
+                if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
+                    compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > P.kprime + kSlack);
             }
             if (!P.dump) {
                 P.tau[list_id] = tau;
@@ -384,11 +458,21 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     const int64_t tps = (n_tiles + p.n_splits - 1) / p.n_splits;
     p.n_splits = (int)((n_tiles + tps - 1) / tps);
     p.tiles_per_split = (int)tps;
-    p.kprime = kprime_req > 0 ? kprime_req : kneed + (kneed * 6 / 10 > 28 ? kneed * 6 / 10 : 28);
+    // Depth to which the UNION of a row's lists must be complete.  The certificate of rescore.cu needs
+    // (exact kneed-th score) - (approximate K'-th score) > eps ~ 0.004 (bf16 rounding bound); for
+    // near-isotropic embeddings at D >= 512 that takes K' ~ 1.9 x kneed (tools/gap_diag.py).
+    p.kprime = kprime_req > 0 ? kprime_req : (kneed * 48 / 25 > kneed + 50 ? kneed * 48 / 25 : kneed + 50);
     if (p.kprime < kneed) p.kprime = kneed;
-    if (p.kprime <= 64) p.cap = 128;
-    else if (p.kprime <= 192) p.cap = 256;
-    else if (p.kprime <= 448) p.cap = 512;
+    // A row has 2 * n_splits lists over disjoint columns; the union of their best k entries is complete to
+    // a depth of about n_lists * k, so each list keeps its share plus 15 % for imbalance.
+    const int lists_per_row = 2 * p.n_splits;
+    p.kprime_list = (p.kprime * 115 / 100 + lists_per_row - 1) / lists_per_row + 4;
+    if (p.kprime_list > p.kprime) p.kprime_list = p.kprime;
+    if (p.kprime_list < 16) p.kprime_list = 16;
+    const int need = p.kprime_list + p.kprime_list / 2 + 40;  // kept + refill room + one chunk + slack
+    if (need <= 128) p.cap = 128;
+    else if (need <= 256) p.cap = 256;
+    else if (need <= 512) p.cap = 512;
     else return -2;
     p.n_lists = p.n_row_blocks * p.n_splits * 256;
     p.a_resident = D <= 512;
@@ -462,7 +546,7 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     a.tiles_per_split = plan.tiles_per_split;
     a.stages = plan.stages;
     a.keys = lists.keys; a.tau = lists.tau; a.count = lists.count;
-    a.kprime = plan.kprime;
+    a.kprime = plan.kprime_list;
     a.dump = dump;
     const CUtensorMap &ta = *reinterpret_cast<const CUtensorMap *>(tmap_a);
     const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);

@@ -222,8 +222,13 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
         stage_row(A, sm, i);
         __syncthreads();
         bool overflow = c > kSpCap;
-        float eps = 0.f;
-        if (use_lists && !overflow) {
+        bool ok = !overflow;
+        if (!use_lists) {
+            if (ok) {
+                if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)c);
+                finish_row(A, sm, i, 0, false, 0.f, 0.f);
+            }
+        } else if (ok) {
             // lists of this row: one per (column split, accumulator half)
             const int64_t rb = i >> 7;
             const int r = (int)(i & 127);
@@ -238,30 +243,55 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 if (threadIdx.x == 0) s_tau = t;
             }
             __syncthreads();
-            const float tau = s_tau;
+            const float tau_union = s_tau;  // the union of the lists is complete above this
             const uint64_t ik = A.img_key[i];
-            for (int l = 0; l < n_l; ++l) {
-                const int64_t id = (((int64_t)(l >> 1) * L.n_row_blocks + rb) * 2 + (l & 1)) * 128 + r;
-                const int cnt = L.count[id];
-                const uint64_t *keys = L.keys + id * L.cap;
-                for (int e = threadIdx.x; e < cnt; e += kThreads) {
-                    const uint64_t k = keys[e];
-                    const uint32_t col = cand_col(k);
-                    if (cand_score(k) > tau && (ik == MMALIGN_NULL_KEY || A.chk_key[col] != ik)) {
-                        const int pos = atomicAdd(&s_nca, 1);
-                        if (pos < kEntCap) sm.cols[pos] = (int32_t)col;
+            const float eps = A.img_err[i] * 1.001f + eps_chunk_max[0] * 1.001f + (float)A.D * 2.4e-7f + 2e-6f;
+            // attempt 0: the best K' of the union by approximate score; attempt 1: the whole union
+            for (int attempt = 0; attempt < 2; ++attempt) {
+                if (threadIdx.x == 0) { s_nca = 0; s_tau = tau_union; }
+                __syncthreads();
+                for (int l = 0; l < n_l; ++l) {
+                    const int64_t id = (((int64_t)(l >> 1) * L.n_row_blocks + rb) * 2 + (l & 1)) * 128 + r;
+                    const int cnt = L.count[id];
+                    const uint64_t *keys = L.keys + id * L.cap;
+                    for (int e = threadIdx.x; e < cnt; e += kThreads) {
+                        const uint64_t k = keys[e];
+                        const uint32_t col = cand_col(k);
+                        const float sa = cand_score(k);
+                        if (sa > tau_union && (ik == MMALIGN_NULL_KEY || A.chk_key[col] != ik)) {
+                            const int pos = atomicAdd(&s_nca, 1);
+                            if (pos < kEntCap) { SortEnt x; x.s = (double)sa; x.j = (int32_t)col; x.e = 0; sm.buf[pos] = x; }
+                        }
                     }
                 }
+                __syncthreads();
+                const int n_all = s_nca;
+                if (n_all + c > kEntCap) { ok = false; break; }
+                const bool truncate = attempt == 0 && n_all > L.kprime;
+                if (truncate) {
+                    const int n2 = next_pow2(n_all);
+                    for (int e = n_all + threadIdx.x; e < n2; e += kThreads) {
+                        SortEnt x; x.s = -CUDART_INF; x.j = 0x7FFFFFFF; x.e = -1;
+                        sm.buf[e] = x;
+                    }
+                    __syncthreads();
+                    block_bitonic(sm.buf, n2);
+                    // the union stays complete above the last kept approximate score
+                    if (threadIdx.x == 0) { s_nca = L.kprime; s_tau = (float)sm.buf[L.kprime - 1].s; }
+                    __syncthreads();
+                }
+                const int n_ca = s_nca;
+                for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[e] = sm.buf[e].j;
+                __syncthreads();
+                if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)(n_ca + c));
+                ok = finish_row(A, sm, i, n_ca, true, s_tau, eps);
+                if (ok || !truncate) break;
+                // not certified at depth K': clear this row's ranks and retry with everything the lists hold
+                if (A.out.pair_rank)
+                    for (int t = threadIdx.x; t < c * A.rp.S; t += kThreads)
+                        A.out.pair_rank[(int64_t)(t / c) * A.P + A.offsets[i] + (t % c)] = 0;
+                __syncthreads();
             }
-            __syncthreads();
-            overflow = s_nca + c > kEntCap;
-            eps = A.img_err[i] * 1.001f + eps_chunk_max[0] * 1.001f + (float)A.D * 2.4e-7f + 2e-6f;
-        }
-        bool ok = !overflow;
-        if (ok) {
-            const int n_ca = use_lists ? s_nca : 0;
-            if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)(n_ca + c));
-            ok = finish_row(A, sm, i, n_ca, use_lists, s_tau, eps);
         }
         if (!ok && threadIdx.x == 0) {
             if (use_lists) fail_rows[atomicAdd(fail_count, 1)] = (int32_t)i;
