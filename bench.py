@@ -66,41 +66,50 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, sampled every 200 ms through NVML in this
+    process (an `nvidia-smi -lms` poller was measured to stall the driver for tens of ms per query)."""
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self._stop, self.thread, self.err = index, [], threading.Event(), None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
 
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        busy = [s for s in sm if s >= 0.5 * max(sm)] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        def loop():
+            R = pynvml
+            names = {"hw_slowdown": R.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": R.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": R.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": R.nvmlClocksEventReasonSwPowerCap}
+            while not self._stop.is_set():
+                try:
+                    sm = R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM)
+                    mask = R.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    pw = R.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    self.samples.append((time.time(), sm, pw, [n for n, b in names.items() if mask & b]))
+                except Exception as e:  # noqa: BLE001
+                    self.err = repr(e)
+                self._stop.wait(0.2)
+        self.thread = threading.Thread(target=loop, daemon=True)
+        self.thread.start()
+
+    def stop(self, t_begin=0.0, t_end=1e30):
+        """Summary of the samples taken in [t_begin, t_end] (the timed region)."""
+        self._stop.set()
+        if self.thread:
+            self.thread.join(1.0)
+        win = [x for x in self.samples if t_begin <= x[0] <= t_end + 0.2]
+        if not win:
+            return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": ["no samples: " + str(self.err)]}
+        sm = [x[1] for x in win]
+        reasons = sorted({r for x in win for r in x[3]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.max_sm), "reasons": reasons,
+                "power_w_max": max(x[2] for x in win), "samples": len(win), "source": "NVML, 200 ms period"}
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -234,11 +243,11 @@ def run_ours(args):
         return float(ms.item()), out
 
     # ---- device-resident arm
-    for _ in range(args.warmup):
-        res = step(img, chk, False)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # started before the warm-up so that its start-up cost is not in the timed region
+    for _ in range(args.warmup):
+        res = step(img, chk, False)
     fused_us, resc_us, scan_us, launches = [], [], [], []
 
     def dev_step():
@@ -246,8 +255,9 @@ def run_ours(args):
         fused_us.append(r["stats"]["fused_us"]); resc_us.append(r["stats"]["rescore_us"])
         scan_us.append(r["stats"]["exact_scan_us"]); launches.append(r["stats"]["kernel_launches"] + 6)
         return r
+    t_begin = time.time()
     ms, res = timed(dev_step, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
     ms_per_step = ms / args.steps
     value = N / (ms_per_step / 1000.0)
 

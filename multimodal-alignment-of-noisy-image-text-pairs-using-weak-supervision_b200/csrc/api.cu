@@ -7,10 +7,27 @@
 #include <stdio.h>
 #include <string.h>
 #include <vector>
+#include <chrono>
+#include <stdlib.h>
 
 using namespace mma;
 
 static thread_local char g_err[512] = "";
+
+// MMALIGN_TRACE=1: host wall-clock of the phases of a call, to stderr
+struct Trace {
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    const char *what;
+    explicit Trace(const char *w) : on(getenv("MMALIGN_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    void mark(const char *phase)
+    {
+        if (!on) return;
+        auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mmalign %s] %-22s %9.3f ms\n", what, phase, std::chrono::duration<double, std::milli>(t - t0).count());
+        t0 = t;
+    }
+};
 
 struct DevBuf {  // growable device scratch
     void *p = nullptr;
@@ -156,6 +173,7 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
     if (n > 0 && (!emb || !key)) return fail(c, MMALIGN_EINVAL, "%s: emb and page_key are required", what);
     if (term_words < 0 || (terms && term_words == 0)) return fail(c, MMALIGN_EINVAL, "%s: bad term_words", what);
     cudaStream_t st = 0;
+    Trace tr(what);
     CU(c, cudaStreamSynchronize(st));
     ss.ready = false;
     c->px_ready = false;
@@ -186,6 +204,7 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
             return fail(c, MMALIGN_ECUDA, "%s: %s", what, msg);
     }
     CU(c, cudaStreamSynchronize(st));
+    tr.mark("upload + prep");
     ss.ready = true;
     return MMALIGN_OK;
 }
@@ -308,8 +327,10 @@ static int schema_index(uint32_t bit)
 extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream)
 {
     if (!c || !prm || !uo) return fail(c, MMALIGN_EINVAL, "mmalign_run: NULL argument");
+    Trace tr("run");
     int rc = ensure_index(c);
     if (rc) return rc;
+    tr.mark("pair index");
     cudaStream_t st = (cudaStream_t)stream;
     const Side &img = c->img.s, &chk = c->chk.s;
     const int64_t N = img.n, M = chk.n, P = c->px.P;
@@ -367,6 +388,7 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
         if (!out.pair_rank) out.pair_rank = (int32_t *)extra.p;
         if (!out.pair_sim) out.pair_sim = (double *)((char *)extra.p + ((SP * sizeof(int32_t) + 255) & ~(size_t)255));
     }
+    tr.mark("params + staging");
     // ---- small device state
     int32_t *fail_count = (int32_t *)c->small.p;
     unsigned long long *cand_counter = (unsigned long long *)((char *)c->small.p + 8);
@@ -411,6 +433,7 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
             kprime_used = plan.kprime;
         }
     }
+    tr.mark("launch scoring");
     // ---- metric sums
     if (want_sums) {
         CU(c, c->metrics_scratch.reserve(metrics_scratch_bytes(rp.S, rp.n_k)));
@@ -423,6 +446,7 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     struct { int32_t fail; int32_t pad; unsigned long long cand; int32_t err; } h = {};
     CU(c, cudaMemcpyAsync(&h, c->small.p, 24, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
+    tr.mark("kernels done");
     if (h.err) { extra.release(); return fail(c, MMALIGN_ELIMIT, "an image has more than 512 same-page chunks (capacity limit of this build)"); }
     if (prm->path == MMALIGN_PATH_FUSED && h.fail > 0) {
         extra.release();
@@ -443,6 +467,7 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     if ((rc = sg.copy_back())) { extra.release(); return rc; }
     CU(c, cudaStreamSynchronize(st));
     extra.release();
+    tr.mark("copy back");
     return MMALIGN_OK;
 }
 

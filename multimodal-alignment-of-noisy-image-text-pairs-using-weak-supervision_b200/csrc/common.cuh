@@ -36,6 +36,7 @@ struct PairIndex {            // CSR of same-page chunks per image (evaluate_ali
     int64_t *offsets = nullptr;      // [N+1] pair offsets, pairs ordered (image, chunk)
     int32_t *sorted_chunk = nullptr; // [M] local chunk indices sorted by (page key, index)
     int64_t *sp_start = nullptr;     // [N] first position in sorted_chunk of the image's page
+    int64_t c_max = 0;               // largest number of same-page chunks of any image
 };
 
 struct RunParams {
@@ -70,7 +71,8 @@ struct CandLists {
     int cap = 0;               // entries per list
     int n_splits = 0;          // column splits per row block
     int64_t n_row_blocks = 0;
-    int kprime = 0;
+    int kprime = 0;            // depth the union of a row's lists is complete to
+    int kprime_list = 0;       // entries each list keeps
 };
 
 // ---------------------------------------------------------------------------
@@ -103,18 +105,56 @@ __device__ __forceinline__ float warp_dot(const float4 *__restrict__ a, const fl
                                           int d4, int lane)
 {
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
-    for (int c = lane; c < d4; c += 32) {
-        const float4 x = a[c];
-        const float4 y = __ldg(b + c);
-        c0 = fmaf(x.x, y.x, c0);
-        c1 = fmaf(x.y, y.y, c1);
-        c2 = fmaf(x.z, y.z, c2);
-        c3 = fmaf(x.w, y.w, c3);
+    // four 512-byte warp loads in flight per step; the fmaf chains still run in increasing k
+    for (int c = lane; c < d4; c += 128) {
+        float4 y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + 32 * u < d4) y[u] = __ldg(b + c + 32 * u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + 32 * u < d4) {
+                const float4 x = a[c + 32 * u];
+                c0 = fmaf(x.x, y[u].x, c0);
+                c1 = fmaf(x.y, y[u].y, c1);
+                c2 = fmaf(x.z, y[u].z, c2);
+                c3 = fmaf(x.w, y[u].w, c3);
+            }
     }
     float s = (c0 + c1) + (c2 + c3);
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(0xFFFFFFFFu, s, off);
     return s;
+}
+
+// Two independent canonical dot products with the loads of both in flight together (rescoring kernel:
+// the gathers are latency-bound).  Each result is bit-identical to warp_dot().
+__device__ __forceinline__ void warp_dot2(const float4 *__restrict__ a, const float4 *__restrict__ b0,
+                                          const float4 *__restrict__ b1, int d4, int lane, float &r0, float &r1)
+{
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    for (int c = lane; c < d4; c += 128) {
+        float4 y[4], z[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + 32 * u < d4) { y[u] = __ldg(b0 + c + 32 * u); z[u] = __ldg(b1 + c + 32 * u); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + 32 * u < d4) {
+                const float4 x = a[c + 32 * u];
+                p0 = fmaf(x.x, y[u].x, p0); p1 = fmaf(x.y, y[u].y, p1);
+                p2 = fmaf(x.z, y[u].z, p2); p3 = fmaf(x.w, y[u].w, p3);
+                q0 = fmaf(x.x, z[u].x, q0); q1 = fmaf(x.y, z[u].y, q1);
+                q2 = fmaf(x.z, z[u].z, q2); q3 = fmaf(x.w, z[u].w, q3);
+            }
+    }
+    float s = (p0 + p1) + (p2 + p3), t = (q0 + q1) + (q2 + q3);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        s = s + __shfl_xor_sync(0xFFFFFFFFu, s, off);
+        t = t + __shfl_xor_sync(0xFFFFFFFFu, t, off);
+    }
+    r0 = s; r1 = t;
 }
 
 // pgvector cosine as SQL sees it, 1 - (a <=> b): evaluate_alignments.py:97, :128

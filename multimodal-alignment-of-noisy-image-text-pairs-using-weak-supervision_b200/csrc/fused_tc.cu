@@ -552,6 +552,7 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;
     lists.kprime = plan.kprime;
+    lists.kprime_list = plan.kprime_list;
 #define VARIANT(KPL) (plan.a_resident ? launch_variant<KPL, true>(ta, tb, a, plan, st) \
                                       : launch_variant<KPL, false>(ta, tb, a, plan, st))
     switch (plan.cap) {

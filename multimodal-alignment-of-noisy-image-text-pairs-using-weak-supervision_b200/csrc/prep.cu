@@ -98,7 +98,8 @@ __global__ void iota_kernel(int32_t *v, int64_t n)
 
 __global__ void page_range_kernel(const uint64_t *__restrict__ img_key, int64_t N,
                                   const uint64_t *__restrict__ sorted_key, int64_t M,
-                                  int64_t *__restrict__ sp_start, int64_t *__restrict__ counts)
+                                  int64_t *__restrict__ sp_start, int64_t *__restrict__ counts,
+                                  unsigned long long *__restrict__ c_max)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i <= N;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -116,7 +117,9 @@ __global__ void page_range_kernel(const uint64_t *__restrict__ img_key, int64_t 
             if (sorted_key[mid] <= k) lo = mid + 1; else hi = mid;
         }
         sp_start[i] = first;
-        counts[i] = (k == MMALIGN_NULL_KEY) ? 0 : lo - first;  // SQL NULL never joins
+        const int64_t cnt = (k == MMALIGN_NULL_KEY) ? 0 : lo - first;  // SQL NULL never joins
+        counts[i] = cnt;
+        if (cnt > 0) atomicMax(c_max, (unsigned long long)cnt);
     }
 }
 
@@ -133,7 +136,8 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, cu
 #define CK(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
     CK(cudaMalloc(&sorted_key, sizeof(uint64_t) * Mx));
     CK(cudaMalloc(&iota, sizeof(int32_t) * Mx));
-    CK(cudaMalloc(&counts, sizeof(int64_t) * (N + 1)));
+    CK(cudaMalloc(&counts, sizeof(int64_t) * (N + 2)));
+    CK(cudaMemsetAsync(counts + N + 1, 0, sizeof(int64_t), st));
     if (M > 0) {
         iota_kernel<<<(unsigned)((M + 255) / 256 > 1184 ? 1184 : (M + 255) / 256), 256, 0, st>>>(iota, M);
         CK(cudaGetLastError());
@@ -147,10 +151,11 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, cu
         CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, chk.key, sorted_key, iota, px.sorted_chunk,
                                            (int)M, 0, 64, st));
     page_range_kernel<<<(unsigned)((N + 256) / 256 > 1184 ? 1184 : (N + 256) / 256), 256, 0, st>>>(
-        img.key, N, sorted_key, M, px.sp_start, counts);
+        img.key, N, sorted_key, M, px.sp_start, counts, reinterpret_cast<unsigned long long *>(counts + N + 1));
     CK(cudaGetLastError());
     CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, px.offsets, (int)(N + 1), st));
     CK(cudaMemcpyAsync(&px.P, px.offsets + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&px.c_max, counts + N + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
 done:
 #undef CK

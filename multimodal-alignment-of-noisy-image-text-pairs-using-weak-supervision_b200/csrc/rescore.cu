@@ -23,49 +23,57 @@ namespace mma {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kEntCap = 1024;  // candidates + same-page entries handled per row
-constexpr int kSpCap = 512;    // same-page chunks per image
+constexpr int kEntCapMax = 1024;  // candidates + same-page entries handled per row (shared-memory sized per launch)
+constexpr int kSpCapMax = 512;    // same-page chunks per image
 constexpr int kScanRound = kWarps * 16;
 
-struct SortEnt {
-    double s;
+// Sort key: score as an order-preserving 64-bit integer, then the chunk index (lower wins).
+struct Key {
+    unsigned long long k;
     int32_t j;  // local chunk index
     int32_t e;  // entry slot
 };
 
-__device__ __forceinline__ bool ent_before(const SortEnt &a, const SortEnt &b)
+__device__ __forceinline__ unsigned long long ord64(double s)
 {
-    return a.s > b.s || (a.s == b.s && a.j < b.j);  // ORDER BY similarity DESC, lower index first
+    const long long u = __double_as_longlong(s);
+    return u < 0 ? ~(unsigned long long)u : ((unsigned long long)u | 0x8000000000000000ull);
 }
+__device__ __forceinline__ bool key_before(unsigned long long ka, int ja, unsigned long long kb, int jb)
+{
+    return ka > kb || (ka == kb && ja < jb);  // ORDER BY similarity DESC, lower index first
+}
+__device__ __forceinline__ Key key_pad() { Key x; x.k = 0ull; x.j = 0x7FFFFFFF; x.e = -1; return x; }
 
 struct RowSmem {
-    float *a;        // [D]
-    int32_t *cols;   // [kEntCap]
-    double *cosv;    // [kEntCap]
-    double *weak;    // [S][kSpCap]
-    SortEnt *buf;    // [kEntCap]
+    Key *buf;                   // [A.ent_cap]
+    double *cosv;               // [A.ent_cap] exact cosine of every entry
+    double *sp_s;               // [A.sp_cap] ranking score of the same-page entries in the current schema
+    unsigned long long *sp_k;   // [A.sp_cap] its order-preserving key
+    int32_t *cols;              // [A.ent_cap]
+    float *a;                   // [D]
 };
 
-__host__ __device__ inline size_t row_smem_bytes(int D)
+__host__ __device__ inline size_t row_smem_bytes(int D, int ent_cap, int sp_cap)
 {
-    return (size_t)kEntCap * sizeof(SortEnt) + (size_t)kEntCap * sizeof(double) +
-           (size_t)kMaxSchemas * kSpCap * sizeof(double) + (size_t)kEntCap * sizeof(int32_t) +
-           (size_t)D * sizeof(float);
+    return (size_t)ent_cap * (sizeof(Key) + sizeof(double) + sizeof(int32_t)) +
+           (size_t)sp_cap * (sizeof(double) + sizeof(unsigned long long)) + (size_t)D * sizeof(float);
 }
 
-__device__ __forceinline__ RowSmem carve(unsigned char *base, int D)
+__device__ __forceinline__ RowSmem carve(unsigned char *base, int ent_cap, int sp_cap)
 {
     RowSmem r;
-    r.buf = reinterpret_cast<SortEnt *>(base);
-    base += (size_t)kEntCap * sizeof(SortEnt);
+    r.buf = reinterpret_cast<Key *>(base);
+    base += (size_t)ent_cap * sizeof(Key);
     r.cosv = reinterpret_cast<double *>(base);
-    base += (size_t)kEntCap * sizeof(double);
-    r.weak = reinterpret_cast<double *>(base);
-    base += (size_t)kMaxSchemas * kSpCap * sizeof(double);
+    base += (size_t)ent_cap * sizeof(double);
+    r.sp_s = reinterpret_cast<double *>(base);
+    base += (size_t)sp_cap * sizeof(double);
+    r.sp_k = reinterpret_cast<unsigned long long *>(base);
+    base += (size_t)sp_cap * sizeof(unsigned long long);
     r.cols = reinterpret_cast<int32_t *>(base);
-    base += (size_t)kEntCap * sizeof(int32_t);
+    base += (size_t)ent_cap * sizeof(int32_t);
     r.a = reinterpret_cast<float *>(base);
-    (void)D;
     return r;
 }
 
@@ -81,24 +89,8 @@ struct RowArgs {
     RunParams rp;
     Outputs out;
     int32_t *error_flag;  // set to 1 when a capacity limit is hit
+    int ent_cap, sp_cap;  // shared-memory capacities of this launch (>= 256 / >= 8)
 };
-
-__device__ void block_bitonic(SortEnt *buf, int n2)
-{
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int t = threadIdx.x; t < n2; t += kThreads) {
-                const int x = t ^ j;
-                if (x > t) {
-                    const SortEnt a = buf[t], b = buf[x];
-                    const bool first_half = (t & k) == 0;
-                    if (first_half ? ent_before(b, a) : ent_before(a, b)) { buf[t] = b; buf[x] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
 
 __device__ __forceinline__ int next_pow2(int n)
 {
@@ -107,92 +99,157 @@ __device__ __forceinline__ int next_pow2(int n)
     return p;
 }
 
-// Row i: entries [0, n_ca) are candidate columns (cols[]), never same-page; the
-// same-page chunks are appended here.  Returns false when the row is not certified.
+// Sorts buf[0, n) best-first; every thread of the block must call it.  Up to 256 keys the network runs in
+// registers (one key per thread; strides below 32 are warp shuffles, the six wider ones go through buf);
+// larger inputs use the classic shared-memory network over the next power of two.
+__device__ void sort_keys(Key *buf, int n)
+{
+    const int tid = threadIdx.x;
+    if (n <= kThreads) {
+        Key me = tid < n ? buf[tid] : key_pad();
+        __syncthreads();
+        for (int k = 2; k <= kThreads; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                Key o;
+                if (j >= 32) {
+                    buf[tid] = me;
+                    __syncthreads();
+                    o = buf[tid ^ j];
+                    __syncthreads();
+                } else {
+                    o.k = __shfl_xor_sync(0xFFFFFFFFu, me.k, j);
+                    o.j = __shfl_xor_sync(0xFFFFFFFFu, me.j, j);
+                    o.e = __shfl_xor_sync(0xFFFFFFFFu, me.e, j);
+                }
+                const bool lower = (tid & j) == 0, up = (tid & k) == 0;
+                const bool o_first = key_before(o.k, o.j, me.k, me.j);
+                if ((lower == up) ? o_first : !o_first) me = o;
+            }
+        }
+        buf[tid] = me;
+        __syncthreads();
+        return;
+    }
+    const int n2 = next_pow2(n);
+    for (int e = n + tid; e < n2; e += kThreads) buf[e] = key_pad();
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = tid; t < n2; t += kThreads) {
+                const int x = t ^ j;
+                if (x > t) {
+                    const Key a = buf[t], b = buf[x];
+                    const bool first_half = (t & k) == 0;
+                    const bool b_first = key_before(b.k, b.j, a.k, a.j);
+                    if (first_half ? b_first : !b_first) { buf[t] = b; buf[x] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// Row i: entries [0, n_ca) are candidate columns (cols[]), never same-page; the same-page chunks are
+// appended here.  The candidates are sorted once by exact cosine (every schema ranks them alike); each
+// schema then merges its same-page entries (cosine + weak-supervision bonus) by counting.
+// Returns false when the row is not certified.
 __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n_ca, bool certify,
                            float tau, float eps)
 {
+    __shared__ double s_kth;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t p0 = A.offsets[i];
     const int c = (int)(A.offsets[i + 1] - p0);
     const int n = n_ca + c;
     const int d4 = A.D >> 2;
     const RunParams &rp = A.rp;
-    // same-page chunks, in increasing chunk index
     for (int p = threadIdx.x; p < c; p += kThreads) sm.cols[n_ca + p] = A.sorted_chunk[A.sp_start[i] + p];
     __syncthreads();
     // exact cosine of every entry
     const float na = A.img_n2[i];
-    for (int e = warp; e < n; e += kWarps) {
-        const int j = sm.cols[e];
-        const float dot = warp_dot(reinterpret_cast<const float4 *>(sm.a),
-                                   reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)j * A.D), d4, lane);
-        if (lane == 0) sm.cosv[e] = sim_from_sums(dot, na, A.chk_n2[j]);
+    for (int e = warp; e < n; e += 2 * kWarps) {
+        const int e1 = e + kWarps;
+        const int j0 = sm.cols[e], j1 = e1 < n ? sm.cols[e1] : j0;
+        float d0, d1;
+        warp_dot2(reinterpret_cast<const float4 *>(sm.a), reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)j0 * A.D),
+                  reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)j1 * A.D), d4, lane, d0, d1);
+        if (lane == 0) sm.cosv[e] = (double)d0;  // fp32 dot for now; the fp64 division runs one thread per entry below
+        if (lane == 1 && e1 < n) sm.cosv[e1] = (double)d1;
     }
-    // weak-supervision bonus of the same-page entries, per schema
-    for (int t = threadIdx.x; t < c * rp.S; t += kThreads) {
-        const int p = t % c, si = t / c, s = rp.schema[si];
-        const int j = sm.cols[n_ca + p];
-        double w = 0.0;
-        if (s != 0) {
-            double lex = 0.0, pos = 0.0, rec[3];
-            if (schema_uses_lex(s))
-                lex = lexical_score(term_hits(A.chk_terms + (int64_t)j * A.term_words,
-                                              A.img_terms ? A.img_terms + i * A.term_words : nullptr,
-                                              A.term_words), rp.n_terms);
-            if (schema_uses_pos(s)) pos = positional_score(A.img_bbox + 4 * i, A.chk_bbox + 4 * (int64_t)j);
-            weak_records(schema_uses_lex(s), schema_uses_pos(s), lex, pos, rec);
-            w = rp.lam_lex * rec[0] + rp.lam_pos * rec[1] + rp.lam_comb * rec[2];
-        }
-        sm.weak[si * kSpCap + p] = w;
-    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < n; e += kThreads)
+        sm.cosv[e] = sim_from_sums((float)sm.cosv[e], na, A.chk_n2[sm.cols[e]]);
     __syncthreads();
     if (A.out.pair_sim)
         for (int p = threadIdx.x; p < c; p += kThreads) A.out.pair_sim[p0 + p] = sm.cosv[n_ca + p];
-    const int n2 = next_pow2(n);
+    for (int e = threadIdx.x; e < n_ca; e += kThreads) {
+        Key x; x.k = ord64(sm.cosv[e]); x.j = sm.cols[e]; x.e = e;
+        sm.buf[e] = x;
+    }
+    __syncthreads();
+    sort_keys(sm.buf, n_ca);
     bool ok = true;
     for (int si = 0; si < rp.S; ++si) {
-        for (int e = threadIdx.x; e < n2; e += kThreads) {
-            SortEnt x;
-            if (e < n) {
-                x.s = sm.cosv[e];
-                if (e >= n_ca) x.s = x.s + sm.weak[si * kSpCap + (e - n_ca)];
-                x.j = sm.cols[e];
-                x.e = e;
-            } else {
-                x.s = -CUDART_INF;
-                x.j = 0x7FFFFFFF;
-                x.e = -1;
+        const int s = rp.schema[si];
+        if (threadIdx.x == 0) s_kth = -CUDART_INF;
+        // ranking score of the same-page entries in this schema
+        for (int p = threadIdx.x; p < c; p += kThreads) {
+            const int j = sm.cols[n_ca + p];
+            double w = 0.0;
+            if (s != 0) {
+                double lex = 0.0, pos = 0.0, rec[3];
+                if (schema_uses_lex(s))
+                    lex = lexical_score(term_hits(A.chk_terms + (int64_t)j * A.term_words,
+                                                  A.img_terms ? A.img_terms + i * A.term_words : nullptr,
+                                                  A.term_words), rp.n_terms);
+                if (schema_uses_pos(s)) pos = positional_score(A.img_bbox + 4 * i, A.chk_bbox + 4 * (int64_t)j);
+                weak_records(schema_uses_lex(s), schema_uses_pos(s), lex, pos, rec);
+                w = rp.lam_lex * rec[0] + rp.lam_pos * rec[1] + rp.lam_comb * rec[2];
             }
-            sm.buf[e] = x;
+            const double sc = sm.cosv[n_ca + p] + w;
+            sm.sp_s[p] = sc;
+            sm.sp_k[p] = ord64(sc);
+            if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P + p0 + p] = sc;
         }
         __syncthreads();
-        if (A.out.pair_score)
-            for (int p = threadIdx.x; p < c; p += kThreads)
-                A.out.pair_score[(int64_t)si * A.P + p0 + p] = sm.buf[n_ca + p].s;
-        __syncthreads();
-        block_bitonic(sm.buf, n2);
-        if (A.out.topk_idx)
-            for (int r = threadIdx.x; r < rp.kmax; r += kThreads) {
-                const int64_t o = ((int64_t)si * A.N + i) * rp.kmax + r;
-                A.out.topk_idx[o] = r < n ? (int64_t)sm.buf[r].j + rp.col_offset : -1;
-                A.out.topk_score[o] = r < n ? sm.buf[r].s : -CUDART_INF;
+        const int64_t o_top = ((int64_t)si * A.N + i) * rp.kmax, o_deep = ((int64_t)si * A.N + i) * rp.kneed;
+        // final position of an element = its position in its own sorted list + elements of the other list before it
+        for (int t = threadIdx.x; t < c + min(n_ca, rp.kneed); t += kThreads) {
+            unsigned long long k;
+            int j, pos;
+            double sc;
+            if (t < c) {  // a same-page entry: binary search in the sorted candidates, count the other same-page entries
+                k = sm.sp_k[t]; j = sm.cols[n_ca + t]; sc = sm.sp_s[t];
+                int lo = 0, hi = n_ca;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (key_before(sm.buf[mid].k, sm.buf[mid].j, k, j)) lo = mid + 1; else hi = mid;
+                }
+                pos = lo;
+                for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[n_ca + q], k, j);
+                if (pos < rp.kneed && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P + p0 + t] = pos + 1;
+            } else {      // a candidate: its sorted position + the same-page entries that beat it
+                const Key x = sm.buf[t - c];
+                k = x.k; j = x.j; sc = sm.cosv[x.e];
+                pos = t - c;
+                for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[n_ca + q], k, j);
             }
-        if (A.out.deep_idx)
-            for (int r = threadIdx.x; r < rp.kneed; r += kThreads) {
-                const int64_t o = ((int64_t)si * A.N + i) * rp.kneed + r;
-                A.out.deep_idx[o] = r < n ? (int64_t)sm.buf[r].j + rp.col_offset : -1;
-                A.out.deep_score[o] = r < n ? sm.buf[r].s : -CUDART_INF;
+            if (pos < rp.kmax && A.out.topk_idx) {
+                A.out.topk_idx[o_top + pos] = (int64_t)j + rp.col_offset;
+                A.out.topk_score[o_top + pos] = sc;
             }
-        if (A.out.pair_rank) {
-            const int lim = n < rp.kneed ? n : rp.kneed;
-            for (int r = threadIdx.x; r < lim; r += kThreads) {
-                const int e = sm.buf[r].e;
-                if (e >= n_ca) A.out.pair_rank[(int64_t)si * A.P + p0 + (e - n_ca)] = r + 1;
+            if (pos < rp.kneed && A.out.deep_idx) {
+                A.out.deep_idx[o_deep + pos] = (int64_t)j + rp.col_offset;
+                A.out.deep_score[o_deep + pos] = sc;
             }
+            if (pos == rp.kneed - 1) s_kth = sc;
         }
-        if (certify && tau > -CUDART_INF_F)
-            ok = ok && (n >= rp.kneed) && (sm.buf[rp.kneed - 1].s > (double)tau + (double)eps);
+        for (int r = n + threadIdx.x; r < rp.kneed; r += kThreads) {  // fewer entries than the lists are wide
+            if (r < rp.kmax && A.out.topk_idx) { A.out.topk_idx[o_top + r] = -1; A.out.topk_score[o_top + r] = -CUDART_INF; }
+            if (A.out.deep_idx) { A.out.deep_idx[o_deep + r] = -1; A.out.deep_score[o_deep + r] = -CUDART_INF; }
+        }
+        __syncthreads();
+        if (certify && tau > -CUDART_INF_F) ok = ok && (n >= rp.kneed) && (s_kth > (double)tau + (double)eps);
         __syncthreads();
     }
     return ok;
@@ -213,7 +270,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const RowSmem sm = carve(smem_raw, A.D);
+    const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
     __shared__ int s_nca;
     __shared__ float s_tau;
     for (int64_t i = blockIdx.x; i < A.N; i += gridDim.x) {
@@ -221,7 +278,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
         if (threadIdx.x == 0) { s_nca = 0; s_tau = -CUDART_INF_F; }
         stage_row(A, sm, i);
         __syncthreads();
-        bool overflow = c > kSpCap;
+        bool overflow = c > A.sp_cap;
         bool ok = !overflow;
         if (!use_lists) {
             if (ok) {
@@ -260,24 +317,18 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                         const float sa = cand_score(k);
                         if (sa > tau_union && (ik == MMALIGN_NULL_KEY || A.chk_key[col] != ik)) {
                             const int pos = atomicAdd(&s_nca, 1);
-                            if (pos < kEntCap) { SortEnt x; x.s = (double)sa; x.j = (int32_t)col; x.e = 0; sm.buf[pos] = x; }
+                            if (pos < A.ent_cap) { Key x; x.k = ord64((double)sa); x.j = (int32_t)col; x.e = (int32_t)__float_as_int(sa); sm.buf[pos] = x; }
                         }
                     }
                 }
                 __syncthreads();
                 const int n_all = s_nca;
-                if (n_all + c > kEntCap) { ok = false; break; }
+                if (n_all + c > A.ent_cap) { ok = false; break; }
                 const bool truncate = attempt == 0 && n_all > L.kprime;
                 if (truncate) {
-                    const int n2 = next_pow2(n_all);
-                    for (int e = n_all + threadIdx.x; e < n2; e += kThreads) {
-                        SortEnt x; x.s = -CUDART_INF; x.j = 0x7FFFFFFF; x.e = -1;
-                        sm.buf[e] = x;
-                    }
-                    __syncthreads();
-                    block_bitonic(sm.buf, n2);
+                    sort_keys(sm.buf, n_all);
                     // the union stays complete above the last kept approximate score
-                    if (threadIdx.x == 0) { s_nca = L.kprime; s_tau = (float)sm.buf[L.kprime - 1].s; }
+                    if (threadIdx.x == 0) { s_nca = L.kprime; s_tau = __int_as_float(sm.buf[L.kprime - 1].e); }
                     __syncthreads();
                 }
                 const int n_ca = s_nca;
@@ -295,7 +346,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
         }
         if (!ok && threadIdx.x == 0) {
             if (use_lists) fail_rows[atomicAdd(fail_count, 1)] = (int32_t)i;
-            else atomicExch(A.error_flag, 1);  // same-page mode: page larger than kSpCap
+            else atomicExch(A.error_flag, 1);  // same-page mode: page larger than A.sp_cap
         }
         __syncthreads();
     }
@@ -308,9 +359,9 @@ __global__ void __launch_bounds__(kThreads)
 exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const RowSmem sm = carve(smem_raw, A.D);
+    const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
     __shared__ int s_cnt;
-    __shared__ double s_thr;
+    __shared__ unsigned long long s_thr;  // key of the kneed-th best candidate so far (0 = none yet)
     __shared__ int s_thr_j;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n_rows = n_rows_dev ? (int64_t)*n_rows_dev : n_rows_host;
@@ -320,67 +371,71 @@ exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int
         const int64_t i = rows ? rows[b] : b;
         const int64_t p0 = A.offsets[i];
         const int c = (int)(A.offsets[i + 1] - p0);
-        if (threadIdx.x == 0) { s_cnt = 0; s_thr = -CUDART_INF; s_thr_j = 0x7FFFFFFF; }
+        if (threadIdx.x == 0) { s_cnt = 0; s_thr = 0ull; s_thr_j = 0x7FFFFFFF; }
         stage_row(A, sm, i);
         // a previous (uncertified) pass may have written ranks for this row
         if (A.out.pair_rank)
             for (int t = threadIdx.x; t < c * A.rp.S; t += kThreads)
                 A.out.pair_rank[(int64_t)(t / c) * A.P + p0 + (t % c)] = 0;
         __syncthreads();
-        if (c > kSpCap) {
+        if (c > A.sp_cap) {
             if (threadIdx.x == 0) atomicExch(A.error_flag, 1);
             continue;
         }
         const float na = A.img_n2[i];
         const uint64_t ik = A.img_key[i];
         for (int64_t base = 0; base < A.M; base += kScanRound) {
-            const double thr = s_thr;
+            const unsigned long long thr = s_thr;
             const int thr_j = s_thr_j;
+            float my_dot = 0.f;  // lane q keeps the dot product of column base + warp * 16 + q
             for (int q = 0; q < 16; ++q) {
                 const int64_t j = base + warp * 16 + q;
                 if (j >= A.M) break;
                 if (ik != MMALIGN_NULL_KEY && A.chk_key[j] == ik) continue;  // enters as a same-page entry
                 const float dot = warp_dot(reinterpret_cast<const float4 *>(sm.a),
                                            reinterpret_cast<const float4 *>(A.chk_emb + j * A.D), d4, lane);
-                if (lane == 0) {
-                    const double s = sim_from_sums(dot, na, A.chk_n2[j]);
-                    if (s > thr || (s == thr && (int)j < thr_j)) {
+                if (lane == q) my_dot = dot;
+            }
+            {
+                const int64_t j = base + warp * 16 + lane;
+                if (lane < 16 && j < A.M && !(ik != MMALIGN_NULL_KEY && A.chk_key[j] == ik)) {
+                    const unsigned long long k = ord64(sim_from_sums(my_dot, na, A.chk_n2[j]));
+                    if (key_before(k, (int)j, thr, thr_j)) {
                         const int pos = atomicAdd(&s_cnt, 1);
-                        SortEnt x; x.s = s; x.j = (int32_t)j; x.e = 0;
+                        Key x; x.k = k; x.j = (int32_t)j; x.e = 0;
                         sm.buf[pos] = x;
                     }
                 }
             }
             __syncthreads();
-            if (s_cnt > kEntCap - kScanRound) {  // uniform: shrink to the best kneed
+            if (s_cnt > A.ent_cap - kScanRound) {  // uniform: shrink to the best kneed
                 const int cnt = s_cnt;
-                for (int e = cnt + threadIdx.x; e < kEntCap; e += kThreads) {
-                    SortEnt x; x.s = -CUDART_INF; x.j = 0x7FFFFFFF; x.e = -1;
-                    sm.buf[e] = x;
-                }
-                __syncthreads();
-                block_bitonic(sm.buf, kEntCap);
+                sort_keys(sm.buf, cnt);
                 if (threadIdx.x == 0) {
                     s_cnt = cnt < kneed ? cnt : kneed;
-                    if (cnt >= kneed) { s_thr = sm.buf[kneed - 1].s; s_thr_j = sm.buf[kneed - 1].j; }
+                    if (cnt >= kneed) { s_thr = sm.buf[kneed - 1].k; s_thr_j = sm.buf[kneed - 1].j; }
                 }
                 __syncthreads();
             }
         }
         const int cnt = s_cnt;
-        const int n2 = next_pow2(cnt);
-        for (int e = cnt + threadIdx.x; e < n2; e += kThreads) {
-            SortEnt x; x.s = -CUDART_INF; x.j = 0x7FFFFFFF; x.e = -1;
-            sm.buf[e] = x;
-        }
-        __syncthreads();
-        block_bitonic(sm.buf, n2);
+        sort_keys(sm.buf, cnt);
         const int n_ca = cnt < kneed ? cnt : kneed;
         for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[e] = sm.buf[e].j;
         __syncthreads();
         finish_row(A, sm, i, n_ca, false, 0.f, 0.f);
         __syncthreads();
     }
+}
+
+static void size_caps(RowArgs &A, const PairIndex &px, int64_t union_entries)
+{
+    int64_t sp = 8;
+    while (sp < px.c_max && sp < kSpCapMax) sp <<= 1;
+    int64_t ent = 256;  // sort_keys needs room for one key per thread
+    while (ent < union_entries + sp && ent < kEntCapMax) ent <<= 1;
+    A.sp_cap = (int)sp;
+    A.ent_cap = (int)ent;
 }
 
 static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
@@ -394,6 +449,7 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
     A.N = img.n; A.M = chk.n; A.D = img.D; A.term_words = chk.term_words;
     A.offsets = px.offsets; A.sorted_chunk = px.sorted_chunk; A.sp_start = px.sp_start; A.P = px.P;
     A.rp = rp; A.out = out; A.error_flag = error_flag;
+    A.ent_cap = kEntCapMax; A.sp_cap = kSpCapMax;
     return A;
 }
 
@@ -403,11 +459,13 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            int32_t *error_flag, cudaStream_t st)
 {
     if (img.n == 0) return cudaSuccess;
-    const size_t smem = row_smem_bytes(img.D);
+    RowArgs A = make_args(img, chk, px, rp, out, error_flag);
+    CandLists L = lists ? *lists : CandLists();
+    // shared memory sized for this launch: the union of a row's lists after the final compaction, plus its page
+    size_caps(A, px, lists ? (int64_t)2 * L.n_splits * (L.kprime_list + 16) : 0);
+    const size_t smem = row_smem_bytes(img.D, A.ent_cap, A.sp_cap);
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const RowArgs A = make_args(img, chk, px, rp, out, error_flag);
-    CandLists L = lists ? *lists : CandLists();
     int64_t grid = img.n < 148 * 16 ? img.n : 148 * 16;
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
                                                            fail_count, cand_counter);
@@ -419,10 +477,11 @@ cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex 
                               const Outputs &out, int32_t *error_flag, cudaStream_t st)
 {
     if (img.n == 0 || (!n_rows_dev && n_rows_host == 0)) return cudaSuccess;
-    const size_t smem = row_smem_bytes(img.D);
+    RowArgs A = make_args(img, chk, px, rp, out, error_flag);
+    size_caps(A, px, kEntCapMax);  // the scan's streaming buffer wants the full capacity
+    const size_t smem = row_smem_bytes(img.D, A.ent_cap, A.sp_cap);
     cudaError_t e = cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const RowArgs A = make_args(img, chk, px, rp, out, error_flag);
     int64_t grid = 148 * 4;
     if (!n_rows_dev && n_rows_host < grid) grid = n_rows_host;
     exact_scan_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, rows, n_rows_dev, n_rows_host);

@@ -46,7 +46,8 @@ class ShardedScorer:
         kw = dict(candidates=candidates, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight,
                   kprime=kprime, path=path)
         if self.world == 1:
-            r = eng.run(schemas, want=("topk", "pairs", "sums"), device_outputs=not host_outputs, **kw)
+            r = eng.run(schemas, want=("topk", "pairs", "sums"), device_outputs=not host_outputs,
+                        pinned_outputs=host_outputs, **kw)
             r["metrics"] = metrics_from_sums(r["hits"], r["rr_sum"], r["sim_sum"], r["num_pairs"])
             r["d2h_bytes"] = sum(r[k].nbytes for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim")) + 200 \
                 if host_outputs else 0

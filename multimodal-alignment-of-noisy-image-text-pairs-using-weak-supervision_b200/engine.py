@@ -67,6 +67,7 @@ class AlignmentEngine:
             raise MMAlignError(rc, self._L.mmalign_last_error(None).decode())
         self.device = int(device)
         self._keep = {}
+        self._pinned = {}
         self.N = self.M = self.D = 0
         self.col_offset = 0
 
@@ -145,7 +146,7 @@ class AlignmentEngine:
     def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
             mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
             path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
-            deep=False, stream=None):
+            pinned_outputs=False, deep=False, stream=None):
         mask = schema_mask(schemas)
         S = bin(mask).count("1")
         ks = [int(k) for k in k_values]
@@ -172,6 +173,20 @@ class AlignmentEngine:
             def alloc(name, shape, dt):
                 t = torch.empty(shape, dtype={"i64": torch.int64, "f64": torch.float64, "i32": torch.int32}[dt], device=dev)
                 res[name] = t
+                return t.data_ptr()
+        elif pinned_outputs:
+            import torch
+
+            def alloc(name, shape, dt):
+                # page-locked result buffers, allocated once and REUSED by later calls of the same shape
+                key = (name, tuple(shape), dt)
+                t = self._pinned.get(key)
+                if t is None:
+                    t = torch.empty(shape, dtype={"i64": torch.int64, "f64": torch.float64, "i32": torch.int32}[dt],
+                                    pin_memory=True)
+                    self._pinned = {k: v for k, v in self._pinned.items() if k[0] != name}
+                    self._pinned[key] = t
+                res[name] = t.numpy()
                 return t.data_ptr()
         else:
             def alloc(name, shape, dt):
