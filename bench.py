@@ -86,14 +86,21 @@ class ClockSampler:
             R = pynvml
             names = {"hw_slowdown": R.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": R.nvmlClocksEventReasonHwThermalSlowdown,
                      "sw_thermal_slowdown": R.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": R.nvmlClocksEventReasonSwPowerCap}
+            it, reasons, pw = 0, [], 0.0
             while not self._stop.is_set():
                 try:
                     sm = R.nvmlDeviceGetClockInfo(h, R.NVML_CLOCK_SM)
-                    mask = R.nvmlDeviceGetCurrentClocksEventReasons(h)
-                    pw = R.nvmlDeviceGetPowerUsage(h) / 1000.0
-                    self.samples.append((time.time(), sm, pw, [n for n, b in names.items() if mask & b]))
+                    # the throttle-reason and power queries were measured (tools/sampler_diag.py) to stall a running
+                    # step by 150-450 ms now and then; the SM clock query does not.  So: clock every 200 ms,
+                    # reasons and power every 2 s.
+                    if it % 10 == 0:
+                        mask = R.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        reasons = [n for n, b in names.items() if mask & b]
+                        pw = R.nvmlDeviceGetPowerUsage(h) / 1000.0
+                    self.samples.append((time.time(), sm, pw, reasons))
                 except Exception as e:  # noqa: BLE001
                     self.err = repr(e)
+                it += 1
                 self._stop.wait(0.2)
         self.thread = threading.Thread(target=loop, daemon=True)
         self.thread.start()
@@ -104,12 +111,23 @@ class ClockSampler:
         if self.thread:
             self.thread.join(1.0)
         win = [x for x in self.samples if t_begin <= x[0] <= t_end + 0.2]
+        try:  # one more look at the throttle reasons right at the end of the region
+            import pynvml as R
+            h = R.nvmlDeviceGetHandleByIndex(self.index)
+            mask = R.nvmlDeviceGetCurrentClocksEventReasons(h)
+            extra = [n for n, b in (("hw_slowdown", R.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", R.nvmlClocksEventReasonHwThermalSlowdown),
+                                    ("sw_thermal_slowdown", R.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", R.nvmlClocksEventReasonSwPowerCap)) if mask & b]
+            if win:
+                win.append((win[-1][0], win[-1][1], win[-1][2], extra))
+        except Exception:  # noqa: BLE001
+            pass
         if not win:
             return {"sm_mhz": None, "sm_max_mhz": getattr(self, "max_sm", None), "reasons": ["no samples: " + str(self.err)]}
         sm = [x[1] for x in win]
         reasons = sorted({r for x in win for r in x[3]})
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.max_sm), "reasons": reasons,
-                "power_w_max": max(x[2] for x in win), "samples": len(win), "source": "NVML, 200 ms period"}
+                "power_w_max": max(x[2] for x in win), "samples": len(win),
+                "source": "NVML: SM clock every 200 ms, throttle reasons and power every 2 s"}
 
 
 # ------------------------------------------------------------------------------------------- reference arm
@@ -209,7 +227,7 @@ def run_ours(args):
     sharded = distributed.ShardedScorer(eng, world, rank, dev)
     run_kw = dict(schemas=SCHEMAS, k_values=K_VALUES, mrr_cutoff=MRR_CUTOFF, weak_weight=WEAK, kprime=args.kprime)
 
-    phase_ms = {}
+    phase_ms, step_ms = {}, {}
 
     def step(im, ck, host_out):
         t0 = time.perf_counter()
@@ -219,6 +237,7 @@ def run_ours(args):
         t2 = time.perf_counter()
         out = sharded.run(host_outputs=host_out, **run_kw)
         t3 = time.perf_counter()
+        step_ms.setdefault("host" if host_out else "device", []).append(round(1e3 * (t3 - t0), 1))
         phase_ms["host" if host_out else "device"] = dict(set_images=1e3 * (t1 - t0), set_chunks=1e3 * (t2 - t1),
                                                           run=1e3 * (t3 - t2), **{k: v for k, v in out["stats"].items() if k.endswith("_us")})
         return out
@@ -319,6 +338,7 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{n2} query rows x all {M} chunks in {dt:.1f} s (oracle/numpy_port.py: numpy sgemm "
                                           f"[{numpy_port.blas_info()}] + argpartition/lexsort, same workload)"}
+    print("wall ms of every step (warm-up included):", json.dumps(step_ms), file=sys.stderr)
     print("phase wall times of the last step (ms; *_us from CUDA events):", json.dumps(phase_ms), file=sys.stderr)
     print(json.dumps(line), flush=True)
     if world > 1:

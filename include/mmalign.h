@@ -77,8 +77,9 @@ typedef struct {
     double lam_pos;        /* weight of a 'positional' record */
     double lam_comb;       /* weight of a 'combined' record; all 0 = reference ranking */
     int32_t path;          /* MMALIGN_PATH_* */
-    int32_t kprime;        /* candidates kept per row by the fused kernel; 0 = auto */
-    int32_t reserved[6];
+    int32_t kprime;        /* depth the fused kernel's candidate lists are complete to; 0 = auto */
+    int32_t n_ranks;       /* sharded passes: number of GPUs the chunk table is sharded over; 0/1 = one */
+    int32_t reserved[5];
 } mmalign_params;
 
 /* Any pointer may be NULL (output not wanted).  S = popcount(schema_mask),
@@ -141,6 +142,24 @@ int mmalign_run(mmalign_ctx *ctx, const mmalign_params *params, mmalign_out *out
  * 'lexical' / 'positional' / 'combined' record of each true pair in `schema`
  * (one MMALIGN_* bit), 0.0 where the reference inserts none. */
 int mmalign_alignments(mmalign_ctx *ctx, uint32_t schema, double *rec, void *stream);
+
+/* Sharded (multi-GPU) run in passes -- the caller performs the collectives in between
+ * (reference implementation: distributed.py::ShardedScorer):
+ *   1. mmalign_fused_pass    K1 on this rank's shard; tau_row [N] = score above which the rank's candidate
+ *                            lists hold every local column.       -> all-reduce(max) of tau_row, and of
+ *                            mmalign_chunk_err_max
+ *   2. mmalign_rescore_pass  exact scores of the rank's entries above the global tau; fills the device
+ *                            outputs (lists, pair arrays) and cert_count [S][N] = local entries provably
+ *                            above every column left out.         -> all-reduce(sum) of cert_count; rows whose
+ *                            sum is below max(Kmax, mrr_cutoff) are not certified
+ *   3. mmalign_rescan_rows   exact scan of those rows (same rows on every rank)
+ *   then merge_topk / count_beating / reduce_metrics as below.  Output pointers are DEVICE pointers. */
+int mmalign_fused_pass(mmalign_ctx *ctx, const mmalign_params *params, float *tau_row, void *stream);
+int mmalign_chunk_err_max(mmalign_ctx *ctx, float *err_max);
+int mmalign_rescore_pass(mmalign_ctx *ctx, const mmalign_params *params, const float *tau_global,
+                         float eps_chunk_global, mmalign_out *out, int32_t *cert_count, void *stream);
+int mmalign_rescan_rows(mmalign_ctx *ctx, const mmalign_params *params, const int32_t *rows,
+                        int64_t n_rows, mmalign_out *out, void *stream);
 
 /* cross-rank merge after an all-gather of every rank's mmalign_run lists
  * (chunks are sharded over ranks):

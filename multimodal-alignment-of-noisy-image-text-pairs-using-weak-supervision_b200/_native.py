@@ -23,7 +23,7 @@ class Params(C.Structure):
     _fields_ = [("schema_mask", C.c_uint32), ("candidates", C.c_int32), ("n_k", C.c_int32),
                 ("k_list", C.c_int32 * 8), ("mrr_cutoff", C.c_int32), ("lam_lex", C.c_double),
                 ("lam_pos", C.c_double), ("lam_comb", C.c_double), ("path", C.c_int32),
-                ("kprime", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("kprime", C.c_int32), ("n_ranks", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class Out(C.Structure):
@@ -36,7 +36,8 @@ class Out(C.Structure):
 EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_last_error",
            "mmalign_set_images", "mmalign_set_chunks", "mmalign_num_pairs", "mmalign_get_pairs",
            "mmalign_run", "mmalign_alignments", "mmalign_merge_topk", "mmalign_count_beating",
-           "mmalign_reduce_metrics", "mmalign_debug_scores"]
+           "mmalign_reduce_metrics", "mmalign_debug_scores", "mmalign_fused_pass", "mmalign_chunk_err_max",
+           "mmalign_rescore_pass", "mmalign_rescan_rows"]
 
 _lib = None
 
@@ -59,10 +60,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+    import os
+    path = Path(os.environ.get("MMALIGN_LIB", LIB_PATH))  # development: try another build of the same ABI
+    if not path.exists():
+        raise RuntimeError(f"{path} is missing: build it with __graft_entry__.build() "
                            "(the scoring path is CUDA-only and has no fallback)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     vp, i64, i32, u32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_double
     L.mmalign_abi_version.restype = C.c_int
     L.mmalign_create.argtypes = [C.POINTER(vp), C.c_int]
@@ -80,6 +83,10 @@ def load():
     L.mmalign_count_beating.argtypes = [vp, vp, vp, i64, i32, i32, i64, vp, vp, vp, vp, vp]
     L.mmalign_reduce_metrics.argtypes = [vp, vp, vp, i32, i64, vp, i32, i32, vp, vp, vp, vp]
     L.mmalign_debug_scores.argtypes = [vp, vp, vp]
+    L.mmalign_fused_pass.argtypes = [vp, C.POINTER(Params), vp, vp]
+    L.mmalign_chunk_err_max.argtypes = [vp, C.POINTER(C.c_float)]
+    L.mmalign_rescore_pass.argtypes = [vp, C.POINTER(Params), vp, C.c_float, C.POINTER(Out), vp, vp]
+    L.mmalign_rescan_rows.argtypes = [vp, C.POINTER(Params), vp, i64, C.POINTER(Out), vp]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):

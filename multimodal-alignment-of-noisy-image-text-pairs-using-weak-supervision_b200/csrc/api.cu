@@ -8,6 +8,7 @@
 #include <string.h>
 #include <vector>
 #include <chrono>
+#include <math.h>
 #include <stdlib.h>
 
 using namespace mma;
@@ -70,10 +71,12 @@ struct mmalign_ctx {
     int64_t n_terms = 0, col_offset = 0;
     PairIndex px;
     bool px_ready = false;
-    DevBuf px_offsets, px_sorted, px_start;
+    DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
     DevBuf fail_rows, small;      // small: fail_count, cand_counter, error_flag, k_list, stats
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
+    CandLists lists;               // written by the last fused pass
+    bool lists_valid = false;
     cudaEvent_t ev[5] = {};        // run start, after fused, after rescore, after exact scan, after metrics
 };
 
@@ -144,7 +147,7 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     cudaDeviceSynchronize();
     c->img.release();
     c->chk.release();
-    DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->list_keys, &c->list_tau, &c->list_count,
+    DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
                       &c->fail_rows, &c->small, &c->metrics_scratch, &c->stage};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
@@ -177,6 +180,7 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
     CU(c, cudaStreamSynchronize(st));
     ss.ready = false;
     c->px_ready = false;
+    c->lists_valid = false;
     ss.s = Side();
     Side &s = ss.s;
     s.n = n; s.D = D; s.term_words = term_words;
@@ -246,7 +250,9 @@ static int ensure_index(mmalign_ctx *c)
     c->px.offsets = (int64_t *)c->px_offsets.p;
     c->px.sorted_chunk = (int32_t *)c->px_sorted.p;
     c->px.sp_start = (int64_t *)c->px_start.p;
-    CU(c, build_pair_index(c->img.s, c->chk.s, c->px, 0));
+    const size_t sb = pair_index_scratch_bytes(N, M);
+    CU(c, c->px_scratch.reserve(sb));
+    CU(c, build_pair_index(c->img.s, c->chk.s, c->px, c->px_scratch.p, sb, 0));
     c->px_ready = true;
     return MMALIGN_OK;
 }
@@ -324,17 +330,9 @@ static int schema_index(uint32_t bit)
     return -1;
 }
 
-extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream)
+static int parse_params(mmalign_ctx *c, const mmalign_params *prm, RunParams *out)
 {
-    if (!c || !prm || !uo) return fail(c, MMALIGN_EINVAL, "mmalign_run: NULL argument");
-    Trace tr("run");
-    int rc = ensure_index(c);
-    if (rc) return rc;
-    tr.mark("pair index");
-    cudaStream_t st = (cudaStream_t)stream;
-    const Side &img = c->img.s, &chk = c->chk.s;
-    const int64_t N = img.n, M = chk.n, P = c->px.P;
-    // ---- parameters
+    const Side &chk = c->chk.s;
     RunParams rp = {};
     for (int s = 0; s < 4; ++s)
         if (prm->schema_mask & (1u << s)) rp.schema[rp.S++] = s;
@@ -356,8 +354,46 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     rp.n_terms = c->n_terms;
     rp.col_offset = c->col_offset;
     const bool needs_terms = (prm->schema_mask & (MMALIGN_LEXICAL | MMALIGN_COMBINED)) != 0;
-    if (needs_terms && !chk.terms && M > 0) return fail(c, MMALIGN_EINVAL, "lexical schema requested but the chunks have no term sets");
+    if (needs_terms && !chk.terms && chk.n > 0) return fail(c, MMALIGN_EINVAL, "lexical schema requested but the chunks have no term sets");
     if (prm->path < 0 || prm->path > 2) return fail(c, MMALIGN_EINVAL, "path=%d unknown", prm->path);
+    if (prm->n_ranks < 0 || prm->n_ranks > 64) return fail(c, MMALIGN_EINVAL, "n_ranks=%d must be in 0..64", prm->n_ranks);
+    *out = rp;
+    return MMALIGN_OK;
+}
+
+// K1 over the current corpus; the lists stay in the context for the rescoring pass
+static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, cudaStream_t st, FusedPlan *plan_out)
+{
+    const Side &img = c->img.s, &chk = c->chk.s;
+    if (img.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", img.D);
+    if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
+    FusedPlan plan;
+    const int prc = fused_plan(img.n, chk.n, img.D, rp.kneed, kprime_req, c->sm_count, n_ranks, &plan);
+    if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)img.n, (long long)chk.n, img.D, kprime_req, prc);
+    CU(c, c->list_keys.reserve((size_t)plan.n_lists * plan.cap * sizeof(uint64_t)));
+    CU(c, c->list_tau.reserve((size_t)plan.n_lists * sizeof(float)));
+    CU(c, c->list_count.reserve((size_t)plan.n_lists * sizeof(int32_t)));
+    CU(c, c->fail_rows.reserve((size_t)img.n * sizeof(int32_t)));
+    c->lists = CandLists();
+    c->lists.keys = (uint64_t *)c->list_keys.p; c->lists.tau = (float *)c->list_tau.p; c->lists.count = (int32_t *)c->list_count.p;
+    CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, c->lists, nullptr, st));
+    c->lists_valid = true;
+    *plan_out = plan;
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream)
+{
+    if (!c || !prm || !uo) return fail(c, MMALIGN_EINVAL, "mmalign_run: NULL argument");
+    Trace tr("run");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    tr.mark("pair index");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Side &img = c->img.s, &chk = c->chk.s;
+    const int64_t N = img.n, M = chk.n, P = c->px.P;
+    RunParams rp;
+    if ((rc = parse_params(c, prm, &rp))) return rc;
     CU(c, cudaSetDevice(c->device));
     // ---- outputs
     Stager sg{c, st};
@@ -404,27 +440,18 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     if (N > 0) {
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
             CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, cand_counter,
-                                 error_flag, st));
+                                 error_flag, nullptr, nullptr, st));
             launches += 1;
         } else if (prm->path == MMALIGN_PATH_EXACT || M == 0) {
             CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, st));
             launches += 1;
         } else {
-            if (img.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", img.D);
-            if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
             FusedPlan plan;
-            const int prc = fused_plan(N, M, img.D, rp.kneed, prm->kprime, c->sm_count, &plan);
-            if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)N, (long long)M, img.D, prm->kprime, prc);
-            CU(c, c->list_keys.reserve((size_t)plan.n_lists * plan.cap * sizeof(uint64_t)));
-            CU(c, c->list_tau.reserve((size_t)plan.n_lists * sizeof(float)));
-            CU(c, c->list_count.reserve((size_t)plan.n_lists * sizeof(int32_t)));
-            CU(c, c->fail_rows.reserve((size_t)N * sizeof(int32_t)));
-            CandLists L;
-            L.keys = (uint64_t *)c->list_keys.p; L.tau = (float *)c->list_tau.p; L.count = (int32_t *)c->list_count.p;
-            CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, L, nullptr, st));
+            if ((rc = run_fused(c, rp, prm->kprime, 1, st, &plan))) return rc;
+            CandLists &L = c->lists;
             CU(c, cudaEventRecord(c->ev[1], st));
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, (int32_t *)c->fail_rows.p, fail_count,
-                                 cand_counter, error_flag, st));
+                                 cand_counter, error_flag, nullptr, nullptr, st));
             CU(c, cudaEventRecord(c->ev[2], st));
             CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, st));
             CU(c, cudaEventRecord(c->ev[3], st));
@@ -468,6 +495,137 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     CU(c, cudaStreamSynchronize(st));
     extra.release();
     tr.mark("copy back");
+    return MMALIGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sharded (multi-GPU) run in passes; the caller performs the collectives in between (distributed.py).
+// ---------------------------------------------------------------------------------------------
+extern "C" int mmalign_fused_pass(mmalign_ctx *c, const mmalign_params *prm, float *tau_row, void *stream)
+{
+    if (!c || !prm || !tau_row) return fail(c, MMALIGN_EINVAL, "mmalign_fused_pass: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    RunParams rp;
+    if ((rc = parse_params(c, prm, &rp))) return rc;
+    if (rp.candidates != MMALIGN_CAND_ALL) return fail(c, MMALIGN_EINVAL, "mmalign_fused_pass is for MMALIGN_CAND_ALL");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    const int64_t N = c->img.s.n;
+    Stager sg{c, st};
+    float *d_tau = nullptr;
+    sg.map(tau_row, (size_t)N, &d_tau);
+    if ((rc = sg.commit())) return rc;
+    if (N == 0) return MMALIGN_OK;
+    if (c->chk.s.n == 0) {  // an empty shard holds every one of its (zero) columns
+        std::vector<float> inf((size_t)N, -INFINITY);
+        CU(c, cudaMemcpyAsync(d_tau, inf.data(), sizeof(float) * N, cudaMemcpyHostToDevice, st));
+        CU(c, cudaStreamSynchronize(st));
+        c->lists_valid = false;
+    } else {
+        FusedPlan plan;
+        CU(c, cudaEventRecord(c->ev[0], st));
+        if ((rc = run_fused(c, rp, prm->kprime, prm->n_ranks > 1 ? prm->n_ranks : 1, st, &plan))) return rc;
+        CU(c, cudaEventRecord(c->ev[1], st));
+        CU(c, launch_row_tau(c->lists, N, d_tau, st));
+    }
+    if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+static int device_outputs_only(mmalign_ctx *c, const mmalign_out *uo, const char *what)
+{
+    const void *ptrs[] = {uo->topk_idx, uo->topk_score, uo->pair_rank, uo->pair_sim, uo->pair_score, uo->deep_idx, uo->deep_score};
+    for (const void *p : ptrs)
+        if (p && !is_device_ptr(p)) return fail(c, MMALIGN_EINVAL, "%s takes device output pointers (it runs between collectives)", what);
+    if (uo->hits || uo->rr_sum || uo->sim_sum) return fail(c, MMALIGN_EINVAL, "%s does not reduce metrics; use mmalign_reduce_metrics after the rank exchange", what);
+    return MMALIGN_OK;
+}
+
+static void outputs_from(const mmalign_out *uo, Outputs *out)
+{
+    *out = Outputs();
+    out->topk_idx = uo->topk_idx; out->topk_score = uo->topk_score; out->pair_rank = uo->pair_rank;
+    out->pair_sim = uo->pair_sim; out->pair_score = uo->pair_score; out->deep_idx = uo->deep_idx; out->deep_score = uo->deep_score;
+}
+
+extern "C" int mmalign_rescore_pass(mmalign_ctx *c, const mmalign_params *prm, const float *tau_global,
+                                    float eps_chunk_global, mmalign_out *uo, int32_t *cert_count, void *stream)
+{
+    if (!c || !prm || !uo || !tau_global || !cert_count) return fail(c, MMALIGN_EINVAL, "mmalign_rescore_pass: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    RunParams rp;
+    if ((rc = parse_params(c, prm, &rp))) return rc;
+    if ((rc = device_outputs_only(c, uo, "mmalign_rescore_pass"))) return rc;
+    if (!is_device_ptr(tau_global) || !is_device_ptr(cert_count)) return fail(c, MMALIGN_EINVAL, "mmalign_rescore_pass: tau_global and cert_count must be device pointers");
+    const int64_t N = c->img.s.n, M = c->chk.s.n, P = c->px.P;
+    if (M > 0 && !c->lists_valid) return fail(c, MMALIGN_ESTATE, "mmalign_fused_pass must run before mmalign_rescore_pass");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    Outputs out;
+    outputs_from(uo, &out);
+    int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
+    unsigned long long *cand_counter = (unsigned long long *)((char *)c->small.p + 8);
+    float *eps_dev = (float *)((char *)c->small.p + 128);
+    CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
+    CU(c, cudaMemcpyAsync(eps_dev, &eps_chunk_global, sizeof(float), cudaMemcpyHostToDevice, st));
+    if (out.pair_rank && P) CU(c, cudaMemsetAsync(out.pair_rank, 0, (size_t)rp.S * P * sizeof(int32_t), st));
+    if (N > 0) {
+        if (M > 0) {
+            CU(c, launch_rescore(c->img.s, c->chk.s, c->px, rp, &c->lists, eps_dev, out, nullptr, nullptr, cand_counter,
+                                 error_flag, tau_global, cert_count, st));
+        } else {  // empty shard: no entries, nothing certified here
+            CU(c, cudaMemsetAsync(cert_count, 0, (size_t)rp.S * N * sizeof(int32_t), st));
+            CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, nullptr, nullptr, N, out, error_flag, st));
+        }
+    }
+    CU(c, cudaEventRecord(c->ev[2], st));
+    struct { int32_t fail; int32_t pad; unsigned long long cand; int32_t err; } h = {};
+    CU(c, cudaMemcpyAsync(&h, c->small.p, 24, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    if (h.err) return fail(c, MMALIGN_ELIMIT, "an image has more than 512 same-page chunks, or a row's lists exceed the rescoring capacity");
+    if (uo->stats && !is_device_ptr(uo->stats)) {
+        float t_fused = 0.f, t_resc = 0.f;
+        if (M > 0) { cudaEventElapsedTime(&t_fused, c->ev[0], c->ev[1]); cudaEventElapsedTime(&t_resc, c->ev[1], c->ev[2]); }
+        const int64_t stats[8] = {0, (int64_t)h.cand, M > 0, 4, c->lists.kprime, (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f), 0};
+        memcpy(uo->stats, stats, sizeof stats);
+    }
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_rescan_rows(mmalign_ctx *c, const mmalign_params *prm, const int32_t *rows, int64_t n_rows,
+                                   mmalign_out *uo, void *stream)
+{
+    if (!c || !prm || !uo || (n_rows > 0 && !rows)) return fail(c, MMALIGN_EINVAL, "mmalign_rescan_rows: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    RunParams rp;
+    if ((rc = parse_params(c, prm, &rp))) return rc;
+    if ((rc = device_outputs_only(c, uo, "mmalign_rescan_rows"))) return rc;
+    if (n_rows == 0) return MMALIGN_OK;
+    if (!is_device_ptr(rows)) return fail(c, MMALIGN_EINVAL, "mmalign_rescan_rows: rows must be a device pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    Outputs out;
+    outputs_from(uo, &out);
+    int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
+    CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
+    CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, rows, nullptr, n_rows, out, error_flag, st));
+    int32_t err = 0;
+    CU(c, cudaMemcpyAsync(&err, error_flag, sizeof err, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    if (err) return fail(c, MMALIGN_ELIMIT, "an image has more than 512 same-page chunks");
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_chunk_err_max(mmalign_ctx *c, float *err_max)
+{
+    if (!c || !err_max) return fail(c, MMALIGN_EINVAL, "mmalign_chunk_err_max: NULL argument");
+    if (!c->chk.ready) return fail(c, MMALIGN_ESTATE, "set_chunks must be called first");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaMemcpy(err_max, c->chk.err_max, sizeof(float), cudaMemcpyDeviceToHost));
     return MMALIGN_OK;
 }
 
@@ -557,7 +715,7 @@ extern "C" int mmalign_debug_scores(mmalign_ctx *c, float *out, void *stream)
     cudaStream_t st = (cudaStream_t)stream;
     CU(c, cudaSetDevice(c->device));
     FusedPlan plan;
-    if (fused_plan(img.n, chk.n, img.D, 10, 0, c->sm_count, &plan)) return fail(c, MMALIGN_ELIMIT, "no fused plan");
+    if (fused_plan(img.n, chk.n, img.D, 10, 0, c->sm_count, 1, &plan)) return fail(c, MMALIGN_ELIMIT, "no fused plan");
     Stager sg{c, st};
     float *d = nullptr;
     sg.map(out, (size_t)img.n * chk.n, &d);

@@ -240,12 +240,15 @@ __device__ __forceinline__ long long term_hits(const uint64_t *chunk_terms, cons
 // prep.cu
 cudaError_t launch_prep(Side &side, cudaStream_t st);
 cudaError_t reduce_max_float(const float *x, int64_t n, float *out, cudaStream_t st);
-cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, cudaStream_t st);
+size_t pair_index_scratch_bytes(int64_t N, int64_t M);
+cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, void *scratch, size_t scratch_bytes,
+                             cudaStream_t st);
 // rescore.cu
 cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
-                           int32_t *error_flag, cudaStream_t st);
+                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, cudaStream_t st);
+cudaError_t launch_row_tau(const CandLists &L, int64_t N, float *tau_row, cudaStream_t st);
 cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                               const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
                               const Outputs &out, int32_t *error_flag, cudaStream_t st);
@@ -276,7 +279,7 @@ struct FusedPlan {
     int stages;
     bool a_resident;
 };
-int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, FusedPlan *plan);
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan);
 cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan, const void *tmap_a,
                          const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st);
 int encode_tensor_map(void *tmap_out, const void *base, int64_t rows, int D, int box_rows,

@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <math_constants.h>
 #include <stdio.h>
+#include <math.h>
 
 namespace mma {
 
@@ -438,7 +439,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, FusedPlan *plan)
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan)
 {
     if (D % BK != 0 || D < BK || N <= 0 || M <= 0) return -1;
     FusedPlan p = {};
@@ -463,10 +464,18 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     // near-isotropic embeddings at D >= 512 that takes K' ~ 1.9 x kneed (tools/gap_diag.py).
     p.kprime = kprime_req > 0 ? kprime_req : (kneed * 48 / 25 > kneed + 50 ? kneed * 48 / 25 : kneed + 50);
     if (p.kprime < kneed) p.kprime = kneed;
-    // A row has 2 * n_splits lists over disjoint columns; the union of their best k entries is complete to
-    // a depth of about n_lists * k, so each list keeps its share plus 15 % for imbalance.
-    const int lists_per_row = 2 * p.n_splits;
-    p.kprime_list = (p.kprime * 115 / 100 + lists_per_row - 1) / lists_per_row + 4;
+    // A row has 2 * n_splits lists over disjoint columns on each of the n_ranks GPUs; the union of their best
+    // k entries is complete to a depth of about n_lists * k, so each list keeps its share plus 15 % for imbalance.
+    const int lists_per_row = 2 * p.n_splits * (n_ranks > 1 ? n_ranks : 1);
+    // The union is complete above the LARGEST of the lists' thresholds.  A list's k-th best score sits at
+    // global rank ~ L*k with relative spread 1/sqrt(k), and the largest of L of them about z_L = sqrt(2 ln L)
+    // spreads above the mean, so the union's depth is ~ L*k*(1 - z_L/sqrt(k)); solve that for depth = K'.
+    {
+        const double L = (double)lists_per_row, share = (double)p.kprime / L;
+        const double z = sqrt(2.0 * log(L));
+        const double rk = 0.5 * (z + sqrt(z * z + 4.0 * share));
+        p.kprime_list = (int)ceil(rk * rk) + 2;
+    }
     if (p.kprime_list > p.kprime) p.kprime_list = p.kprime;
     if (p.kprime_list < 16) p.kprime_list = 16;
     const int need = p.kprime_list + p.kprime_list / 2 + 40;  // kept + refill room + one chunk + slack

@@ -123,33 +123,39 @@ __global__ void page_range_kernel(const uint64_t *__restrict__ img_key, int64_t 
     }
 }
 
-cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, cudaStream_t st)
+// scratch layout: sorted keys [M] u64 | iota [M] i32 | counts [N+2] i64 | CUB temp
+size_t pair_index_scratch_bytes(int64_t N, int64_t M)
+{
+    const int64_t Mx = M > 0 ? M : 1;
+    size_t sort_bytes = 0, scan_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, (int)Mx, 0, 64, 0);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int64_t *)nullptr, (int64_t *)nullptr, (int)(N + 1), 0);
+    const size_t tmp = sort_bytes > scan_bytes ? sort_bytes : scan_bytes;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    return up(sizeof(uint64_t) * Mx) + up(sizeof(int32_t) * Mx) + up(sizeof(int64_t) * (N + 2)) + up(tmp) + 256;
+}
+
+cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, void *scratch, size_t scratch_bytes,
+                             cudaStream_t st)
 {
     const int64_t N = img.n, M = chk.n;
-    cudaError_t e;
-    uint64_t *sorted_key = nullptr;
-    int32_t *iota = nullptr;
-    int64_t *counts = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0, scan_bytes = 0;
     const int64_t Mx = M > 0 ? M : 1;
-#define CK(x) do { e = (x); if (e != cudaSuccess) goto done; } while (0)
-    CK(cudaMalloc(&sorted_key, sizeof(uint64_t) * Mx));
-    CK(cudaMalloc(&iota, sizeof(int32_t) * Mx));
-    CK(cudaMalloc(&counts, sizeof(int64_t) * (N + 2)));
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char *base = static_cast<char *>(scratch);
+    uint64_t *sorted_key = reinterpret_cast<uint64_t *>(base); base += up(sizeof(uint64_t) * Mx);
+    int32_t *iota = reinterpret_cast<int32_t *>(base); base += up(sizeof(int32_t) * Mx);
+    int64_t *counts = reinterpret_cast<int64_t *>(base); base += up(sizeof(int64_t) * (N + 2));
+    void *tmp = base;
+    size_t tmp_bytes = scratch_bytes - (size_t)(base - static_cast<char *>(scratch));
+    cudaError_t e;
+#define CK(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     CK(cudaMemsetAsync(counts + N + 1, 0, sizeof(int64_t), st));
     if (M > 0) {
         iota_kernel<<<(unsigned)((M + 255) / 256 > 1184 ? 1184 : (M + 255) / 256), 256, 0, st>>>(iota, M);
         CK(cudaGetLastError());
-        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, chk.key, sorted_key, iota,
-                                           px.sorted_chunk, (int)M, 0, 64, st));
+        CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, chk.key, sorted_key, iota, px.sorted_chunk, (int)M, 0, 64, st));
     }
-    CK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, px.offsets, (int)(N + 1), st));
-    if (scan_bytes > tmp_bytes) tmp_bytes = scan_bytes;
-    CK(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    if (M > 0)
-        CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, chk.key, sorted_key, iota, px.sorted_chunk,
-                                           (int)M, 0, 64, st));
     page_range_kernel<<<(unsigned)((N + 256) / 256 > 1184 ? 1184 : (N + 256) / 256), 256, 0, st>>>(
         img.key, N, sorted_key, M, px.sp_start, counts, reinterpret_cast<unsigned long long *>(counts + N + 1));
     CK(cudaGetLastError());
@@ -157,13 +163,8 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, cu
     CK(cudaMemcpyAsync(&px.P, px.offsets + N, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(&px.c_max, counts + N + 1, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-done:
 #undef CK
-    cudaFree(sorted_key);
-    cudaFree(iota);
-    cudaFree(counts);
-    cudaFree(tmp);
-    return e;
+    return cudaSuccess;
 }
 
 } // namespace mma

@@ -154,9 +154,11 @@ __device__ void sort_keys(Key *buf, int n)
 // schema then merges its same-page entries (cosine + weak-supervision bonus) by counting.
 // Returns false when the row is not certified.
 __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n_ca, bool certify,
-                           float tau, float eps)
+                           float tau, float eps, int32_t *cert_count = nullptr)
 {
     __shared__ double s_kth;
+    __shared__ int s_cert;
+    const double cert_thr = (double)tau + (double)eps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t p0 = A.offsets[i];
     const int c = (int)(A.offsets[i + 1] - p0);
@@ -191,7 +193,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
     bool ok = true;
     for (int si = 0; si < rp.S; ++si) {
         const int s = rp.schema[si];
-        if (threadIdx.x == 0) s_kth = -CUDART_INF;
+        if (threadIdx.x == 0) { s_kth = -CUDART_INF; s_cert = 0; }
         // ranking score of the same-page entries in this schema
         for (int p = threadIdx.x; p < c; p += kThreads) {
             const int j = sm.cols[n_ca + p];
@@ -243,13 +245,17 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
                 A.out.deep_score[o_deep + pos] = sc;
             }
             if (pos == rp.kneed - 1) s_kth = sc;
+            if (cert_count && sc > cert_thr) atomicAdd(&s_cert, 1);
         }
         for (int r = n + threadIdx.x; r < rp.kneed; r += kThreads) {  // fewer entries than the lists are wide
             if (r < rp.kmax && A.out.topk_idx) { A.out.topk_idx[o_top + r] = -1; A.out.topk_score[o_top + r] = -CUDART_INF; }
             if (A.out.deep_idx) { A.out.deep_idx[o_deep + r] = -1; A.out.deep_score[o_deep + r] = -CUDART_INF; }
         }
         __syncthreads();
-        if (certify && tau > -CUDART_INF_F) ok = ok && (n >= rp.kneed) && (s_kth > (double)tau + (double)eps);
+        if (certify && tau > -CUDART_INF_F) ok = ok && (n >= rp.kneed) && (s_kth > cert_thr);
+        // sharded runs certify globally: this rank's entries that are provably above every column it left out
+        // (counted among its best kneed + same-page entries, which is all the global test needs)
+        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.N + i] = tau > -CUDART_INF_F ? s_cert : rp.kneed;
         __syncthreads();
     }
     return ok;
@@ -265,9 +271,11 @@ __device__ __forceinline__ void stage_row(const RowArgs &A, const RowSmem &sm, i
 // ---------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads)
+// 64 registers -> 4 CTAs per SM: measured 110 ms at config 5 against 128 / 161 ms at 3 / 2 CTAs per SM
+__global__ void __launch_bounds__(kThreads, 4)
 rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_max,
-               int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter)
+               int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
+               const float *tau_global, int32_t *cert_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
@@ -300,7 +308,8 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 if (threadIdx.x == 0) s_tau = t;
             }
             __syncthreads();
-            const float tau_union = s_tau;  // the union of the lists is complete above this
+            // the union of the lists is complete above this (sharded runs: the maximum over all ranks)
+            const float tau_union = tau_global ? fmaxf(tau_global[i], s_tau) : s_tau;
             const uint64_t ik = A.img_key[i];
             const float eps = A.img_err[i] * 1.001f + eps_chunk_max[0] * 1.001f + (float)A.D * 2.4e-7f + 2e-6f;
             // attempt 0: the best K' of the union by approximate score; attempt 1: the whole union
@@ -324,7 +333,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 __syncthreads();
                 const int n_all = s_nca;
                 if (n_all + c > A.ent_cap) { ok = false; break; }
-                const bool truncate = attempt == 0 && n_all > L.kprime;
+                const bool truncate = !tau_global && attempt == 0 && n_all > L.kprime;
                 if (truncate) {
                     sort_keys(sm.buf, n_all);
                     // the union stays complete above the last kept approximate score
@@ -335,6 +344,10 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[e] = sm.buf[e].j;
                 __syncthreads();
                 if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)(n_ca + c));
+                if (tau_global) {  // certified after the cross-rank count, not here
+                    finish_row(A, sm, i, n_ca, false, s_tau, eps, cert_count);
+                    break;
+                }
                 ok = finish_row(A, sm, i, n_ca, true, s_tau, eps);
                 if (ok || !truncate) break;
                 // not certified at depth K': clear this row's ranks and retry with everything the lists hold
@@ -456,7 +469,7 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
 cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
-                           int32_t *error_flag, cudaStream_t st)
+                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, cudaStream_t st)
 {
     if (img.n == 0) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag);
@@ -468,7 +481,7 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     if (e != cudaSuccess) return e;
     int64_t grid = img.n < 148 * 16 ? img.n : 148 * 16;
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
-                                                           fail_count, cand_counter);
+                                                           fail_count, cand_counter, tau_global, cert_count);
     return cudaGetLastError();
 }
 
@@ -536,6 +549,28 @@ __global__ void pair_chunk_kernel(const int64_t *offsets, const int32_t *sorted_
         const int64_t p0 = offsets[i], c = offsets[i + 1] - p0, s0 = sp_start[i];
         for (int64_t p = lane; p < c; p += 32) pair_chunk[p0 + p] = (int64_t)sorted_chunk[s0 + p] + col_offset;
     }
+}
+
+// per-row completeness threshold of this rank's lists (sharded runs exchange it with an all-reduce max)
+__global__ void row_tau_kernel(CandLists L, int64_t N, float *tau_row)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rb = i >> 7;
+        const int r = (int)(i & 127);
+        float t = -CUDART_INF_F;
+        for (int l = 0; l < 2 * L.n_splits; ++l)
+            t = fmaxf(t, L.tau[(((int64_t)(l >> 1) * L.n_row_blocks + rb) * 2 + (l & 1)) * 128 + r]);
+        tau_row[i] = t;
+    }
+}
+
+cudaError_t launch_row_tau(const CandLists &L, int64_t N, float *tau_row, cudaStream_t st)
+{
+    if (N == 0) return cudaSuccess;
+    int64_t grid = (N + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    row_tau_kernel<<<(unsigned)grid, 256, 0, st>>>(L, N, tau_row);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pair_chunk(const PairIndex &px, int64_t N, int64_t col_offset, int64_t *pair_chunk,

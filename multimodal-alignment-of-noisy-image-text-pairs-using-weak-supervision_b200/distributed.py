@@ -3,6 +3,8 @@ images replicated.  torch.distributed (NCCL over NVLink) 
 three exchanges of a step; every merge/count/reduction on the data is a kernel of the
 CUDA library:
 
+  0. all-reduce(max) of the per-row list thresholds (and of the chunk rounding-error bound), then
+     all-reduce(sum) of the per-row certificate counts            (mmalign_fused_pass / rescore_pass)
   1. all-gather of each rank's exact top-K lists  -> mmalign_merge_topk      (global lists)
   2. all-gather of each rank's true pairs (image, chunk, score per schema)
         -> mmalign_count_beating against the rank's own exact lists
@@ -39,6 +41,8 @@ class ShardedScorer:
         if dist is None and world > 1:
             import torch.distributed as dist
         self.dist = dist
+        self._pinned = {}
+        self.MAX = getattr(getattr(dist, "ReduceOp", None), "MAX", "max") if dist is not None else "max"
 
     def run(self, *, schemas, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), kprime=0, host_outputs=False,
             candidates="all", path="auto"):
@@ -55,7 +59,20 @@ class ShardedScorer:
         import torch
         dist = self.dist
         G = self.world
-        r = eng.run(schemas, want=("topk", "pairs"), device_outputs=True, deep=True, **kw)
+        # 0. the depth K' of the candidate lists is shared by the ranks: every rank keeps its share, the ranks
+        #    agree on a per-row threshold, and each re-scores only what lies above it (~K'/G entries per row)
+        ses = eng.sharded_session(schemas, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight,
+                                  kprime=kprime, n_ranks=G)
+        tau = ses.fused_pass()
+        dist.all_reduce(tau, op=self.MAX)
+        eps = torch.tensor([ses.chunk_err_max()], dtype=torch.float32, device=tau.device)
+        dist.all_reduce(eps, op=self.MAX)
+        r, cert = ses.rescore_pass(tau, float(eps.item()))
+        dist.all_reduce(cert)
+        # a row is certified when, over all ranks, at least kneed entries lie provably above everything left out
+        bad = (cert < ses.kneed).any(dim=0) & torch.isfinite(tau)
+        rows = torch.nonzero(bad).to(torch.int32).flatten().contiguous()
+        ses.rescan_rows(rows)
         S, N, K = r["topk_idx"].shape
         # 1. global top-K lists
         gi = [torch.empty_like(r["topk_idx"]) for _ in range(G)]
@@ -102,8 +119,19 @@ class ShardedScorer:
         out = dict(topk_idx=m_idx, topk_score=m_score, pair_rank=pair_rank, pair_sim=r["pair_sim"], hits=hits_g,
                    rr_sum=rr_g, sim_sum=float(sim_g), num_pairs=P_g, stats=r["stats"],
                    metrics=metrics_from_sums(hits_g, rr_g, sim_g, P_g), d2h_bytes=0)
-        if host_outputs:
+        if host_outputs:  # page-locked host buffers, reused across steps
             for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim"):
-                out[k] = out[k].cpu().numpy()
+                t = out[k]
+                if not t.is_cuda:
+                    out[k] = t.numpy()
+                    continue
+                buf = self._pinned.get(k)
+                if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+                    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    self._pinned[k] = buf
+                buf.copy_(t, non_blocking=True)
+                out[k] = buf.numpy()
+            if self._pinned:
+                torch.cuda.synchronize()
             out["d2h_bytes"] = sum(out[k].nbytes for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim")) + 200
         return out

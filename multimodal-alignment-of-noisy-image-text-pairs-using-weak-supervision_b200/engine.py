@@ -143,12 +143,9 @@ class AlignmentEngine:
         return off, pc[:P]
 
     # -- scoring ----------------------------------------------------------------
-    def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
-            mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
-            path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
-            pinned_outputs=False, deep=False, stream=None):
+    @staticmethod
+    def _params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime, n_ranks=0):
         mask = schema_mask(schemas)
-        S = bin(mask).count("1")
         ks = [int(k) for k in k_values]
         prm = _native.Params()
         prm.schema_mask = mask
@@ -161,6 +158,14 @@ class AlignmentEngine:
         prm.lam_comb = float(weak_weight[0] + weak_weight[1]) if lam_comb is None else float(lam_comb)
         prm.path = PATHS[path] if isinstance(path, str) else int(path)
         prm.kprime = int(kprime)
+        prm.n_ranks = int(n_ranks)
+        return prm, mask, bin(mask).count("1"), ks
+
+    def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
+            mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
+            path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
+            pinned_outputs=False, deep=False, stream=None):
+        prm, mask, S, ks = self._params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime)
         kmax = max(ks) if ks else 0
         kneed = max(kmax, int(mrr_cutoff))
         P = self.num_pairs()
@@ -235,6 +240,11 @@ class AlignmentEngine:
         self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))
         return out
 
+    # -- sharded passes (device tensors; see include/mmalign.h and distributed.py) ------------
+    def sharded_session(self, schemas, *, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), lam_comb=None, kprime=0,
+                        n_ranks=1):
+        return _ShardedSession(self, schemas, k_values, mrr_cutoff, weak_weight, lam_comb, kprime, n_ranks)
+
     # -- multi-GPU helpers (device tensors) ---------------------------------------
     def merge_topk(self, gathered_idx, gathered_score):
         """[G, L, K] gathered lists -> merged [L, K] (torch CUDA tensors)."""
@@ -268,3 +278,63 @@ class AlignmentEngine:
                                                    ks.ctypes.data, len(ks), int(mrr_cutoff), hits.ctypes.data,
                                                    rr.ctypes.data, sim.ctypes.data, None))
         return hits, rr, float(sim[0])
+
+
+class _ShardedSession:
+    """The three passes of a sharded run on one rank (mmalign_fused_pass / rescore_pass / rescan_rows)."""
+
+    def __init__(self, eng, schemas, k_values, mrr_cutoff, weak_weight, lam_comb, kprime, n_ranks):
+        import torch
+        self.eng, self.torch = eng, torch
+        self.prm, self.mask, self.S, self.ks = eng._params(schemas, "all", k_values, mrr_cutoff, weak_weight, lam_comb,
+                                                           "auto", kprime, n_ranks)
+        self.kmax, self.kneed = max(self.ks), max(max(self.ks), int(mrr_cutoff))
+        self.dev = torch.device("cuda", eng.device)
+        self.out = None
+
+    def fused_pass(self):
+        """K1 on this rank's shard; returns tau_row [N] (device)."""
+        tau = self.torch.empty(self.eng.N, dtype=self.torch.float32, device=self.dev)
+        self.eng._check(self.eng._L.mmalign_fused_pass(self.eng._ctx, C.byref(self.prm), tau.data_ptr(), None))
+        return tau
+
+    def chunk_err_max(self) -> float:
+        v = C.c_float()
+        self.eng._check(self.eng._L.mmalign_chunk_err_max(self.eng._ctx, C.byref(v)))
+        return float(v.value)
+
+    def _outputs(self):
+        t, S, N, P = self.torch, self.S, self.eng.N, self.eng.num_pairs()
+        res = dict(topk_idx=t.empty((S, N, self.kmax), dtype=t.int64, device=self.dev),
+                   topk_score=t.empty((S, N, self.kmax), dtype=t.float64, device=self.dev),
+                   pair_rank=t.empty((S, P), dtype=t.int32, device=self.dev),
+                   pair_sim=t.empty((P,), dtype=t.float64, device=self.dev),
+                   pair_score=t.empty((S, P), dtype=t.float64, device=self.dev),
+                   deep_idx=t.empty((S, N, self.kneed), dtype=t.int64, device=self.dev),
+                   deep_score=t.empty((S, N, self.kneed), dtype=t.float64, device=self.dev))
+        out = _native.Out()
+        for k, v in res.items():
+            setattr(out, k, v.data_ptr())
+        return res, out
+
+    def rescore_pass(self, tau_global, eps_chunk_global: float):
+        """Exact scores of this rank's entries above the global tau.  Returns (results, cert_count [S,N])."""
+        res, out = self._outputs()
+        stats = np.zeros(8, np.int64)
+        out.stats = stats.ctypes.data
+        cert = self.torch.empty((self.S, self.eng.N), dtype=self.torch.int32, device=self.dev)
+        self.eng._check(self.eng._L.mmalign_rescore_pass(self.eng._ctx, C.byref(self.prm), tau_global.data_ptr(),
+                                                         C.c_float(eps_chunk_global), C.byref(out), cert.data_ptr(), None))
+        res["stats"] = dict(rows_rescanned=0, candidates_rescored=int(stats[1]), fused_launches=int(stats[2]),
+                            kernel_launches=int(stats[3]), kprime=int(stats[4]), fused_us=int(stats[5]),
+                            rescore_us=int(stats[6]), exact_scan_us=0)
+        self.res, self.out = res, out
+        return res, cert
+
+    def rescan_rows(self, rows):
+        """Exact scan of `rows` (int32 device tensor) into the outputs of the last rescore_pass."""
+        if rows.numel():
+            self.out.stats = None
+            self.eng._check(self.eng._L.mmalign_rescan_rows(self.eng._ctx, C.byref(self.prm), rows.data_ptr(),
+                                                            int(rows.numel()), C.byref(self.out), None))
+            self.res["stats"]["rows_rescanned"] = int(rows.numel())

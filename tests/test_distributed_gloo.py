@@ -27,8 +27,27 @@ class OracleEngine:
         self.o, self.img, self.chk, self.T, self.off0 = oracle, img, chk_shard, T, col_offset
         self.N = len(img["key"])
 
-    def run(self, schemas, *, want, device_outputs, deep=False, candidates, k_values, mrr_cutoff, weak_weight,
-            kprime, path):
+    def sharded_session(self, schemas, *, k_values, mrr_cutoff, weak_weight, kprime, n_ranks):
+        eng = self
+
+        class Session:
+            kneed = max(max(k_values), mrr_cutoff)
+
+            def fused_pass(self):  # the stand-in keeps every local column: complete above -inf
+                return torch.full((eng.N,), float("-inf"))
+
+            def chunk_err_max(self):
+                return 0.0
+
+            def rescore_pass(self, tau, eps):
+                r = eng.run(schemas, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight)
+                return r, torch.full((4, eng.N), self.kneed, dtype=torch.int32)
+
+            def rescan_rows(self, rows):
+                assert rows.numel() == 0
+        return Session()
+
+    def run(self, schemas, *, k_values, mrr_cutoff, weak_weight, **_):
         kmax, kneed = max(k_values), max(max(k_values), mrr_cutoff)
         lam = (weak_weight[0], weak_weight[1], weak_weight[0] + weak_weight[1])
         a = self.o.evaluate(self.img, self.chk, T=self.T, schema_mask=MASK, candidates="all", lam=lam, kmax=kneed, cutoff=kneed)

@@ -1,0 +1,88 @@
+"""The multi-rank path with the REAL kernels on one GPU: two ranks run as threads, each with its own
+engine and chunk shard; a thread-barrier stand-in for torch.distributed carries the three exchanges
+(the kernels of the ranks never wait on each other, only the host threads do).  Result must equal the
+single-process oracle.  The real NCCL run is tests/test_gpu_nccl.py (needs 2 GPUs)."""
+import importlib
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import PKG_NAME
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
+
+ALL4 = ["vanilla_clip", "clip_lexical", "clip_positional", "clip_combined"]
+
+
+class ThreadDist:
+    def __init__(self, world):
+        self.world, self.slots, self.bar = world, {}, threading.Barrier(world)
+
+    def bind(self, rank):
+        d = self
+        class _D:
+            def all_gather(self, out, t):
+                torch.cuda.synchronize()
+                d.slots[rank] = t
+                d.bar.wait()
+                for r in range(d.world):
+                    out[r].copy_(d.slots[r])
+                torch.cuda.synchronize()
+                d.bar.wait()
+
+            def all_reduce(self, t, op="sum"):
+                torch.cuda.synchronize()
+                d.slots[rank] = t.clone()
+                d.bar.wait()
+                if op == "max":
+                    s = torch.stack([d.slots[r] for r in range(d.world)]).amax(dim=0)
+                else:
+                    s = sum(d.slots[r] for r in range(d.world))
+                torch.cuda.synchronize()
+                d.bar.wait()
+                t.copy_(s)
+        return _D()
+
+
+@pytest.mark.parametrize("N,M,D,world", [(300, 2003, 128, 2), (200, 5000, 512, 4)])
+def test_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
+    distributed = importlib.import_module(PKG_NAME + ".distributed")
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=41)
+    ks, cutoff, lam = (1, 5, 10, 20), 100, (0.3, 0.2)
+    td = ThreadDist(world)
+    results, errors = {}, []
+
+    def rank_main(rank):
+        try:
+            torch.cuda.set_device(0)
+            lo, hi = distributed.shard_range(M, world, rank)
+            eng = pkg.AlignmentEngine(0)
+            eng.set_images(img["emb"], img["key"], img["bbox"], None)
+            eng.set_chunks(chk["emb"][lo:hi], chk["key"][lo:hi], chk["bbox"][lo:hi], chk["terms"][lo:hi], n_terms=512,
+                           col_offset=lo)
+            sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=td.bind(rank))
+            results[rank] = (lo, hi, sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True))
+            eng.close()
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            td.bar.abort()
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    o = oracle.evaluate(img, chk, T=512, schema_mask=15, candidates="all", lam=(lam[0], lam[1], lam[0] + lam[1]),
+                        kmax=max(ks), cutoff=cutoff)
+    for rank in range(world):
+        lo, hi, r = results[rank]
+        assert np.array_equal(r["topk_idx"], o["topk_idx"]) and np.array_equal(r["topk_score"], o["topk_score"])
+        mine = (o["pair_chunk"] >= lo) & (o["pair_chunk"] < hi)
+        assert np.array_equal(r["pair_rank"], o["pair_rank"][:, mine])
+        assert np.array_equal(r["pair_sim"], o["pair_sim"][mine])
+        assert r["num_pairs"] == len(o["pair_chunk"])
+        for si in range(4):
+            for q, k in enumerate(ks):
+                assert r["hits"][si, q] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
