@@ -239,7 +239,8 @@ def run_ours(args):
         t3 = time.perf_counter()
         step_ms.setdefault("host" if host_out else "device", []).append(round(1e3 * (t3 - t0), 1))
         phase_ms["host" if host_out else "device"] = dict(set_images=1e3 * (t1 - t0), set_chunks=1e3 * (t2 - t1),
-                                                          run=1e3 * (t3 - t2), **{k: v for k, v in out["stats"].items() if k.endswith("_us")})
+                                                          run=1e3 * (t3 - t2), **{k: v for k, v in out["stats"].items() if k.endswith("_us")},
+                                                          **({"exchange": out["phases_ms"]} if "phases_ms" in out else {}))
         return out
 
     def barrier():

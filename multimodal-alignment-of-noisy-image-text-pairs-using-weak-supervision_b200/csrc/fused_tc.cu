@@ -22,6 +22,7 @@
 #include <math_constants.h>
 #include <stdio.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace mma {
 
@@ -414,6 +415,12 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     tc_fence_before();  // last read of this accumulator: hand it back to the MMA warp
                     mbar_arrive(bar_tempty + 8u * acc);
                     process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime);
+                    // Routine compaction happens HERE, after the accumulator went back to the MMA warp, so that its
+                    // global-memory latency is off the MMA critical path (the check inside process_chunk only fires
+                    // when a single tile overflows the remaining room, i.e. in the first tiles of a sweep).
+                    __syncwarp();
+                    if (__any_sync(0xFFFFFFFFu, n > CAP - 72))
+                        compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > CAP - 72);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }

@@ -21,7 +21,7 @@
 
 namespace mma {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;  // small CTAs: 8 rows in flight per SM hide the per-row chain of dependent loads
 constexpr int kWarps = kThreads / 32;
 constexpr int kEntCapMax = 1024;  // candidates + same-page entries handled per row (shared-memory sized per launch)
 constexpr int kSpCapMax = 512;    // same-page chunks per image
@@ -50,6 +50,8 @@ struct RowSmem {
     double *cosv;               // [A.ent_cap] exact cosine of every entry
     double *sp_s;               // [A.sp_cap] ranking score of the same-page entries in the current schema
     unsigned long long *sp_k;   // [A.sp_cap] its order-preserving key
+    double *sp_lex, *sp_pos;    // [A.sp_cap] raw lexical / positional score of the same-page entries
+    int32_t *sp_cols;           // [A.sp_cap] the row's same-page chunks (local index, increasing)
     int32_t *cols;              // [A.ent_cap]
     float *a;                   // [D]
 };
@@ -57,7 +59,7 @@ struct RowSmem {
 __host__ __device__ inline size_t row_smem_bytes(int D, int ent_cap, int sp_cap)
 {
     return (size_t)ent_cap * (sizeof(Key) + sizeof(double) + sizeof(int32_t)) +
-           (size_t)sp_cap * (sizeof(double) + sizeof(unsigned long long)) + (size_t)D * sizeof(float);
+           (size_t)sp_cap * (3 * sizeof(double) + sizeof(unsigned long long) + sizeof(int32_t)) + (size_t)D * sizeof(float);
 }
 
 __device__ __forceinline__ RowSmem carve(unsigned char *base, int ent_cap, int sp_cap)
@@ -71,8 +73,14 @@ __device__ __forceinline__ RowSmem carve(unsigned char *base, int ent_cap, int s
     base += (size_t)sp_cap * sizeof(double);
     r.sp_k = reinterpret_cast<unsigned long long *>(base);
     base += (size_t)sp_cap * sizeof(unsigned long long);
+    r.sp_lex = reinterpret_cast<double *>(base);
+    base += (size_t)sp_cap * sizeof(double);
+    r.sp_pos = reinterpret_cast<double *>(base);
+    base += (size_t)sp_cap * sizeof(double);
     r.cols = reinterpret_cast<int32_t *>(base);
     base += (size_t)ent_cap * sizeof(int32_t);
+    r.sp_cols = reinterpret_cast<int32_t *>(base);
+    base += (size_t)sp_cap * sizeof(int32_t);
     r.a = reinterpret_cast<float *>(base);
     return r;
 }
@@ -90,6 +98,7 @@ struct RowArgs {
     Outputs out;
     int32_t *error_flag;  // set to 1 when a capacity limit is hit
     int ent_cap, sp_cap;  // shared-memory capacities of this launch (>= 256 / >= 8)
+    bool need_lex, need_pos;  // some requested schema uses the lexical / positional term
 };
 
 __device__ __forceinline__ int next_pow2(int n)
@@ -105,28 +114,40 @@ __device__ __forceinline__ int next_pow2(int n)
 __device__ void sort_keys(Key *buf, int n)
 {
     const int tid = threadIdx.x;
-    if (n <= kThreads) {
-        Key me = tid < n ? buf[tid] : key_pad();
+    if (n <= 2 * kThreads) {
+        // keys tid and tid + kThreads live in registers
+        Key me[2];
+        me[0] = tid < n ? buf[tid] : key_pad();
+        me[1] = tid + kThreads < n ? buf[tid + kThreads] : key_pad();
         __syncthreads();
-        for (int k = 2; k <= kThreads; k <<= 1) {
+        for (int k = 2; k <= 2 * kThreads; k <<= 1) {
             for (int j = k >> 1; j > 0; j >>= 1) {
-                Key o;
-                if (j >= 32) {
-                    buf[tid] = me;
+                Key o[2];
+                if (j == kThreads) {
+                    o[0] = me[1]; o[1] = me[0];
+                } else if (j >= 32) {
+                    buf[tid] = me[0]; buf[tid + kThreads] = me[1];
                     __syncthreads();
-                    o = buf[tid ^ j];
+                    o[0] = buf[tid ^ j]; o[1] = buf[(tid ^ j) + kThreads];
                     __syncthreads();
                 } else {
-                    o.k = __shfl_xor_sync(0xFFFFFFFFu, me.k, j);
-                    o.j = __shfl_xor_sync(0xFFFFFFFFu, me.j, j);
-                    o.e = __shfl_xor_sync(0xFFFFFFFFu, me.e, j);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        o[r].k = __shfl_xor_sync(0xFFFFFFFFu, me[r].k, j);
+                        o[r].j = __shfl_xor_sync(0xFFFFFFFFu, me[r].j, j);
+                        o[r].e = __shfl_xor_sync(0xFFFFFFFFu, me[r].e, j);
+                    }
                 }
-                const bool lower = (tid & j) == 0, up = (tid & k) == 0;
-                const bool o_first = key_before(o.k, o.j, me.k, me.j);
-                if ((lower == up) ? o_first : !o_first) me = o;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int i = tid + r * kThreads;
+                    const bool lower = (i & j) == 0, up = (i & k) == 0;
+                    const bool o_first = key_before(o[r].k, o[r].j, me[r].k, me[r].j);
+                    if ((lower == up) ? o_first : !o_first) me[r] = o[r];
+                }
             }
         }
-        buf[tid] = me;
+        buf[tid] = me[0]; buf[tid + kThreads] = me[1];
         __syncthreads();
         return;
     }
@@ -165,7 +186,18 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
     const int n = n_ca + c;
     const int d4 = A.D >> 2;
     const RunParams &rp = A.rp;
-    for (int p = threadIdx.x; p < c; p += kThreads) sm.cols[n_ca + p] = A.sorted_chunk[A.sp_start[i] + p];
+    // same-page entries: columns were staged by the caller (sm.sp_cols); their raw weak terms are schema-independent
+    for (int p = threadIdx.x; p < c; p += kThreads) {
+        const int j = sm.sp_cols[p];
+        sm.cols[n_ca + p] = j;
+        double lex = 0.0, pos = 0.0;
+        if (A.need_lex)
+            lex = lexical_score(term_hits(A.chk_terms + (int64_t)j * A.term_words,
+                                          A.img_terms ? A.img_terms + i * A.term_words : nullptr, A.term_words), rp.n_terms);
+        if (A.need_pos) pos = positional_score(A.img_bbox + 4 * i, A.chk_bbox + 4 * (int64_t)j);
+        sm.sp_lex[p] = lex;
+        sm.sp_pos[p] = pos;
+    }
     __syncthreads();
     // exact cosine of every entry
     const float na = A.img_n2[i];
@@ -196,16 +228,11 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         if (threadIdx.x == 0) { s_kth = -CUDART_INF; s_cert = 0; }
         // ranking score of the same-page entries in this schema
         for (int p = threadIdx.x; p < c; p += kThreads) {
-            const int j = sm.cols[n_ca + p];
             double w = 0.0;
             if (s != 0) {
-                double lex = 0.0, pos = 0.0, rec[3];
-                if (schema_uses_lex(s))
-                    lex = lexical_score(term_hits(A.chk_terms + (int64_t)j * A.term_words,
-                                                  A.img_terms ? A.img_terms + i * A.term_words : nullptr,
-                                                  A.term_words), rp.n_terms);
-                if (schema_uses_pos(s)) pos = positional_score(A.img_bbox + 4 * i, A.chk_bbox + 4 * (int64_t)j);
-                weak_records(schema_uses_lex(s), schema_uses_pos(s), lex, pos, rec);
+                double rec[3];
+                weak_records(schema_uses_lex(s), schema_uses_pos(s), schema_uses_lex(s) ? sm.sp_lex[p] : 0.0,
+                             schema_uses_pos(s) ? sm.sp_pos[p] : 0.0, rec);
                 w = rp.lam_lex * rec[0] + rp.lam_pos * rec[1] + rp.lam_comb * rec[2];
             }
             const double sc = sm.cosv[n_ca + p] + w;
@@ -266,13 +293,18 @@ __device__ __forceinline__ void stage_row(const RowArgs &A, const RowSmem &sm, i
     const float4 *src = reinterpret_cast<const float4 *>(A.img_emb + i * A.D);
     float4 *dst = reinterpret_cast<float4 *>(sm.a);
     for (int c = threadIdx.x; c < (A.D >> 2); c += kThreads) dst[c] = src[c];
+    const int cnt = (int)(A.offsets[i + 1] - A.offsets[i]);
+    if (cnt <= A.sp_cap) {
+        const int64_t s0 = A.sp_start[i];
+        for (int p = threadIdx.x; p < cnt; p += kThreads) sm.sp_cols[p] = A.sorted_chunk[s0 + p];
+    }
 }
 
 // ---------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------
-// 64 registers -> 4 CTAs per SM: measured 110 ms at config 5 against 128 / 161 ms at 3 / 2 CTAs per SM
-__global__ void __launch_bounds__(kThreads, 4)
+// 64 registers -> 8 CTAs of 128 threads per SM (measured at config 5 with 256-thread CTAs: 110 ms at 64 registers against 128 / 161 ms at 80 / 124)
+__global__ void __launch_bounds__(kThreads, 8)
 rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_max,
                int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
                const float *tau_global, int32_t *cert_count)
@@ -324,7 +356,12 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                         const uint64_t k = keys[e];
                         const uint32_t col = cand_col(k);
                         const float sa = cand_score(k);
-                        if (sa > tau_union && (ik == MMALIGN_NULL_KEY || A.chk_key[col] != ik)) {
+                        bool same_page = false;  // same-page chunks enter through the pair index, not through the lists
+                        if (ik != MMALIGN_NULL_KEY) {
+                            if (c <= 32) { for (int q = 0; q < c; ++q) same_page = same_page || sm.sp_cols[q] == (int32_t)col; }
+                            else same_page = A.chk_key[col] == ik;
+                        }
+                        if (sa > tau_union && !same_page) {
                             const int pos = atomicAdd(&s_nca, 1);
                             if (pos < A.ent_cap) { Key x; x.k = ord64((double)sa); x.j = (int32_t)col; x.e = (int32_t)__float_as_int(sa); sm.buf[pos] = x; }
                         }
@@ -463,6 +500,11 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
     A.offsets = px.offsets; A.sorted_chunk = px.sorted_chunk; A.sp_start = px.sp_start; A.P = px.P;
     A.rp = rp; A.out = out; A.error_flag = error_flag;
     A.ent_cap = kEntCapMax; A.sp_cap = kSpCapMax;
+    A.need_lex = A.need_pos = false;
+    for (int q = 0; q < rp.S; ++q) {
+        A.need_lex = A.need_lex || rp.schema[q] == 1 || rp.schema[q] == 3;
+        A.need_pos = A.need_pos || rp.schema[q] == 2 || rp.schema[q] == 3;
+    }
     return A;
 }
 

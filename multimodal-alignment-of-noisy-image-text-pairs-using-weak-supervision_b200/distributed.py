@@ -56,23 +56,34 @@ class ShardedScorer:
             r["d2h_bytes"] = sum(r[k].nbytes for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim")) + 200 \
                 if host_outputs else 0
             return r
+        import time
         import torch
         dist = self.dist
         G = self.world
+        marks = []
+
+        def mark(name):
+            torch.cuda.synchronize() if torch.cuda.is_available() else None
+            marks.append((name, time.perf_counter()))
+        mark("start")
         # 0. the depth K' of the candidate lists is shared by the ranks: every rank keeps its share, the ranks
         #    agree on a per-row threshold, and each re-scores only what lies above it (~K'/G entries per row)
         ses = eng.sharded_session(schemas, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight,
                                   kprime=kprime, n_ranks=G)
         tau = ses.fused_pass()
+        mark("fused_pass")
         dist.all_reduce(tau, op=self.MAX)
         eps = torch.tensor([ses.chunk_err_max()], dtype=torch.float32, device=tau.device)
         dist.all_reduce(eps, op=self.MAX)
+        mark("tau exchange")
         r, cert = ses.rescore_pass(tau, float(eps.item()))
+        mark("rescore_pass")
         dist.all_reduce(cert)
         # a row is certified when, over all ranks, at least kneed entries lie provably above everything left out
         bad = (cert < ses.kneed).any(dim=0) & torch.isfinite(tau)
         rows = torch.nonzero(bad).to(torch.int32).flatten().contiguous()
         ses.rescan_rows(rows)
+        mark("certificate + rescan")
         S, N, K = r["topk_idx"].shape
         # 1. global top-K lists
         gi = [torch.empty_like(r["topk_idx"]) for _ in range(G)]
@@ -81,6 +92,7 @@ class ShardedScorer:
         dist.all_gather(gs, r["topk_score"].contiguous())
         m_idx, m_score = eng.merge_topk(torch.stack(gi).view(G, S * N, K), torch.stack(gs).view(G, S * N, K))
         m_idx, m_score = m_idx.view(S, N, K), m_score.view(S, N, K)
+        mark("top-K gather + merge")
         # 2. global rank of every true pair
         off, pc = eng.pairs_device()
         P = int(pc.shape[0])
@@ -107,18 +119,21 @@ class ShardedScorer:
         kneed = r["deep_idx"].shape[2]
         mine = counts[:, self.rank * Pmax:self.rank * Pmax + P]
         pair_rank = torch.where(mine < kneed, mine + 1, torch.zeros_like(mine)).to(torch.int32).contiguous()
+        mark("pair ranks")
         # 3. metric sums
         hits, rr, sim = eng.reduce_metrics(pair_rank, r["pair_sim"], k_values, mrr_cutoff)
         packed = torch.tensor(np.concatenate([hits.reshape(-1).astype(np.float64), rr, [sim, float(P)]]),
                               dtype=torch.float64, device=pc.device)
         dist.all_reduce(packed)
         packed = packed.cpu().numpy()
+        mark("metric sums")
         nk = len(k_values)
         hits_g = np.rint(packed[:S * nk]).astype(np.int64).reshape(S, nk)
         rr_g, sim_g, P_g = packed[S * nk:S * nk + S], packed[-2], int(round(packed[-1]))
         out = dict(topk_idx=m_idx, topk_score=m_score, pair_rank=pair_rank, pair_sim=r["pair_sim"], hits=hits_g,
                    rr_sum=rr_g, sim_sum=float(sim_g), num_pairs=P_g, stats=r["stats"],
-                   metrics=metrics_from_sums(hits_g, rr_g, sim_g, P_g), d2h_bytes=0)
+                   metrics=metrics_from_sums(hits_g, rr_g, sim_g, P_g), d2h_bytes=0,
+                   phases_ms={b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(marks, marks[1:])})
         if host_outputs:  # page-locked host buffers, reused across steps
             for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim"):
                 t = out[k]
