@@ -479,7 +479,7 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     // spreads above the mean, so the union's depth is ~ L*k*(1 - z_L/sqrt(k)); solve that for depth = K'.
     {
         const double L = (double)lists_per_row, share = (double)p.kprime / L;
-        const double z = sqrt(2.0 * log(L));
+        const double z = sqrt(2.0 * log(L)) + 0.4;  // + 0.4: one uncertified row in 1e6 still costs a rescan launch
         const double rk = 0.5 * (z + sqrt(z * z + 4.0 * share));
         p.kprime_list = (int)ceil(rk * rk) + 2;
     }

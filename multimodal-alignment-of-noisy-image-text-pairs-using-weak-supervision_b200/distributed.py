@@ -5,7 +5,8 @@ CUDA library:
 
   0. all-reduce(max) of the per-row list thresholds (and of the chunk rounding-error bound), then
      all-reduce(sum) of the per-row certificate counts            (mmalign_fused_pass / rescore_pass)
-  1. all-gather of each rank's exact top-K lists  -> mmalign_merge_topk      (global lists)
+  1. all-to-all of each rank's exact top-K lists  -> mmalign_merge_topk: rank g merges and owns the lists
+     of query slab g (`topk_row0`, ceil(N/G) rows)
   2. all-gather of each rank's true pairs (image, chunk, score per schema)
         -> mmalign_count_beating against the rank's own exact lists
         -> all-reduce(sum) of the counts            (global rank of every true pair)
@@ -85,13 +86,32 @@ class ShardedScorer:
         ses.rescan_rows(rows)
         mark("certificate + rescan")
         S, N, K = r["topk_idx"].shape
-        # 1. global top-K lists
-        gi = [torch.empty_like(r["topk_idx"]) for _ in range(G)]
-        gs = [torch.empty_like(r["topk_score"]) for _ in range(G)]
-        dist.all_gather(gi, r["topk_idx"].contiguous())
-        dist.all_gather(gs, r["topk_score"].contiguous())
-        m_idx, m_score = eng.merge_topk(torch.stack(gi).view(G, S * N, K), torch.stack(gs).view(G, S * N, K))
-        m_idx, m_score = m_idx.view(S, N, K), m_score.view(S, N, K)
+        # 1. global top-K lists, query-sharded: rank g merges the lists of query slab g (one all-to-all; every
+        #    rank receives 1/G of what an all-gather would deliver) and owns the result for those queries
+        slab = -(-N // G)
+        row0 = min(N, self.rank * slab)
+        rows_here = max(0, min(N, row0 + slab) - row0)
+        if hasattr(dist, "all_to_all_single"):
+            pad = slab * G - N
+            ti, ts = r["topk_idx"], r["topk_score"]
+            if pad:
+                ti = torch.cat([ti, ti.new_full((S, pad, K), -1)], dim=1)
+                ts = torch.cat([ts, ts.new_full((S, pad, K), float("-inf"))], dim=1)
+            send_i = ti.view(S, G, slab, K).permute(1, 0, 2, 3).contiguous()
+            send_s = ts.view(S, G, slab, K).permute(1, 0, 2, 3).contiguous()
+            recv_i, recv_s = torch.empty_like(send_i), torch.empty_like(send_s)
+            dist.all_to_all_single(recv_i, send_i)
+            dist.all_to_all_single(recv_s, send_s)
+            m_idx, m_score = eng.merge_topk(recv_i.view(G, S * slab, K), recv_s.view(G, S * slab, K))
+            m_idx, m_score = m_idx.view(S, slab, K)[:, :rows_here], m_score.view(S, slab, K)[:, :rows_here]
+        else:  # backends without all-to-all: all-gather, merge everything, keep the slab
+            gi = [torch.empty_like(r["topk_idx"]) for _ in range(G)]
+            gs = [torch.empty_like(r["topk_score"]) for _ in range(G)]
+            dist.all_gather(gi, r["topk_idx"].contiguous())
+            dist.all_gather(gs, r["topk_score"].contiguous())
+            m_idx, m_score = eng.merge_topk(torch.stack(gi).view(G, S * N, K), torch.stack(gs).view(G, S * N, K))
+            m_idx = m_idx.view(S, N, K)[:, row0:row0 + rows_here]
+            m_score = m_score.view(S, N, K)[:, row0:row0 + rows_here]
         mark("top-K gather + merge")
         # 2. global rank of every true pair
         off, pc = eng.pairs_device()
@@ -132,7 +152,7 @@ class ShardedScorer:
         rr_g, sim_g, P_g = packed[S * nk:S * nk + S], packed[-2], int(round(packed[-1]))
         out = dict(topk_idx=m_idx, topk_score=m_score, pair_rank=pair_rank, pair_sim=r["pair_sim"], hits=hits_g,
                    rr_sum=rr_g, sim_sum=float(sim_g), num_pairs=P_g, stats=r["stats"],
-                   metrics=metrics_from_sums(hits_g, rr_g, sim_g, P_g), d2h_bytes=0,
+                   metrics=metrics_from_sums(hits_g, rr_g, sim_g, P_g), d2h_bytes=0, topk_row0=row0,
                    phases_ms={b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(marks, marks[1:])})
         if host_outputs:  # page-locked host buffers, reused across steps
             for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim"):

@@ -32,6 +32,16 @@ class ThreadDist:
                 torch.cuda.synchronize()
                 d.bar.wait()
 
+            def all_to_all_single(self, out, inp):
+                torch.cuda.synchronize()
+                d.slots[rank] = inp
+                d.bar.wait()
+                n = inp.shape[0] // d.world
+                for r in range(d.world):
+                    out[r * n:(r + 1) * n].copy_(d.slots[r][rank * n:(rank + 1) * n])
+                torch.cuda.synchronize()
+                d.bar.wait()
+
             def all_reduce(self, t, op="sum"):
                 torch.cuda.synchronize()
                 d.slots[rank] = t.clone()
@@ -46,7 +56,7 @@ class ThreadDist:
         return _D()
 
 
-@pytest.mark.parametrize("N,M,D,world", [(300, 2003, 128, 2), (200, 5000, 512, 4)])
+@pytest.mark.parametrize("N,M,D,world", [(300, 2003, 128, 2), (201, 5000, 512, 4), (130, 4000, 64, 8)])
 def test_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
     distributed = importlib.import_module(PKG_NAME + ".distributed")
     img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=41)
@@ -78,7 +88,10 @@ def test_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
                         kmax=max(ks), cutoff=cutoff)
     for rank in range(world):
         lo, hi, r = results[rank]
-        assert np.array_equal(r["topk_idx"], o["topk_idx"]) and np.array_equal(r["topk_score"], o["topk_score"])
+        q0 = r["topk_row0"]
+        q1 = q0 + r["topk_idx"].shape[1]
+        assert q1 - q0 == max(0, min(N, q0 + -(-N // world)) - q0)
+        assert np.array_equal(r["topk_idx"], o["topk_idx"][:, q0:q1]) and np.array_equal(r["topk_score"], o["topk_score"][:, q0:q1])
         mine = (o["pair_chunk"] >= lo) & (o["pair_chunk"] < hi)
         assert np.array_equal(r["pair_rank"], o["pair_rank"][:, mine])
         assert np.array_equal(r["pair_sim"], o["pair_sim"][mine])
