@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kprime", type=int, default=0)
+    ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather"],
+                    help="multi-GPU: alltoall = contraction sharded by chunk columns, rescoring by query rows (default); "
+                         "allgather = fully sharded variant (distributed.AllGatherScorer)")
     return ap.parse_args()
 
 
@@ -196,10 +199,13 @@ def run_reference(args):
 
 
 def workload(args, G):
+    how = (f"each of {G} GPU(s) ingests 1/{G} of the images and chunks (NVLink all-gather replicates them inside the step); "
+           "contraction sharded by chunk columns, exact rescoring by query rows" if getattr(args, "exchange", "alltoall") == "alltoall"
+           else f"chunks sharded over {G} GPU(s), images replicated")
     return {"workload": f"BASELINE config 5: {args.N} images x {args.M} chunks, D={args.D}, all four schemas in one pass, "
                         f"K in {list(K_VALUES)} + MRR@{MRR_CUTOFF}, candidates=all, weak_weight={WEAK}",
             "N": args.N, "M": args.M, "D": args.D, "schemas": 4, "k_values": list(K_VALUES), "mrr_cutoff": MRR_CUTOFF,
-            "sharding": f"chunks sharded over {G} GPU(s), images replicated",
+            "sharding": how,
             "l2": "inputs (2 x %.1f GB bf16 operands) are far larger than the 126 MB L2" % (args.N * args.D * 2 / 1e9)}
 
 
@@ -222,26 +228,44 @@ def run_ours(args):
     P = peaks()
     N, M, D = args.N, args.M, args.D
     r0, r1 = distributed.shard_range(M, world, rank)
-    img, chk, meta = synthetic.make_torch(N, M, D, T=T_TERMS, device=dev, row0=r0, rows=r1 - r0)
     eng = pkg.AlignmentEngine(local)
-    sharded = distributed.ShardedScorer(eng, world, rank, dev)
     run_kw = dict(schemas=SCHEMAS, k_values=K_VALUES, mrr_cutoff=MRR_CUTOFF, weak_weight=WEAK, kprime=args.kprime)
-
     phase_ms, step_ms = {}, {}
+    if args.exchange == "alltoall" or world == 1:
+        # every rank ingests its slab of the images and its shard of the chunks
+        i0, i1 = distributed.slab_range(N, world, rank)
+        img, chk, meta = synthetic.make_torch(N, M, D, T=T_TERMS, device=dev, row0=r0, rows=r1 - r0, img_row0=i0,
+                                              img_rows=i1 - i0)
+        sharded = distributed.ShardedScorer(eng, world, rank, dev)
 
-    def step(im, ck, host_out):
-        t0 = time.perf_counter()
-        eng.set_images(im["emb"], im["key"], im["bbox"], im["terms"])
-        t1 = time.perf_counter()
-        eng.set_chunks(ck["emb"], ck["key"], ck["bbox"], ck["terms"], n_terms=T_TERMS, col_offset=r0)
-        t2 = time.perf_counter()
-        out = sharded.run(host_outputs=host_out, **run_kw)
-        t3 = time.perf_counter()
-        step_ms.setdefault("host" if host_out else "device", []).append(round(1e3 * (t3 - t0), 1))
-        phase_ms["host" if host_out else "device"] = dict(set_images=1e3 * (t1 - t0), set_chunks=1e3 * (t2 - t1),
-                                                          run=1e3 * (t3 - t2), **{k: v for k, v in out["stats"].items() if k.endswith("_us")},
-                                                          **({"exchange": out["phases_ms"]} if "phases_ms" in out else {}))
-        return out
+        def step(im, ck, host_out):
+            t0 = time.perf_counter()
+            sharded.load(im, ck, N=N, M=M, n_terms=T_TERMS)
+            t2 = time.perf_counter()
+            out = sharded.run(host_outputs=host_out, **run_kw)
+            t3 = time.perf_counter()
+            step_ms.setdefault("host" if host_out else "device", []).append(round(1e3 * (t3 - t0), 1))
+            phase_ms["host" if host_out else "device"] = dict(load=1e3 * (t2 - t0), run=1e3 * (t3 - t2),
+                                                              **{k: v for k, v in out["stats"].items() if k.endswith("_us")},
+                                                              **({"exchange": out["phases_ms"]} if "phases_ms" in out else {}))
+            return out
+    else:
+        img, chk, meta = synthetic.make_torch(N, M, D, T=T_TERMS, device=dev, row0=r0, rows=r1 - r0)
+        sharded = distributed.AllGatherScorer(eng, world, rank, dev)
+
+        def step(im, ck, host_out):
+            t0 = time.perf_counter()
+            eng.set_images(im["emb"], im["key"], im["bbox"], im["terms"])
+            t1 = time.perf_counter()
+            eng.set_chunks(ck["emb"], ck["key"], ck["bbox"], ck["terms"], n_terms=T_TERMS, col_offset=r0)
+            t2 = time.perf_counter()
+            out = sharded.run(host_outputs=host_out, **run_kw)
+            t3 = time.perf_counter()
+            step_ms.setdefault("host" if host_out else "device", []).append(round(1e3 * (t3 - t0), 1))
+            phase_ms["host" if host_out else "device"] = dict(set_images=1e3 * (t1 - t0), set_chunks=1e3 * (t2 - t1),
+                                                              run=1e3 * (t3 - t2), **{k: v for k, v in out["stats"].items() if k.endswith("_us")},
+                                                              **({"exchange": out["phases_ms"]} if "phases_ms" in out else {}))
+            return out
 
     def barrier():
         if world > 1:
@@ -290,9 +314,11 @@ def run_ours(args):
         for _ in range(min(args.warmup, 2)):
             res_h = step(img_h, chk_h, True)
         ms_h, res_h = timed(lambda: step(img_h, chk_h, True), args.steps)
-        d2h = res_h["d2h_bytes"]
-        e2e = {"value": N / (ms_h / args.steps / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_h / args.steps}
+        io = torch.tensor([float(h2d), float(res_h["d2h_bytes"])], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(io)  # bytes of the whole job: every rank copies its own shard in and its own results out
+        e2e = {"value": N / (ms_h / args.steps / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": int(io[0].item()),
+               "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_h / args.steps}
         del img_h, chk_h
 
     if rank != 0:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MMALIGN_ABI_VERSION 1
+#define MMALIGN_ABI_VERSION 2
 #define MMALIGN_NULL_KEY 0xFFFFFFFFFFFFFFFFull
 
 enum {
@@ -79,7 +79,11 @@ typedef struct {
     int32_t path;          /* MMALIGN_PATH_* */
     int32_t kprime;        /* depth the fused kernel's candidate lists are complete to; 0 = auto */
     int32_t n_ranks;       /* sharded passes: number of GPUs the chunk table is sharded over; 0/1 = one */
-    int32_t reserved[5];
+    int32_t reserved0;
+    int64_t shard_col0;    /* mmalign_fused_pass: the contraction runs on chunk rows [shard_col0, shard_col0 + */
+    int64_t shard_cols;    /*   shard_cols) of the table given to set_chunks; 0, 0 = the whole table          */
+    int64_t slab_row0;     /* mmalign_rescore_slab: image rows [slab_row0, slab_row0 + slab_rows) are ranked;  */
+    int64_t slab_rows;     /*   0, 0 = every image                                                             */
 } mmalign_params;
 
 /* Any pointer may be NULL (output not wanted).  S = popcount(schema_mask),
@@ -143,8 +147,8 @@ int mmalign_run(mmalign_ctx *ctx, const mmalign_params *params, mmalign_out *out
  * (one MMALIGN_* bit), 0.0 where the reference inserts none. */
 int mmalign_alignments(mmalign_ctx *ctx, uint32_t schema, double *rec, void *stream);
 
-/* Sharded (multi-GPU) run in passes -- the caller performs the collectives in between
- * (reference implementation: distributed.py::ShardedScorer):
+/* Sharded (multi-GPU) run in passes, fully sharded variant (no rank holds another rank's chunks) -- the
+ * caller performs the collectives in between (distributed.py::AllGatherScorer):
  *   1. mmalign_fused_pass    K1 on this rank's shard; tau_row [N] = score above which the rank's candidate
  *                            lists hold every local column.       -> all-reduce(max) of tau_row, and of
  *                            mmalign_chunk_err_max
@@ -160,6 +164,30 @@ int mmalign_rescore_pass(mmalign_ctx *ctx, const mmalign_params *params, const f
                          float eps_chunk_global, mmalign_out *out, int32_t *cert_count, void *stream);
 int mmalign_rescan_rows(mmalign_ctx *ctx, const mmalign_params *params, const int32_t *rows,
                         int64_t n_rows, mmalign_out *out, void *stream);
+
+/* Sharded run, default exchange (distributed.py::ShardedScorer): the contraction is sharded by CHUNK
+ * columns, the exact rescoring by QUERY rows.  Every rank holds the whole corpus (each rank ingests 1/G
+ * of it and the rest arrives by an NCCL all-gather over NVLink) and calls set_images / set_chunks on all of it.
+ *   1. mmalign_fused_pass    with params.shard_col0 / shard_cols = this rank's column range (tau_row may be NULL)
+ *   2. mmalign_export_lists  packs, for each destination rank d, the candidates of the image rows of slab d:
+ *                            keys [n_dest][slab_rows][stride] (lo = GLOBAL chunk index, hi = fp32 score bits),
+ *                            count [n_dest][slab_rows] (-1 = the row overflowed `stride`: it will be scanned
+ *                            exactly), tau [n_dest][slab_rows] (the rank's columns above tau are all present).
+ *                            stride >= mmalign_list_stride() of every rank.   -> all-to-all of the three arrays
+ *   3. mmalign_rescore_slab  with params.slab_row0 / slab_rows = this rank's query slab and the received lists
+ *                            keys [n_src][list_rows][stride], count / tau [n_src][list_rows] (list_rows = the
+ *                            slab_rows of the export; the rank's last rows may be padding): exact rescoring, certificate, exact scan of uncertified rows, metric
+ *                            sums -- mmalign_run restricted to the slab; outputs are sized by the slab:
+ *                            topk [S][slab_rows][Kmax], pair arrays [S][P_slab] (mmalign_num_pairs_range).
+ *                            -> all-reduce(sum) of hits / rr_sum / sim_sum / num_pairs
+ * Device pointers for keys / count / tau. */
+int mmalign_list_stride(mmalign_ctx *ctx, int32_t *stride);
+int mmalign_export_lists(mmalign_ctx *ctx, int32_t n_dest, int64_t slab_rows, int32_t stride,
+                         uint64_t *keys, int32_t *count, float *tau, void *stream);
+int mmalign_rescore_slab(mmalign_ctx *ctx, const mmalign_params *params, const uint64_t *keys,
+                         const int32_t *count, const float *tau, int32_t n_src, int64_t list_rows,
+                         int32_t stride, mmalign_out *out, void *stream);
+int mmalign_num_pairs_range(mmalign_ctx *ctx, int64_t row0, int64_t rows, int64_t *num_pairs);
 
 /* cross-rank merge after an all-gather of every rank's mmalign_run lists
  * (chunks are sharded over ranks):

@@ -23,7 +23,9 @@ class Params(C.Structure):
     _fields_ = [("schema_mask", C.c_uint32), ("candidates", C.c_int32), ("n_k", C.c_int32),
                 ("k_list", C.c_int32 * 8), ("mrr_cutoff", C.c_int32), ("lam_lex", C.c_double),
                 ("lam_pos", C.c_double), ("lam_comb", C.c_double), ("path", C.c_int32),
-                ("kprime", C.c_int32), ("n_ranks", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("kprime", C.c_int32), ("n_ranks", C.c_int32), ("reserved0", C.c_int32),
+                ("shard_col0", C.c_int64), ("shard_cols", C.c_int64), ("slab_row0", C.c_int64),
+                ("slab_rows", C.c_int64)]
 
 
 class Out(C.Structure):
@@ -37,7 +39,9 @@ EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_
            "mmalign_set_images", "mmalign_set_chunks", "mmalign_num_pairs", "mmalign_get_pairs",
            "mmalign_run", "mmalign_alignments", "mmalign_merge_topk", "mmalign_count_beating",
            "mmalign_reduce_metrics", "mmalign_debug_scores", "mmalign_fused_pass", "mmalign_chunk_err_max",
-           "mmalign_rescore_pass", "mmalign_rescan_rows"]
+           "mmalign_rescore_pass", "mmalign_rescan_rows", "mmalign_list_stride", "mmalign_export_lists",
+           "mmalign_rescore_slab", "mmalign_num_pairs_range"]
+ABI_VERSION = 2
 
 _lib = None
 
@@ -87,9 +91,15 @@ def load():
     L.mmalign_chunk_err_max.argtypes = [vp, C.POINTER(C.c_float)]
     L.mmalign_rescore_pass.argtypes = [vp, C.POINTER(Params), vp, C.c_float, C.POINTER(Out), vp, vp]
     L.mmalign_rescan_rows.argtypes = [vp, C.POINTER(Params), vp, i64, C.POINTER(Out), vp]
+    L.mmalign_list_stride.argtypes = [vp, C.POINTER(i32)]
+    L.mmalign_export_lists.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp]
+    L.mmalign_rescore_slab.argtypes = [vp, C.POINTER(Params), vp, vp, vp, i32, i64, i32, C.POINTER(Out), vp]
+    L.mmalign_num_pairs_range.argtypes = [vp, i64, i64, C.POINTER(i64)]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):
             getattr(L, name).restype = C.c_int
+    if L.mmalign_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path} has ABI version {L.mmalign_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
     _lib = L
     return L

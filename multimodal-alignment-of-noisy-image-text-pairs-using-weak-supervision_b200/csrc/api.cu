@@ -77,6 +77,8 @@ struct mmalign_ctx {
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     CandLists lists;               // written by the last fused pass
     bool lists_valid = false;
+    int64_t lists_col0 = 0;        // first chunk row of the column range the lists were built on
+    int64_t last_fused_us = 0;     // CUDA-event time of the last mmalign_fused_pass
     cudaEvent_t ev[5] = {};        // run start, after fused, after rescore, after exact scan, after metrics
 };
 
@@ -361,12 +363,48 @@ static int parse_params(mmalign_ctx *c, const mmalign_params *prm, RunParams *ou
     return MMALIGN_OK;
 }
 
-// K1 over the current corpus; the lists stay in the context for the rescoring pass
-static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, cudaStream_t st, FusedPlan *plan_out)
+// Range checks of the sharded parameters; (0, 0) means everything.
+static int resolve_range(mmalign_ctx *c, int64_t lo, int64_t cnt, int64_t total, const char *what, int64_t *o_lo, int64_t *o_cnt)
 {
-    const Side &img = c->img.s, &chk = c->chk.s;
+    if (lo == 0 && cnt == 0) { *o_lo = 0; *o_cnt = total; return MMALIGN_OK; }
+    if (lo < 0 || cnt < 0 || lo + cnt > total) return fail(c, MMALIGN_EINVAL, "%s [%lld, +%lld) is outside 0..%lld", what, (long long)lo, (long long)cnt, (long long)total);
+    *o_lo = lo; *o_cnt = cnt;
+    return MMALIGN_OK;
+}
+
+// Rows [row0, row0 + n_rows) with their slice of the pair arrays (two 8-byte reads of the pair index).
+static int make_row_range(mmalign_ctx *c, int64_t row0, int64_t n_rows, cudaStream_t st, RowRange *out)
+{
+    RowRange r;
+    r.row0 = row0; r.n_rows = n_rows;
+    int64_t h[2] = {0, 0};
+    CU(c, cudaMemcpyAsync(&h[0], c->px.offsets + row0, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(&h[1], c->px.offsets + row0 + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    r.pair0 = h[0]; r.P_out = h[1] - h[0];
+    *out = r;
+    return MMALIGN_OK;
+}
+
+// K1 of image rows [row0, +n_rows) against chunk rows [col0, +n_cols) of the current corpus; the lists (row and
+// column indices relative to the ranges) stay in the context for the rescoring / export pass
+static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, int64_t row0, int64_t n_rows,
+                     int64_t col0, int64_t n_cols, cudaStream_t st, FusedPlan *plan_out)
+{
+    Side img = c->img.s, chk = c->chk.s;
     if (img.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", img.D);
     if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
+    alignas(64) CUtensorMap tmap_a = c->img.tmap, tmap_b = c->chk.tmap;
+    char msg[256];
+    if (row0 != 0 || n_rows != img.n) {
+        if (encode_tensor_map(&tmap_a, img.emb_bf16 + row0 * img.D, n_rows, img.D, 128, msg, sizeof msg)) return fail(c, MMALIGN_ECUDA, "%s", msg);
+        img.n = n_rows;
+    }
+    if (col0 != 0 || n_cols != chk.n) {
+        if (encode_tensor_map(&tmap_b, chk.emb_bf16 + col0 * chk.D, n_cols, chk.D, 256, msg, sizeof msg)) return fail(c, MMALIGN_ECUDA, "%s", msg);
+        chk.n = n_cols;
+    }
+    c->lists_col0 = col0;
     FusedPlan plan;
     const int prc = fused_plan(img.n, chk.n, img.D, rp.kneed, kprime_req, c->sm_count, n_ranks, &plan);
     if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)img.n, (long long)chk.n, img.D, kprime_req, prc);
@@ -376,25 +414,31 @@ static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_
     CU(c, c->fail_rows.reserve((size_t)img.n * sizeof(int32_t)));
     c->lists = CandLists();
     c->lists.keys = (uint64_t *)c->list_keys.p; c->lists.tau = (float *)c->list_tau.p; c->lists.count = (int32_t *)c->list_count.p;
-    CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, c->lists, nullptr, st));
+    CU(c, launch_fused(img, chk, plan, &tmap_a, &tmap_b, c->lists, nullptr, st));
     c->lists_valid = true;
     *plan_out = plan;
     return MMALIGN_OK;
 }
 
-extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream)
+// mmalign_run and mmalign_rescore_slab: rank image rows [slab_row0, +slab_rows) (0, 0 = all).  `imported` = the
+// candidate lists received from the ranks' fused passes (global chunk indices); without it the fused kernel runs here.
+static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream, const CandLists *imported)
 {
-    if (!c || !prm || !uo) return fail(c, MMALIGN_EINVAL, "mmalign_run: NULL argument");
     Trace tr("run");
     int rc = ensure_index(c);
     if (rc) return rc;
     tr.mark("pair index");
     cudaStream_t st = (cudaStream_t)stream;
     const Side &img = c->img.s, &chk = c->chk.s;
-    const int64_t N = img.n, M = chk.n, P = c->px.P;
+    const int64_t M = chk.n;
     RunParams rp;
     if ((rc = parse_params(c, prm, &rp))) return rc;
     CU(c, cudaSetDevice(c->device));
+    int64_t row0, N;  // the slab; per-row outputs are [S][N][..], per-pair outputs [S][P]
+    if ((rc = resolve_range(c, prm->slab_row0, prm->slab_rows, img.n, "slab rows", &row0, &N))) return rc;
+    RowRange range;
+    if ((rc = make_row_range(c, row0, N, st, &range))) return rc;
+    const int64_t P = range.P_out;
     // ---- outputs
     Stager sg{c, st};
     Outputs out = {};
@@ -440,24 +484,30 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     if (N > 0) {
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
             CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, cand_counter,
-                                 error_flag, nullptr, nullptr, st));
+                                 error_flag, nullptr, nullptr, range, st));
             launches += 1;
         } else if (prm->path == MMALIGN_PATH_EXACT || M == 0) {
-            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, st));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, range, st));
             launches += 1;
         } else {
-            FusedPlan plan;
-            if ((rc = run_fused(c, rp, prm->kprime, 1, st, &plan))) return rc;
-            CandLists &L = c->lists;
+            if (imported) {
+                CU(c, c->fail_rows.reserve((size_t)img.n * sizeof(int32_t)));
+                kprime_used = imported->kprime;
+            } else {
+                FusedPlan plan;
+                if ((rc = run_fused(c, rp, prm->kprime, 1, row0, N, 0, M, st, &plan))) return rc;
+                fused_launches = 1;
+                launches += 1;
+                kprime_used = plan.kprime;
+            }
+            const CandLists &L = imported ? *imported : c->lists;
             CU(c, cudaEventRecord(c->ev[1], st));
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, (int32_t *)c->fail_rows.p, fail_count,
-                                 cand_counter, error_flag, nullptr, nullptr, st));
+                                 cand_counter, error_flag, nullptr, nullptr, range, st));
             CU(c, cudaEventRecord(c->ev[2], st));
-            CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, st));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, range, st));
             CU(c, cudaEventRecord(c->ev[3], st));
-            launches += 3;
-            fused_launches = 1;
-            kprime_used = plan.kprime;
+            launches += 2;
         }
     }
     tr.mark("launch scoring");
@@ -482,13 +532,14 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     if (d_np) CU(c, cudaMemcpyAsync(d_np, &P, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (d_stats) {
         float t_fused = 0.f, t_resc = 0.f, t_scan = 0.f;
-        if (fused_launches) {
-            cudaEventElapsedTime(&t_fused, c->ev[0], c->ev[1]);
+        if (fused_launches || imported) {
+            if (fused_launches) cudaEventElapsedTime(&t_fused, c->ev[0], c->ev[1]);
             cudaEventElapsedTime(&t_resc, c->ev[1], c->ev[2]);
             cudaEventElapsedTime(&t_scan, c->ev[2], c->ev[3]);
         }
-        const int64_t stats[8] = {h.fail, (int64_t)h.cand, fused_launches, launches, kprime_used,
-                                  (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f), (int64_t)(t_scan * 1000.f)};
+        const int64_t stats[8] = {h.fail, (int64_t)h.cand, imported ? 1 : fused_launches, launches + (imported ? 2 : 0), kprime_used,
+                                  imported ? c->last_fused_us : (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f),
+                                  (int64_t)(t_scan * 1000.f)};
         CU(c, cudaMemcpyAsync(d_stats, stats, sizeof stats, cudaMemcpyHostToDevice, st));
     }
     if ((rc = sg.copy_back())) { extra.release(); return rc; }
@@ -498,12 +549,81 @@ extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_ou
     return MMALIGN_OK;
 }
 
+extern "C" int mmalign_run(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream)
+{
+    if (!c || !prm || !uo) return fail(c, MMALIGN_EINVAL, "mmalign_run: NULL argument");
+    return run_impl(c, prm, uo, stream, nullptr);
+}
+
+extern "C" int mmalign_rescore_slab(mmalign_ctx *c, const mmalign_params *prm, const uint64_t *keys, const int32_t *count,
+                                    const float *tau, int32_t n_src, int64_t list_rows, int32_t stride, mmalign_out *uo,
+                                    void *stream)
+{
+    if (!c || !prm || !uo || !keys || !count || !tau) return fail(c, MMALIGN_EINVAL, "mmalign_rescore_slab: NULL argument");
+    if (n_src < 1 || n_src > 64 || stride < 1) return fail(c, MMALIGN_EINVAL, "mmalign_rescore_slab: bad n_src/stride");
+    if (!is_device_ptr(keys) || !is_device_ptr(count) || !is_device_ptr(tau))
+        return fail(c, MMALIGN_EINVAL, "mmalign_rescore_slab: the received lists must be device pointers");
+    if (prm->candidates != MMALIGN_CAND_ALL || prm->path == MMALIGN_PATH_EXACT)
+        return fail(c, MMALIGN_EINVAL, "mmalign_rescore_slab is the second half of the fused path (MMALIGN_CAND_ALL)");
+    if (!c->img.ready) return fail(c, MMALIGN_ESTATE, "set_images and set_chunks must be called first");
+    int64_t row0, rows;
+    int rc = resolve_range(c, prm->slab_row0, prm->slab_rows, c->img.s.n, "slab rows", &row0, &rows);
+    if (rc) return rc;
+    if (list_rows < rows) return fail(c, MMALIGN_EINVAL, "mmalign_rescore_slab: list_rows=%lld is smaller than the slab (%lld rows)", (long long)list_rows, (long long)rows);
+    FusedPlan plan;  // K' as the ranks' fused passes chose it (same arguments, same answer)
+    RunParams rp;
+    if ((rc = parse_params(c, prm, &rp))) return rc;
+    if (fused_plan(c->img.s.n, c->chk.s.n > 0 ? c->chk.s.n : 1, c->img.s.D, rp.kneed, prm->kprime, c->sm_count, 1, &plan))
+        return fail(c, MMALIGN_ELIMIT, "no fused plan");
+    CandLists L;
+    L.imp_keys = keys; L.imp_count = count; L.imp_tau = tau;
+    L.imp_src = n_src; L.imp_stride = stride; L.imp_rows = list_rows;
+    L.kprime = plan.kprime;
+    return run_impl(c, prm, uo, stream, &L);
+}
+
+extern "C" int mmalign_num_pairs_range(mmalign_ctx *c, int64_t row0, int64_t rows, int64_t *num_pairs)
+{
+    if (!c || !num_pairs) return fail(c, MMALIGN_EINVAL, "mmalign_num_pairs_range: NULL argument");
+    int rc = ensure_index(c);
+    if (rc) return rc;
+    int64_t r0, n;
+    if ((rc = resolve_range(c, row0, rows, c->img.s.n, "rows", &r0, &n))) return rc;
+    RowRange range;
+    if ((rc = make_row_range(c, r0, n, 0, &range))) return rc;
+    *num_pairs = range.P_out;
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_list_stride(mmalign_ctx *c, int32_t *stride)
+{
+    if (!c || !stride) return fail(c, MMALIGN_EINVAL, "mmalign_list_stride: NULL argument");
+    // an empty shard exports nothing
+    *stride = c->lists_valid ? 2 * c->lists.n_splits * (c->lists.kprime_list + kListSlack) : 1;
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_export_lists(mmalign_ctx *c, int32_t n_dest, int64_t slab_rows, int32_t stride, uint64_t *keys,
+                                    int32_t *count, float *tau, void *stream)
+{
+    if (!c || !keys || !count || !tau) return fail(c, MMALIGN_EINVAL, "mmalign_export_lists: NULL argument");
+    if (!c->img.ready || !c->chk.ready) return fail(c, MMALIGN_ESTATE, "set_images and set_chunks must be called first");
+    if (n_dest < 1 || slab_rows < 1 || stride < 1 || (int64_t)n_dest * slab_rows < c->img.s.n)
+        return fail(c, MMALIGN_EINVAL, "mmalign_export_lists: n_dest x slab_rows must cover the %lld image rows", (long long)c->img.s.n);
+    if (!is_device_ptr(keys) || !is_device_ptr(count) || !is_device_ptr(tau))
+        return fail(c, MMALIGN_EINVAL, "mmalign_export_lists writes device buffers (they feed an all-to-all)");
+    CU(c, cudaSetDevice(c->device));
+    CandLists L = c->lists_valid ? c->lists : CandLists();  // an empty shard: no lists, complete above -inf
+    CU(c, launch_export_lists(L, c->img.s.n, n_dest, slab_rows, stride, c->lists_col0, keys, count, tau, (cudaStream_t)stream));
+    return MMALIGN_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Sharded (multi-GPU) run in passes; the caller performs the collectives in between (distributed.py).
 // ---------------------------------------------------------------------------------------------
 extern "C" int mmalign_fused_pass(mmalign_ctx *c, const mmalign_params *prm, float *tau_row, void *stream)
 {
-    if (!c || !prm || !tau_row) return fail(c, MMALIGN_EINVAL, "mmalign_fused_pass: NULL argument");
+    if (!c || !prm) return fail(c, MMALIGN_EINVAL, "mmalign_fused_pass: NULL argument");
     int rc = ensure_index(c);
     if (rc) return rc;
     RunParams rp;
@@ -512,25 +632,37 @@ extern "C" int mmalign_fused_pass(mmalign_ctx *c, const mmalign_params *prm, flo
     cudaStream_t st = (cudaStream_t)stream;
     CU(c, cudaSetDevice(c->device));
     const int64_t N = c->img.s.n;
+    int64_t col0, n_cols;
+    if ((rc = resolve_range(c, prm->shard_col0, prm->shard_cols, c->chk.s.n, "shard columns", &col0, &n_cols))) return rc;
+    if (prm->shard_col0 != 0 && prm->shard_cols == 0) n_cols = 0;  // an empty shard at the end of the table
     Stager sg{c, st};
     float *d_tau = nullptr;
     sg.map(tau_row, (size_t)N, &d_tau);
     if ((rc = sg.commit())) return rc;
+    c->last_fused_us = 0;
     if (N == 0) return MMALIGN_OK;
-    if (c->chk.s.n == 0) {  // an empty shard holds every one of its (zero) columns
-        std::vector<float> inf((size_t)N, -INFINITY);
-        CU(c, cudaMemcpyAsync(d_tau, inf.data(), sizeof(float) * N, cudaMemcpyHostToDevice, st));
-        CU(c, cudaStreamSynchronize(st));
+    if (n_cols == 0) {  // an empty shard holds every one of its (zero) columns
+        if (d_tau) {
+            std::vector<float> inf((size_t)N, -INFINITY);
+            CU(c, cudaMemcpyAsync(d_tau, inf.data(), sizeof(float) * N, cudaMemcpyHostToDevice, st));
+            CU(c, cudaStreamSynchronize(st));
+        }
         c->lists_valid = false;
+        c->lists_col0 = col0;
     } else {
         FusedPlan plan;
         CU(c, cudaEventRecord(c->ev[0], st));
-        if ((rc = run_fused(c, rp, prm->kprime, prm->n_ranks > 1 ? prm->n_ranks : 1, st, &plan))) return rc;
+        if ((rc = run_fused(c, rp, prm->kprime, prm->n_ranks > 1 ? prm->n_ranks : 1, 0, N, col0, n_cols, st, &plan))) return rc;
         CU(c, cudaEventRecord(c->ev[1], st));
-        CU(c, launch_row_tau(c->lists, N, d_tau, st));
+        if (d_tau) CU(c, launch_row_tau(c->lists, N, d_tau, st));
     }
     if ((rc = sg.copy_back())) return rc;
     CU(c, cudaStreamSynchronize(st));
+    if (n_cols > 0) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+        c->last_fused_us = (int64_t)(ms * 1000.f);
+    }
     return MMALIGN_OK;
 }
 
@@ -575,10 +707,10 @@ extern "C" int mmalign_rescore_pass(mmalign_ctx *c, const mmalign_params *prm, c
     if (N > 0) {
         if (M > 0) {
             CU(c, launch_rescore(c->img.s, c->chk.s, c->px, rp, &c->lists, eps_dev, out, nullptr, nullptr, cand_counter,
-                                 error_flag, tau_global, cert_count, st));
+                                 error_flag, tau_global, cert_count, RowRange(), st));
         } else {  // empty shard: no entries, nothing certified here
             CU(c, cudaMemsetAsync(cert_count, 0, (size_t)rp.S * N * sizeof(int32_t), st));
-            CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, nullptr, nullptr, N, out, error_flag, st));
+            CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, nullptr, nullptr, N, out, error_flag, RowRange(), st));
         }
     }
     CU(c, cudaEventRecord(c->ev[2], st));
@@ -612,7 +744,7 @@ extern "C" int mmalign_rescan_rows(mmalign_ctx *c, const mmalign_params *prm, co
     outputs_from(uo, &out);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
     CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
-    CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, rows, nullptr, n_rows, out, error_flag, st));
+    CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, rows, nullptr, n_rows, out, error_flag, RowRange(), st));
     int32_t err = 0;
     CU(c, cudaMemcpyAsync(&err, error_flag, sizeof err, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));

@@ -73,6 +73,17 @@ struct CandLists {
     int64_t n_row_blocks = 0;
     int kprime = 0;            // depth the union of a row's lists is complete to
     int kprime_list = 0;       // entries each list keeps
+    // imported lists (mmalign_rescore_slab): one list per source rank and slab row, GLOBAL chunk indices
+    const uint64_t *imp_keys = nullptr;  // [imp_src][imp_rows][imp_stride]
+    const int32_t *imp_count = nullptr;  // [imp_src][imp_rows], -1 = overflowed at the source
+    const float *imp_tau = nullptr;      // [imp_src][imp_rows]
+    int imp_src = 0, imp_stride = 0;
+    int64_t imp_rows = 0;
+};
+
+struct RowRange {             // image rows a rescoring launch ranks (0, 0 = all); outputs are indexed relative to it
+    int64_t row0 = 0, n_rows = 0;
+    int64_t pair0 = 0, P_out = 0;  // offsets[row0], offsets[row0 + n_rows] - offsets[row0]
 };
 
 // ---------------------------------------------------------------------------
@@ -247,11 +258,15 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, vo
 cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
-                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, cudaStream_t st);
+                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, RowRange rows,
+                           cudaStream_t st);
+constexpr int kListSlack = 8;  // a list compacted to K' entries may keep up to K' + kListSlack (fused_tc.cu)
+cudaError_t launch_export_lists(const CandLists &L, int64_t N, int n_dest, int64_t slab_rows, int stride,
+                                int64_t col_offset, uint64_t *keys, int32_t *count, float *tau, cudaStream_t st);
 cudaError_t launch_row_tau(const CandLists &L, int64_t N, float *tau_row, cudaStream_t st);
 cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                               const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
-                              const Outputs &out, int32_t *error_flag, cudaStream_t st);
+                              const Outputs &out, int32_t *error_flag, RowRange range, cudaStream_t st);
 cudaError_t launch_alignments(const Side &img, const Side &chk, const PairIndex &px, int schema,
                               int64_t n_terms, bool raw, double *rec, cudaStream_t st);
 cudaError_t launch_pair_chunk(const PairIndex &px, int64_t N, int64_t col_offset, int64_t *pair_chunk,

@@ -145,7 +145,7 @@ struct FusedArgs {
 // Candidate lists.  An entry is 8 bytes: lo = chunk column, hi = fp32 score bits.
 // Thread (row, half) owns list `ubase + off0`; `n` entries are live.
 // ---------------------------------------------------------------------------
-constexpr int kSlack = 8;  // a compaction may keep up to K' + kSlack entries (saves bisection steps)
+constexpr int kSlack = kListSlack;  // a compaction may keep up to K' + kSlack entries (saves bisection steps)
 
 // Warp-cooperative compaction of the lists of the lanes that ask for it: keeps the best ~K'
 // entries and raises the lane's threshold tau to the smallest kept score.

@@ -99,6 +99,9 @@ struct RowArgs {
     int32_t *error_flag;  // set to 1 when a capacity limit is hit
     int ent_cap, sp_cap;  // shared-memory capacities of this launch (>= 256 / >= 8)
     bool need_lex, need_pos;  // some requested schema uses the lexical / positional term
+    // rows [row0, row0 + n_rows) are ranked; per-row outputs are indexed by (i - row0), per-pair outputs by
+    // (pair - offsets[row0]) and sized P_out = offsets[row0 + n_rows] - offsets[row0]
+    int64_t row0, n_rows, pair0, P_out;
 };
 
 __device__ __forceinline__ int next_pow2(int n)
@@ -181,8 +184,9 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
     __shared__ int s_cert;
     const double cert_thr = (double)tau + (double)eps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t p0 = A.offsets[i];
-    const int c = (int)(A.offsets[i + 1] - p0);
+    const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
+    const int64_t p0 = A.offsets[i] - A.pair0;  // position of the row's first pair in the per-pair outputs
+    const int64_t io = i - A.row0;               // position of the row in the per-row outputs
     const int n = n_ca + c;
     const int d4 = A.D >> 2;
     const RunParams &rp = A.rp;
@@ -238,10 +242,10 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
             const double sc = sm.cosv[n_ca + p] + w;
             sm.sp_s[p] = sc;
             sm.sp_k[p] = ord64(sc);
-            if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P + p0 + p] = sc;
+            if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P_out + p0 + p] = sc;
         }
         __syncthreads();
-        const int64_t o_top = ((int64_t)si * A.N + i) * rp.kmax, o_deep = ((int64_t)si * A.N + i) * rp.kneed;
+        const int64_t o_top = ((int64_t)si * A.n_rows + io) * rp.kmax, o_deep = ((int64_t)si * A.n_rows + io) * rp.kneed;
         // final position of an element = its position in its own sorted list + elements of the other list before it
         for (int t = threadIdx.x; t < c + min(n_ca, rp.kneed); t += kThreads) {
             unsigned long long k;
@@ -256,7 +260,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
                 }
                 pos = lo;
                 for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[n_ca + q], k, j);
-                if (pos < rp.kneed && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P + p0 + t] = pos + 1;
+                if (pos < rp.kneed && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P_out + p0 + t] = pos + 1;
             } else {      // a candidate: its sorted position + the same-page entries that beat it
                 const Key x = sm.buf[t - c];
                 k = x.k; j = x.j; sc = sm.cosv[x.e];
@@ -282,7 +286,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         if (certify && tau > -CUDART_INF_F) ok = ok && (n >= rp.kneed) && (s_kth > cert_thr);
         // sharded runs certify globally: this rank's entries that are provably above every column it left out
         // (counted among its best kneed + same-page entries, which is all the global test needs)
-        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.N + i] = tau > -CUDART_INF_F ? s_cert : rp.kneed;
+        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.n_rows + io] = tau > -CUDART_INF_F ? s_cert : rp.kneed;
         __syncthreads();
     }
     return ok;
@@ -303,6 +307,25 @@ __device__ __forceinline__ void stage_row(const RowArgs &A, const RowSmem &sm, i
 // ---------------------------------------------------------------------------
 // K2
 // ---------------------------------------------------------------------------
+// List l of image row i.  Native layout (written by the fused kernel of this GPU): one list per (column split,
+// accumulator half), local chunk indices.  Imported layout (mmalign_rescore_slab): one list per source rank,
+// global chunk indices, cnt < 0 = the source could not fit the row into the exchange stride.
+struct ListView { const uint64_t *keys; int cnt; float tau; };
+__device__ __forceinline__ int lists_per_row(const CandLists &L) { return L.imp_keys ? L.imp_src : L.n_splits * 2; }
+__device__ __forceinline__ ListView list_view(const CandLists &L, int64_t i, int64_t row0, int l)
+{
+    ListView v;
+    if (L.imp_keys) {
+        const int64_t id = (int64_t)l * L.imp_rows + (i - row0);
+        v.keys = L.imp_keys + id * L.imp_stride; v.cnt = L.imp_count[id]; v.tau = L.imp_tau[id];
+    } else {  // the fused kernel numbers its rows from the first row of its range
+        const int64_t li = i - row0;
+        const int64_t id = (((int64_t)(l >> 1) * L.n_row_blocks + (li >> 7)) * 2 + (l & 1)) * 128 + (li & 127);
+        v.keys = L.keys + id * L.cap; v.cnt = L.count[id]; v.tau = L.tau[id];
+    }
+    return v;
+}
+
 // 64 registers -> 8 CTAs of 128 threads per SM (measured at config 5 with 256-thread CTAs: 110 ms at 64 registers against 128 / 161 ms at 80 / 124)
 __global__ void __launch_bounds__(kThreads, 8)
 rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_max,
@@ -313,7 +336,8 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
     const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
     __shared__ int s_nca;
     __shared__ float s_tau;
-    for (int64_t i = blockIdx.x; i < A.N; i += gridDim.x) {
+    for (int64_t b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
+        const int64_t i = A.row0 + b;
         const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
         if (threadIdx.x == 0) { s_nca = 0; s_tau = -CUDART_INF_F; }
         stage_row(A, sm, i);
@@ -326,15 +350,12 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 finish_row(A, sm, i, 0, false, 0.f, 0.f);
             }
         } else if (ok) {
-            // lists of this row: one per (column split, accumulator half)
-            const int64_t rb = i >> 7;
-            const int r = (int)(i & 127);
-            const int n_l = L.n_splits * 2;
+            const int n_l = lists_per_row(L);
             if (threadIdx.x < 32) {
                 float t = -CUDART_INF_F;
                 for (int l = threadIdx.x; l < n_l; l += 32) {
-                    const int64_t id = (((int64_t)(l >> 1) * L.n_row_blocks + rb) * 2 + (l & 1)) * 128 + r;
-                    t = fmaxf(t, L.tau[id]);
+                    const ListView v = list_view(L, i, A.row0, l);
+                    t = fmaxf(t, v.cnt < 0 ? CUDART_INF_F : v.tau);  // an overflowed list certifies nothing
                 }
                 for (int off = 16; off >= 1; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
                 if (threadIdx.x == 0) s_tau = t;
@@ -342,16 +363,17 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
             __syncthreads();
             // the union of the lists is complete above this (sharded runs: the maximum over all ranks)
             const float tau_union = tau_global ? fmaxf(tau_global[i], s_tau) : s_tau;
+            if (tau_union == CUDART_INF_F) ok = false;
             const uint64_t ik = A.img_key[i];
             const float eps = A.img_err[i] * 1.001f + eps_chunk_max[0] * 1.001f + (float)A.D * 2.4e-7f + 2e-6f;
             // attempt 0: the best K' of the union by approximate score; attempt 1: the whole union
-            for (int attempt = 0; attempt < 2; ++attempt) {
+            for (int attempt = 0; ok && attempt < 2; ++attempt) {
                 if (threadIdx.x == 0) { s_nca = 0; s_tau = tau_union; }
                 __syncthreads();
                 for (int l = 0; l < n_l; ++l) {
-                    const int64_t id = (((int64_t)(l >> 1) * L.n_row_blocks + rb) * 2 + (l & 1)) * 128 + r;
-                    const int cnt = L.count[id];
-                    const uint64_t *keys = L.keys + id * L.cap;
+                    const ListView v = list_view(L, i, A.row0, l);
+                    const int cnt = v.cnt;
+                    const uint64_t *keys = v.keys;
                     for (int e = threadIdx.x; e < cnt; e += kThreads) {
                         const uint64_t k = keys[e];
                         const uint32_t col = cand_col(k);
@@ -390,7 +412,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 // not certified at depth K': clear this row's ranks and retry with everything the lists hold
                 if (A.out.pair_rank)
                     for (int t = threadIdx.x; t < c * A.rp.S; t += kThreads)
-                        A.out.pair_rank[(int64_t)(t / c) * A.P + A.offsets[i] + (t % c)] = 0;
+                        A.out.pair_rank[(int64_t)(t / c) * A.P_out + (A.offsets[i] - A.pair0) + (t % c)] = 0;
                 __syncthreads();
             }
         }
@@ -418,7 +440,7 @@ exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int
     const int d4 = A.D >> 2;
     const int kneed = A.rp.kneed;
     for (int64_t b = blockIdx.x; b < n_rows; b += gridDim.x) {
-        const int64_t i = rows ? rows[b] : b;
+        const int64_t i = rows ? rows[b] : A.row0 + b;
         const int64_t p0 = A.offsets[i];
         const int c = (int)(A.offsets[i + 1] - p0);
         if (threadIdx.x == 0) { s_cnt = 0; s_thr = 0ull; s_thr_j = 0x7FFFFFFF; }
@@ -426,7 +448,7 @@ exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int
         // a previous (uncertified) pass may have written ranks for this row
         if (A.out.pair_rank)
             for (int t = threadIdx.x; t < c * A.rp.S; t += kThreads)
-                A.out.pair_rank[(int64_t)(t / c) * A.P + p0 + (t % c)] = 0;
+                A.out.pair_rank[(int64_t)(t / c) * A.P_out + (p0 - A.pair0) + (t % c)] = 0;
         __syncthreads();
         if (c > A.sp_cap) {
             if (threadIdx.x == 0) atomicExch(A.error_flag, 1);
@@ -489,7 +511,7 @@ static void size_caps(RowArgs &A, const PairIndex &px, int64_t union_entries)
 }
 
 static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
-                         const Outputs &out, int32_t *error_flag)
+                         const Outputs &out, int32_t *error_flag, const RowRange *range = nullptr)
 {
     RowArgs A;
     A.img_emb = img.emb; A.img_key = img.key; A.img_bbox = img.bbox; A.img_terms = img.terms;
@@ -500,6 +522,10 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
     A.offsets = px.offsets; A.sorted_chunk = px.sorted_chunk; A.sp_start = px.sp_start; A.P = px.P;
     A.rp = rp; A.out = out; A.error_flag = error_flag;
     A.ent_cap = kEntCapMax; A.sp_cap = kSpCapMax;
+    A.row0 = 0; A.n_rows = img.n; A.pair0 = 0; A.P_out = px.P;
+    if (range && range->n_rows >= 0 && !(range->row0 == 0 && range->n_rows == 0)) {
+        A.row0 = range->row0; A.n_rows = range->n_rows; A.pair0 = range->pair0; A.P_out = range->P_out;
+    }
     A.need_lex = A.need_pos = false;
     for (int q = 0; q < rp.S; ++q) {
         A.need_lex = A.need_lex || rp.schema[q] == 1 || rp.schema[q] == 3;
@@ -511,17 +537,20 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
 cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
-                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, cudaStream_t st)
+                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, RowRange range,
+                           cudaStream_t st)
 {
     if (img.n == 0) return cudaSuccess;
-    RowArgs A = make_args(img, chk, px, rp, out, error_flag);
+    RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
+    if (A.n_rows == 0) return cudaSuccess;
     CandLists L = lists ? *lists : CandLists();
     // shared memory sized for this launch: the union of a row's lists after the final compaction, plus its page
-    size_caps(A, px, lists ? (int64_t)2 * L.n_splits * (L.kprime_list + 16) : 0);
+    size_caps(A, px, !lists ? 0 : L.imp_keys ? (int64_t)L.imp_src * L.imp_stride
+                                             : (int64_t)2 * L.n_splits * (L.kprime_list + 16));
     const size_t smem = row_smem_bytes(img.D, A.ent_cap, A.sp_cap);
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t grid = img.n < 148 * 16 ? img.n : 148 * 16;
+    int64_t grid = A.n_rows < 148 * 16 ? A.n_rows : 148 * 16;
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
                                                            fail_count, cand_counter, tau_global, cert_count);
     return cudaGetLastError();
@@ -529,10 +558,10 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
 
 cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                               const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
-                              const Outputs &out, int32_t *error_flag, cudaStream_t st)
+                              const Outputs &out, int32_t *error_flag, RowRange range, cudaStream_t st)
 {
     if (img.n == 0 || (!n_rows_dev && n_rows_host == 0)) return cudaSuccess;
-    RowArgs A = make_args(img, chk, px, rp, out, error_flag);
+    RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
     size_caps(A, px, kEntCapMax);  // the scan's streaming buffer wants the full capacity
     const size_t smem = row_smem_bytes(img.D, A.ent_cap, A.sp_cap);
     cudaError_t e = cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -604,6 +633,51 @@ __global__ void row_tau_kernel(CandLists L, int64_t N, float *tau_row)
             t = fmaxf(t, L.tau[(((int64_t)(l >> 1) * L.n_row_blocks + rb) * 2 + (l & 1)) * 128 + r]);
         tau_row[i] = t;
     }
+}
+
+// Packs the rows' candidates for the all-to-all of the sharded run: destination d owns image rows
+// [d * slab_rows, (d + 1) * slab_rows), so output row w IS global image row w.  One warp per row: the row's
+// lists are concatenated above the row's completeness threshold, columns become global chunk indices.
+__global__ void export_lists_kernel(CandLists L, int64_t N, int64_t total_rows, int stride, int64_t col_offset,
+                                    uint64_t *__restrict__ keys, int32_t *__restrict__ count, float *__restrict__ tau)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int n_l = L.keys ? 2 * L.n_splits : 0;
+    for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < total_rows;
+         w += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        float t = -CUDART_INF_F;
+        int n = 0;
+        if (w < N) {
+            for (int l = 0; l < n_l; ++l) t = fmaxf(t, list_view(L, w, 0, l).tau);
+            uint64_t *dst = keys + w * stride;
+            for (int l = 0; l < n_l; ++l) {
+                const ListView v = list_view(L, w, 0, l);
+                for (int e0 = 0; e0 < v.cnt; e0 += 32) {
+                    const int e = e0 + lane;
+                    uint64_t k = 0;
+                    bool keep = false;
+                    if (e < v.cnt) { k = v.keys[e]; keep = cand_score(k) > t; }
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                    const int pos = n + __popc(m & lt_mask);
+                    if (keep && pos < stride)
+                        dst[pos] = (k & 0xFFFFFFFF00000000ull) | (uint64_t)((int64_t)cand_col(k) + col_offset);
+                    n += __popc(m);
+                }
+            }
+        }
+        if (lane == 0) { count[w] = n > stride ? -1 : n; tau[w] = t; }
+    }
+}
+
+cudaError_t launch_export_lists(const CandLists &L, int64_t N, int n_dest, int64_t slab_rows, int stride,
+                                int64_t col_offset, uint64_t *keys, int32_t *count, float *tau, cudaStream_t st)
+{
+    const int64_t total = (int64_t)n_dest * slab_rows;
+    int64_t grid = (total * 32 + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    export_lists_kernel<<<(unsigned)grid, 256, 0, st>>>(L, N, total, stride, col_offset, keys, count, tau);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_row_tau(const CandLists &L, int64_t N, float *tau_row, cudaStream_t st)

@@ -1,7 +1,21 @@
-"""Multi-GPU plumbing: one process per GPU, chunks sharded by contiguous column range,
-images replicated.  torch.distributed (NCCL over NVLink) carries the
-three exchanges of a step; every merge/count/reduction on the data is a kernel of the
-CUDA library:
+"""Multi-GPU plumbing: one process per GPU.  torch.distributed (NCCL over
+NVLink) carries the exchanges of a step; every merge/count/reduction on the data is a kernel of
+the CUDA library.
+
+ShardedScorer (default).  The similarity contraction -- all of the FLOPs -- is sharded by CHUNK columns;
+the exact rescoring and ranking is sharded by QUERY rows:
+
+  load   every rank ingests 1/G of the images and 1/G of the chunks (host->device or device-resident) and
+         an all-gather over NVLink replicates the tables (4 GB at config 5: ~20x faster than PCIe would be)
+  1.     fused tcgen05 pass: every image row against this rank's chunk columns -> per-row candidate lists
+  2.     all-to-all of the candidate lists: rank g receives, from every rank, the lists of query slab g
+  3.     exact rescoring, certificate, rescan and metric sums of slab g against the whole chunk table --
+         exactly the single-GPU second half, so top-K lists, true-pair ranks and similarities need no
+         further merge; rank g owns the results of its slab
+  4.     all-reduce(sum) of the metric sums.
+
+AllGatherScorer (fully sharded variant: no rank ever holds another rank's chunk rows; for chunk tables
+too large to replicate).  Images replicated, three exchanges:
 
   0. all-reduce(max) of the per-row list thresholds (and of the chunk rounding-error bound), then
      all-reduce(sum) of the per-row certificate counts            (mmalign_fused_pass / rescore_pass)
@@ -36,7 +50,130 @@ def metrics_from_sums(hits, rr_sum, sim_sum, num_pairs):
                 avg_similarity=float(sim_sum) / P, num_pairs=P)
 
 
+def slab_size(N: int, world: int) -> int:
+    """Query rows per rank: whole 128-row blocks (the fused kernel's row tile), ceil(blocks / world) each."""
+    blocks = -(-N // 128)
+    return max(1, -(-blocks // max(world, 1))) * 128
+
+
+def slab_range(N: int, world: int, rank: int):
+    per = slab_size(N, world)
+    lo = min(N, rank * per)
+    return lo, min(N, lo + per)
+
+
 class ShardedScorer:
+    """Contraction sharded by chunk columns, rescoring by query rows (module docstring)."""
+    FIELDS = ("emb", "key", "bbox", "terms")
+
+    def __init__(self, engine, world: int = 1, rank: int = 0, device=None, dist=None):
+        self.eng, self.world, self.rank, self.device = engine, world, rank, device
+        if dist is None and world > 1:
+            import torch.distributed as dist
+        self.dist = dist
+        self._full = {}
+        self.N = self.M = 0
+        self.MAX = getattr(getattr(dist, "ReduceOp", None), "MAX", "max") if dist is not None else "max"
+
+    # -- ingest ---------------------------------------------------------------------------------------
+    def _replicate(self, side, shard, total, per):
+        """All-gather of one table: every rank contributes `per` rows (the last ranks fewer; their slots are
+        padded) into persistent [G * per, ...] buffers.  Returns the dict of full tables cut to `total` rows."""
+        import torch
+        G, out = self.world, {}
+        for f in self.FIELDS:
+            x = shard.get(f)
+            if x is None:
+                out[f] = None
+                continue
+            if not type(x).__module__.startswith("torch"):
+                x = torch.from_numpy(x.view("int64") if x.dtype.kind == "u" else x)
+            if x.dtype == torch.uint64:
+                x = x.view(torch.int64)
+            shape = (G * per,) + tuple(x.shape[1:])
+            buf = self._full.get((side, f))
+            if buf is None or buf.shape != shape or buf.dtype != x.dtype:
+                buf = torch.empty(shape, dtype=x.dtype, device=self.device if self.device is not None else x.device)
+                self._full[(side, f)] = buf
+            slot = buf[self.rank * per:(self.rank + 1) * per]
+            slot[:x.shape[0]].copy_(x, non_blocking=True)  # host->device for pinned host shards
+            if hasattr(self.dist, "all_gather_into_tensor"):
+                self.dist.all_gather_into_tensor(buf, slot)
+            else:
+                parts = [torch.empty_like(slot) for _ in range(G)]
+                self.dist.all_gather(parts, slot.contiguous())
+                for g, p_ in enumerate(parts):
+                    buf[g * per:(g + 1) * per].copy_(p_)
+            out[f] = buf[:total]
+        return out
+
+    def load(self, img, chk, *, N: int, M: int, n_terms: int = 0):
+        """img: image rows slab_range(N, world, rank); chk: chunk rows shard_range(M, world, rank) -- dicts of
+        emb / key / bbox / terms (CUDA or pinned host torch tensors, or numpy arrays)."""
+        self.N, self.M = int(N), int(M)
+        if self.world > 1:
+            img = self._replicate("img", img, N, slab_size(N, self.world))
+            chk = self._replicate("chk", chk, M, -(-M // self.world) if M else 1)
+        self.eng.set_images(img["emb"], img["key"], img.get("bbox"), img.get("terms"))
+        self.eng.set_chunks(chk["emb"], chk["key"], chk.get("bbox"), chk.get("terms"), n_terms=n_terms, col_offset=0)
+
+    # -- one step --------------------------------------------------------------------------------------
+    def run(self, *, schemas, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), kprime=0, host_outputs=False,
+            candidates="all", path="auto"):
+        eng = self.eng
+        kw = dict(candidates=candidates, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight,
+                  kprime=kprime, path=path)
+        out_kw = dict(want=("topk", "pairs", "sums"), device_outputs=not host_outputs, pinned_outputs=host_outputs)
+        if self.world == 1:
+            r = eng.run(schemas, **out_kw, **kw)
+            r["topk_row0"] = 0
+        else:
+            import time
+            import torch
+            dist, G, N, M = self.dist, self.world, self.N, self.M
+            marks = [("start", time.perf_counter())]
+
+            def mark(name):
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+                marks.append((name, time.perf_counter()))
+            lo, hi = shard_range(M, G, self.rank)
+            eng.fused_pass(schemas, shard=(lo, hi - lo), k_values=k_values, mrr_cutoff=mrr_cutoff,
+                           weak_weight=weak_weight, kprime=kprime, n_ranks=G)
+            mark("fused_pass")
+            per = slab_size(N, G)
+            stride = torch.tensor([eng.list_stride()], dtype=torch.int32, device=self.device)
+            dist.all_reduce(stride, op=self.MAX)
+            stride = int(stride.item())
+            keys, count, tau = eng.export_lists(G, per, stride)
+            rk, rc, rt = torch.empty_like(keys), torch.empty_like(count), torch.empty_like(tau)
+            dist.all_to_all_single(rk, keys)
+            dist.all_to_all_single(rc, count)
+            dist.all_to_all_single(rt, tau)
+            mark("list exchange")
+            row0, row1 = slab_range(N, G, self.rank)
+            r = eng.run(schemas, slab=(row0, row1 - row0), imported=(rk, rc, rt), **out_kw, **kw)
+            r["topk_row0"] = row0
+            mark("rescore slab")
+            S, nk = r["hits"].shape
+            packed = torch.tensor(np.concatenate([r["hits"].reshape(-1).astype(np.float64), r["rr_sum"],
+                                                  [r["sim_sum"], float(r["num_pairs"])]]),
+                                  dtype=torch.float64, device=self.device)
+            dist.all_reduce(packed)
+            packed = packed.cpu().numpy()
+            mark("metric sums")
+            r["hits"] = np.rint(packed[:S * nk]).astype(np.int64).reshape(S, nk)
+            r["rr_sum"], r["sim_sum"], r["num_pairs"] = packed[S * nk:S * nk + S], float(packed[-2]), int(round(packed[-1]))
+            r["phases_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(marks, marks[1:])}
+        r["metrics"] = metrics_from_sums(r["hits"], r["rr_sum"], r["sim_sum"], r["num_pairs"])
+        r["d2h_bytes"] = sum(r[k].nbytes for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim")) + 200 \
+            if host_outputs else 0
+        return r
+
+
+class AllGatherScorer:
+    """Fully sharded variant (module docstring): chunks never leave their rank, images replicated."""
+
     def __init__(self, engine, world: int = 1, rank: int = 0, device=None, dist=None):
         self.eng, self.world, self.rank, self.device = engine, world, rank, device
         if dist is None and world > 1:

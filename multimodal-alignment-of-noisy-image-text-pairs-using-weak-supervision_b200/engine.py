@@ -124,6 +124,11 @@ class AlignmentEngine:
         self._check(self._L.mmalign_num_pairs(self._ctx, C.byref(p)))
         return p.value
 
+    def num_pairs_range(self, row0: int, rows: int) -> int:
+        p = C.c_int64()
+        self._check(self._L.mmalign_num_pairs_range(self._ctx, int(row0), int(rows), C.byref(p)))
+        return p.value
+
     def pairs(self):
         """(pair_offsets [N+1], pair_chunk [P]) -- evaluate_alignments.py:48-69 in (image, chunk) order."""
         P = self.num_pairs()
@@ -144,7 +149,8 @@ class AlignmentEngine:
 
     # -- scoring ----------------------------------------------------------------
     @staticmethod
-    def _params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime, n_ranks=0):
+    def _params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime, n_ranks=0,
+                shard=None, slab=None):
         mask = schema_mask(schemas)
         ks = [int(k) for k in k_values]
         prm = _native.Params()
@@ -159,17 +165,27 @@ class AlignmentEngine:
         prm.path = PATHS[path] if isinstance(path, str) else int(path)
         prm.kprime = int(kprime)
         prm.n_ranks = int(n_ranks)
+        if shard is not None:  # (first chunk row, rows) the fused pass contracts against
+            prm.shard_col0, prm.shard_cols = int(shard[0]), int(shard[1])
+        if slab is not None:   # (first image row, rows) that are ranked
+            prm.slab_row0, prm.slab_rows = int(slab[0]), int(slab[1])
         return prm, mask, bin(mask).count("1"), ks
 
     def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
             mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
             path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
-            pinned_outputs=False, deep=False, stream=None):
-        prm, mask, S, ks = self._params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime)
+            pinned_outputs=False, deep=False, stream=None, slab=None, imported=None):
+        """slab=(row0, rows): rank only those image rows (outputs are sized by the slab).
+        imported=(keys, count, tau): candidate lists received from the ranks' fused passes
+        (mmalign_rescore_slab) instead of running the fused kernel here."""
+        prm, mask, S, ks = self._params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime,
+                                        slab=slab)
         kmax = max(ks) if ks else 0
         kneed = max(kmax, int(mrr_cutoff))
-        P = self.num_pairs()
-        N = self.N
+        if slab is None or tuple(slab) == (0, 0):
+            P, N = self.num_pairs(), self.N
+        else:
+            P, N = self.num_pairs_range(*slab), int(slab[1])
         res, out = {}, _native.Out()
         if device_outputs:
             import torch
@@ -217,7 +233,14 @@ class AlignmentEngine:
             out.hits, out.rr_sum, out.sim_sum = hits.ctypes.data, rr.ctypes.data, sim.ctypes.data
         out.num_pairs, out.stats = npairs.ctypes.data, stats.ctypes.data
         st = None if stream is None else C.c_void_p(int(stream))
-        self._check(self._L.mmalign_run(self._ctx, C.byref(prm), C.byref(out), st))
+        if imported is None:
+            self._check(self._L.mmalign_run(self._ctx, C.byref(prm), C.byref(out), st))
+        else:
+            keys, count, tau = imported  # [n_src, list_rows, stride], [n_src, list_rows] x 2
+            n_src, list_rows, stride = keys.shape
+            self._check(self._L.mmalign_rescore_slab(self._ctx, C.byref(prm), keys.data_ptr(), count.data_ptr(),
+                                                     tau.data_ptr(), int(n_src), int(list_rows), int(stride),
+                                                     C.byref(out), st))
         res.update(hits=hits, rr_sum=rr, sim_sum=float(sim[0]), num_pairs=int(npairs[0]),
                    stats=dict(rows_rescanned=int(stats[0]), candidates_rescored=int(stats[1]),
                               fused_launches=int(stats[2]), kernel_launches=int(stats[3]),
@@ -240,7 +263,33 @@ class AlignmentEngine:
         self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))
         return out
 
-    # -- sharded passes (device tensors; see include/mmalign.h and distributed.py) ------------
+    # -- sharded run, default exchange: contraction sharded by chunk columns, rescoring by query rows -----
+    def fused_pass(self, schemas, *, shard, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), lam_comb=None,
+                   kprime=0, n_ranks=1):
+        """K1 of every image row against chunk rows [shard[0], shard[0] + shard[1]); the lists stay in the context."""
+        prm, *_ = self._params(schemas, "all", k_values, mrr_cutoff, weak_weight, lam_comb, "auto", kprime, n_ranks,
+                               shard=shard)
+        if shard[1] == 0 and shard[0] == 0:
+            raise ValueError("fused_pass: an empty shard must be given as (M, 0), not (0, 0) = the whole table")
+        self._check(self._L.mmalign_fused_pass(self._ctx, C.byref(prm), None, None))
+
+    def list_stride(self) -> int:
+        v = C.c_int32()
+        self._check(self._L.mmalign_list_stride(self._ctx, C.byref(v)))
+        return int(v.value)
+
+    def export_lists(self, n_dest: int, slab_rows: int, stride: int):
+        """(keys [n_dest, slab_rows, stride] int64 view of u64, count [n_dest, slab_rows], tau [n_dest, slab_rows])."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        keys = torch.empty((n_dest, slab_rows, stride), dtype=torch.int64, device=dev)
+        count = torch.empty((n_dest, slab_rows), dtype=torch.int32, device=dev)
+        tau = torch.empty((n_dest, slab_rows), dtype=torch.float32, device=dev)
+        self._check(self._L.mmalign_export_lists(self._ctx, int(n_dest), int(slab_rows), int(stride), keys.data_ptr(),
+                                                 count.data_ptr(), tau.data_ptr(), None))
+        return keys, count, tau
+
+    # -- sharded passes, fully sharded variant (device tensors; see include/mmalign.h and distributed.py) ------------
     def sharded_session(self, schemas, *, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), lam_comb=None, kprime=0,
                         n_ranks=1):
         return _ShardedSession(self, schemas, k_values, mrr_cutoff, weak_weight, lam_comb, kprime, n_ranks)

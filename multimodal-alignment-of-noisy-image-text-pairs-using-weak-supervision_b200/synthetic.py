@@ -55,9 +55,10 @@ def make_numpy(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000):
 
 
 def make_torch(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, device="cuda",
-               row0=0, rows=None):
+               row0=0, rows=None, img_row0=0, img_rows=None):
     """Full-size corpora generated on the device, by GLOBAL row index in blocks of 65536 rows,
-    so that any chunk shard [row0, row0+rows) is identical whatever the world size."""
+    so that any chunk shard [row0, row0+rows) and any image slab [img_row0, img_row0+img_rows) is
+    identical whatever the world size."""
     import torch
 
     BLK = 65536
@@ -114,13 +115,16 @@ def make_torch(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, devi
     terms = (tb[:, :, :63].long() * weights).sum(-1)
     terms = torch.where(tb[:, :, 63], terms | torch.iinfo(torch.int64).min, terms).contiguous()
     chk = dict(emb=ce, key=keys(cpage), bbox=bboxes(4, row0, row0 + rows), terms=terms)
-    # images (replicated on every rank)
+    # images
+    i0 = img_row0
+    i1 = N if img_rows is None else img_row0 + img_rows
+    N = i1 - i0
     n_pages = max(1, M // CHUNKS_PER_PAGE)
-    r = uniform_rows(5, 0, N, 2)
+    r = uniform_rows(5, i0, i1, 2)
     ipage = (r[:, 0] * n_pages).long().clamp_(0, n_pages - 1)
     pick = (ipage * CHUNKS_PER_PAGE + (r[:, 1] * CHUNKS_PER_PAGE).long()).clamp_(0, M - 1)
     # the planted chunk row may live on another shard: regenerate it from its global index
-    u = unit(normal_rows(2, 0, N, D))
+    u = unit(normal_rows(2, i0, i1, D))
     ie = torch.empty((N, D), dtype=torch.float32, device=device)
     SL = 1 << 18
     for s in range(0, N, SL):
@@ -132,5 +136,5 @@ def make_torch(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, devi
             sel = (pk // BLK) == b
             src[sel] = rowsb[pk[sel] - b * BLK]
         ie[s:s + SL] = unit(src + signal * u[s:s + SL])
-    img = dict(emb=ie, key=keys(ipage), bbox=bboxes(6, 0, N), terms=None)
+    img = dict(emb=ie, key=keys(ipage), bbox=bboxes(6, i0, i1), terms=None)
     return img, chk, dict(T=T, planted=pick)

@@ -108,7 +108,7 @@ def worker(rank, world, port, q):
     lo, hi = distributed.shard_range(203, world, rank)
     shard = {k: (v[lo:hi] if v is not None else None) for k, v in chk.items()}
     eng = OracleEngine(oracle, img, shard, 64, lo)
-    sc = distributed.ShardedScorer(eng, world, rank, None, dist=dist)
+    sc = distributed.AllGatherScorer(eng, world, rank, None, dist=dist)
     r = sc.run(schemas=None, k_values=KS, mrr_cutoff=CUTOFF, weak_weight=LAM[:2], host_outputs=True)
     # gather each rank's pair ranks for the global check
     q.put((rank, lo, r["topk_idx"], r["topk_score"], r["pair_rank"], r["hits"], r["rr_sum"], r["sim_sum"],

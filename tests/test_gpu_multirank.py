@@ -1,7 +1,7 @@
-"""The multi-rank path with the REAL kernels on one GPU: two ranks run as threads, each with its own
-engine and chunk shard; a thread-barrier stand-in for torch.distributed carries the three exchanges
-(the kernels of the ranks never wait on each other, only the host threads do).  Result must equal the
-single-process oracle.  The real NCCL run is tests/test_gpu_nccl.py (needs 2 GPUs)."""
+"""The multi-rank paths with the REAL kernels on one GPU: the ranks run as threads, each with its own
+engine and shard; a thread-barrier stand-in for torch.distributed carries the exchanges (the kernels of
+the ranks never wait on each other, only the host threads do).  Results must equal the single-process
+oracle.  The real NCCL run is tests/test_gpu_nccl.py (needs 2 GPUs)."""
 import importlib
 import threading
 
@@ -32,6 +32,10 @@ class ThreadDist:
                 torch.cuda.synchronize()
                 d.bar.wait()
 
+            def all_gather_into_tensor(self, out, t):
+                n = t.shape[0]
+                self.all_gather([out[r * n:(r + 1) * n] for r in range(d.world)], t.clone())
+
             def all_to_all_single(self, out, inp):
                 torch.cuda.synchronize()
                 d.slots[rank] = inp
@@ -47,7 +51,7 @@ class ThreadDist:
                 d.slots[rank] = t.clone()
                 d.bar.wait()
                 if op == "max":
-                    s = torch.stack([d.slots[r] for r in range(d.world)]).amax(dim=0)
+                    s = torch.stack([d.slots[r] for r in range(d.world)]).amax(dim=0).to(t.dtype)
                 else:
                     s = sum(d.slots[r] for r in range(d.world))
                 torch.cuda.synchronize()
@@ -56,8 +60,70 @@ class ThreadDist:
         return _D()
 
 
+def _run_ranks(world, rank_main):
+    td = ThreadDist(world)
+    results, errors = {}, []
+
+    def guarded(rank):
+        try:
+            torch.cuda.set_device(0)
+            results[rank] = rank_main(rank, td.bind(rank))
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            td.bar.abort()
+    threads = [threading.Thread(target=guarded, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    return results
+
+
+@pytest.mark.parametrize("N,M,D,world,kprime", [(300, 2003, 128, 2, 0), (201, 5000, 512, 4, 0), (130, 4000, 64, 8, 0),
+                                                (700, 3000, 64, 3, 0), (5, 3, 64, 4, 0), (400, 6000, 64, 2, 101)])
+def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic, N, M, D, world, kprime):
+    """ShardedScorer: each rank ingests 1/G of both tables, contracts against its chunk columns, exchanges the
+    candidate lists and owns the exact results of its query slab.  D=64 makes near-ties and rescans likely;
+    kprime=101 (barely above the needed depth 100) forces uncertified rows through the exact scan."""
+    distributed = importlib.import_module(PKG_NAME + ".distributed")
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=43)
+    ks, cutoff, lam = (1, 5, 10, 20), 100, (0.3, 0.2)
+    cut = lambda d, lo, hi: {k: (v[lo:hi] if v is not None else None) for k, v in d.items()}
+
+    def rank_main(rank, dist):
+        eng = pkg.AlignmentEngine(0)
+        sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=dist)
+        sc.load(cut(img, *distributed.slab_range(N, world, rank)), cut(chk, *distributed.shard_range(M, world, rank)),
+                N=N, M=M, n_terms=512)
+        r = sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True, kprime=kprime)
+        r = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in r.items()}
+        eng.close()
+        return r
+    results = _run_ranks(world, rank_main)
+    o = oracle.evaluate(img, chk, T=512, schema_mask=15, candidates="all", lam=(lam[0], lam[1], lam[0] + lam[1]),
+                        kmax=max(ks), cutoff=cutoff)
+    rescanned = 0
+    for rank in range(world):
+        r = results[rank]
+        q0, q1 = distributed.slab_range(N, world, rank)
+        assert r["topk_row0"] == q0 and r["topk_idx"].shape[1] == q1 - q0
+        assert np.array_equal(r["topk_idx"], o["topk_idx"][:, q0:q1]) and np.array_equal(r["topk_score"], o["topk_score"][:, q0:q1])
+        p0, p1 = o["pair_offsets"][q0], o["pair_offsets"][q1]
+        assert np.array_equal(r["pair_rank"], o["pair_rank"][:, p0:p1])
+        assert np.array_equal(r["pair_sim"], o["pair_sim"][p0:p1])
+        assert r["num_pairs"] == len(o["pair_chunk"])
+        for si in range(4):
+            for q, k in enumerate(ks):
+                assert r["hits"][si, q] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
+        assert r["sim_sum"] == pytest.approx(float(o["pair_sim"].sum()), rel=1e-12)
+        rescanned += r["stats"]["rows_rescanned"]
+    if kprime:
+        assert rescanned > 0
+
+
 @pytest.mark.parametrize("N,M,D,world", [(300, 2003, 128, 2), (201, 5000, 512, 4), (130, 4000, 64, 8)])
-def test_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
+def test_fully_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
     distributed = importlib.import_module(PKG_NAME + ".distributed")
     img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=41)
     ks, cutoff, lam = (1, 5, 10, 20), 100, (0.3, 0.2)
@@ -72,7 +138,7 @@ def test_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
             eng.set_images(img["emb"], img["key"], img["bbox"], None)
             eng.set_chunks(chk["emb"][lo:hi], chk["key"][lo:hi], chk["bbox"][lo:hi], chk["terms"][lo:hi], n_terms=512,
                            col_offset=lo)
-            sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=td.bind(rank))
+            sc = distributed.AllGatherScorer(eng, world, rank, torch.device("cuda", 0), dist=td.bind(rank))
             results[rank] = (lo, hi, sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True))
             eng.close()
         except BaseException as e:  # noqa: BLE001
