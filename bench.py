@@ -321,6 +321,8 @@ def run_ours(args):
                "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_h / args.steps}
         del img_h, chk_h
 
+    if os.environ.get("MMALIGN_BENCH_RANKS"):  # every rank's view of its last step
+        print(f"[rank {rank}] phases of the last step:", json.dumps(phase_ms), file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -73,7 +73,7 @@ struct mmalign_ctx {
     bool px_ready = false;
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
-    DevBuf fail_rows, small;      // small: fail_count, cand_counter, error_flag, k_list, stats
+    DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;  // small: fail_count, cand_counter, error_flag, k_list, stats
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     CandLists lists;               // written by the last fused pass
     bool lists_valid = false;
@@ -150,7 +150,7 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     c->img.release();
     c->chk.release();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
-                      &c->fail_rows, &c->small, &c->metrics_scratch, &c->stage};
+                      &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -483,13 +483,18 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     for (int q = 1; q < 4; ++q) CU(c, cudaEventRecord(c->ev[q], st));  // overwritten by the phases that run
     if (N > 0) {
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
-            CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, cand_counter,
+            CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, nullptr, cand_counter,
                                  error_flag, nullptr, nullptr, range, st));
             launches += 1;
         } else if (prm->path == MMALIGN_PATH_EXACT || M == 0) {
-            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, range, st));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, range, nullptr, st));
             launches += 1;
         } else {
+            CU(c, c->fail_thr.reserve((size_t)img.n * sizeof(unsigned long long)));
+            CU(c, c->scan_buf.reserve(scan_scratch_bytes()));
+            CU(c, c->scan_cnt.reserve(sizeof(int32_t) * kScanSlots));
+            ScanScratch pre;
+            pre.thr = (unsigned long long *)c->fail_thr.p; pre.buf = c->scan_buf.p; pre.cnt = (int32_t *)c->scan_cnt.p;
             if (imported) {
                 CU(c, c->fail_rows.reserve((size_t)img.n * sizeof(int32_t)));
                 kprime_used = imported->kprime;
@@ -503,11 +508,11 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             const CandLists &L = imported ? *imported : c->lists;
             CU(c, cudaEventRecord(c->ev[1], st));
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, (int32_t *)c->fail_rows.p, fail_count,
-                                 cand_counter, error_flag, nullptr, nullptr, range, st));
+                                 pre.thr, cand_counter, error_flag, nullptr, nullptr, range, st));
             CU(c, cudaEventRecord(c->ev[2], st));
-            CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, range, st));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, range, &pre, st));
             CU(c, cudaEventRecord(c->ev[3], st));
-            launches += 2;
+            launches += 3;
         }
     }
     tr.mark("launch scoring");
@@ -706,11 +711,11 @@ extern "C" int mmalign_rescore_pass(mmalign_ctx *c, const mmalign_params *prm, c
     if (out.pair_rank && P) CU(c, cudaMemsetAsync(out.pair_rank, 0, (size_t)rp.S * P * sizeof(int32_t), st));
     if (N > 0) {
         if (M > 0) {
-            CU(c, launch_rescore(c->img.s, c->chk.s, c->px, rp, &c->lists, eps_dev, out, nullptr, nullptr, cand_counter,
+            CU(c, launch_rescore(c->img.s, c->chk.s, c->px, rp, &c->lists, eps_dev, out, nullptr, nullptr, nullptr, cand_counter,
                                  error_flag, tau_global, cert_count, RowRange(), st));
         } else {  // empty shard: no entries, nothing certified here
             CU(c, cudaMemsetAsync(cert_count, 0, (size_t)rp.S * N * sizeof(int32_t), st));
-            CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, nullptr, nullptr, N, out, error_flag, RowRange(), st));
+            CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, nullptr, nullptr, N, out, error_flag, RowRange(), nullptr, st));
         }
     }
     CU(c, cudaEventRecord(c->ev[2], st));
@@ -744,7 +749,7 @@ extern "C" int mmalign_rescan_rows(mmalign_ctx *c, const mmalign_params *prm, co
     outputs_from(uo, &out);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
     CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
-    CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, rows, nullptr, n_rows, out, error_flag, RowRange(), st));
+    CU(c, launch_exact_scan(c->img.s, c->chk.s, c->px, rp, rows, nullptr, n_rows, out, error_flag, RowRange(), nullptr, st));
     int32_t err = 0;
     CU(c, cudaMemcpyAsync(&err, error_flag, sizeof err, cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));

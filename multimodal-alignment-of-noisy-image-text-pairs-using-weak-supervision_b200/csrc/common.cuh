@@ -257,16 +257,25 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, vo
 // rescore.cu
 cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
-                           int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
-                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, RowRange rows,
-                           cudaStream_t st);
+                           int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
+                           unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
+                           int32_t *cert_count, RowRange rows, cudaStream_t st);
+// scratch of the two-stage exact scan: per failed row (slot) its threshold, and what stage 1 kept for it
+constexpr int kScanSlots = 2048, kScanCap = 1024;
+struct ScanScratch {
+    unsigned long long *thr = nullptr;  // [N] written by the rescoring kernel next to fail_rows
+    void *buf = nullptr;                // [kScanSlots][kScanCap] 16-byte entries
+    int32_t *cnt = nullptr;             // [kScanSlots]
+};
+size_t scan_scratch_bytes();
 constexpr int kListSlack = 8;  // a list compacted to K' entries may keep up to K' + kListSlack (fused_tc.cu)
 cudaError_t launch_export_lists(const CandLists &L, int64_t N, int n_dest, int64_t slab_rows, int stride,
                                 int64_t col_offset, uint64_t *keys, int32_t *count, float *tau, cudaStream_t st);
 cudaError_t launch_row_tau(const CandLists &L, int64_t N, float *tau_row, cudaStream_t st);
 cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                               const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
-                              const Outputs &out, int32_t *error_flag, RowRange range, cudaStream_t st);
+                              const Outputs &out, int32_t *error_flag, RowRange range, const ScanScratch *pre,
+                              cudaStream_t st);
 cudaError_t launch_alignments(const Side &img, const Side &chk, const PairIndex &px, int schema,
                               int64_t n_terms, bool raw, double *rec, cudaStream_t st);
 cudaError_t launch_pair_chunk(const PairIndex &px, int64_t N, int64_t col_offset, int64_t *pair_chunk,

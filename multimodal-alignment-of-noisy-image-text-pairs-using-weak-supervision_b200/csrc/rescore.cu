@@ -310,6 +310,7 @@ __device__ __forceinline__ void stage_row(const RowArgs &A, const RowSmem &sm, i
 // List l of image row i.  Native layout (written by the fused kernel of this GPU): one list per (column split,
 // accumulator half), local chunk indices.  Imported layout (mmalign_rescore_slab): one list per source rank,
 // global chunk indices, cnt < 0 = the source could not fit the row into the exchange stride.
+constexpr int kMaxListsPerRow = 128;
 struct ListView { const uint64_t *keys; int cnt; float tau; };
 __device__ __forceinline__ int lists_per_row(const CandLists &L) { return L.imp_keys ? L.imp_src : L.n_splits * 2; }
 __device__ __forceinline__ ListView list_view(const CandLists &L, int64_t i, int64_t row0, int l)
@@ -329,13 +330,15 @@ __device__ __forceinline__ ListView list_view(const CandLists &L, int64_t i, int
 // 64 registers -> 8 CTAs of 128 threads per SM (measured at config 5 with 256-thread CTAs: 110 ms at 64 registers against 128 / 161 ms at 80 / 124)
 __global__ void __launch_bounds__(kThreads, 8)
 rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_max,
-               int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
+               int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr, unsigned long long *cand_counter,
                const float *tau_global, int32_t *cert_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
     __shared__ int s_nca;
     __shared__ float s_tau;
+    __shared__ int s_lcnt[kMaxListsPerRow];
+    __shared__ const uint64_t *s_lkeys[kMaxListsPerRow];
     for (int64_t b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
         const int64_t i = A.row0 + b;
         const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
@@ -344,6 +347,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
         __syncthreads();
         bool overflow = c > A.sp_cap;
         bool ok = !overflow;
+        int sorted_nca = 0;  // candidates (sorted by exact cosine in sm.buf) of the last attempt that was not certified
         if (!use_lists) {
             if (ok) {
                 if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)c);
@@ -351,11 +355,14 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
             }
         } else if (ok) {
             const int n_l = lists_per_row(L);
+            const int lw = L.imp_keys ? ((L.imp_stride + 31) & ~31) : L.cap;  // >= entries of any list
             if (threadIdx.x < 32) {
                 float t = -CUDART_INF_F;
                 for (int l = threadIdx.x; l < n_l; l += 32) {
                     const ListView v = list_view(L, i, A.row0, l);
                     t = fmaxf(t, v.cnt < 0 ? CUDART_INF_F : v.tau);  // an overflowed list certifies nothing
+                    s_lcnt[l] = v.cnt;
+                    s_lkeys[l] = v.keys;
                 }
                 for (int off = 16; off >= 1; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
                 if (threadIdx.x == 0) s_tau = t;
@@ -370,12 +377,21 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
             for (int attempt = 0; ok && attempt < 2; ++attempt) {
                 if (threadIdx.x == 0) { s_nca = 0; s_tau = tau_union; }
                 __syncthreads();
-                for (int l = 0; l < n_l; ++l) {
-                    const ListView v = list_view(L, i, A.row0, l);
-                    const int cnt = v.cnt;
-                    const uint64_t *keys = v.keys;
-                    for (int e = threadIdx.x; e < cnt; e += kThreads) {
-                        const uint64_t k = keys[e];
+                // all lists of the row in one flat sweep (list = x / lw, entry = x % lw), four loads in flight per thread
+                for (int x0 = threadIdx.x; x0 < n_l * lw; x0 += 4 * kThreads) {
+                    uint64_t kk[4];
+                    bool live[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int x = x0 + u * kThreads;
+                        const int l = x / lw, e = x - l * lw;
+                        live[u] = x < n_l * lw && e < s_lcnt[l];
+                        if (live[u]) kk[u] = s_lkeys[l][e];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (!live[u]) continue;
+                        const uint64_t k = kk[u];
                         const uint32_t col = cand_col(k);
                         const float sa = cand_score(k);
                         bool same_page = false;  // same-page chunks enter through the pair index, not through the lists
@@ -408,6 +424,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                     break;
                 }
                 ok = finish_row(A, sm, i, n_ca, true, s_tau, eps);
+                sorted_nca = ok ? 0 : n_ca;
                 if (ok || !truncate) break;
                 // not certified at depth K': clear this row's ranks and retry with everything the lists hold
                 if (A.out.pair_rank)
@@ -417,8 +434,13 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
             }
         }
         if (!ok && threadIdx.x == 0) {
-            if (use_lists) fail_rows[atomicAdd(fail_count, 1)] = (int32_t)i;
-            else atomicExch(A.error_flag, 1);  // same-page mode: page larger than A.sp_cap
+            if (use_lists) {
+                const int slot = atomicAdd(fail_count, 1);
+                fail_rows[slot] = (int32_t)i;
+                // The kneed-th best exact cosine among the candidates bounds the true kneed-th best from below:
+                // the exact scan only has to look at columns that reach it (exact_prefilter_kernel).
+                if (fail_thr) fail_thr[slot] = sorted_nca >= A.rp.kneed ? sm.buf[A.rp.kneed - 1].k : 0ull;
+            } else atomicExch(A.error_flag, 1);  // same-page mode: page larger than A.sp_cap
         }
         __syncthreads();
     }
@@ -427,8 +449,64 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
 // ---------------------------------------------------------------------------
 // Exact scan
 // ---------------------------------------------------------------------------
+// Stage 1 for rows that failed the certificate: the whole GPU scans the row's columns (work item = row x column
+// split) in the canonical fp32 order and keeps what reaches the row's threshold thr (a lower bound of its kneed-th
+// best exact cosine, from the failed attempt).  Almost nothing does -- the candidate set missed the certificate
+// by a margin, not by much -- so stage 2 (exact_scan_kernel) ranks a handful of entries instead of streaming
+// M columns through one CTA.  A row whose survivors overflow `cap` is streamed by stage 2 as before.
+constexpr int kPreThreads = 256;
+constexpr int kPreMinCols = 2048;  // columns per work item, at least
+
+__global__ void __launch_bounds__(kPreThreads)
+exact_prefilter_kernel(RowArgs A, const int32_t *__restrict__ rows, const int32_t *__restrict__ n_rows_dev,
+                       const unsigned long long *__restrict__ thr, Key *scan_buf, int32_t *scan_cnt, int cap,
+                       int max_slots)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *a = reinterpret_cast<float *>(smem_raw);
+    const int n_fail = min(*n_rows_dev, max_slots);
+    if (n_fail == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int d4 = A.D >> 2;
+    int64_t n_sp = (int64_t)gridDim.x / n_fail;
+    const int64_t sp_max = (A.M + kPreMinCols - 1) / kPreMinCols;
+    if (n_sp > sp_max) n_sp = sp_max;
+    if (n_sp < 1) n_sp = 1;
+    const int64_t cols_per = (A.M + n_sp - 1) / n_sp;
+    for (int64_t w = blockIdx.x; w < (int64_t)n_fail * n_sp; w += gridDim.x) {
+        const int slot = (int)(w / n_sp);
+        const int64_t sp = w % n_sp;
+        const int64_t i = rows[slot];
+        __syncthreads();
+        for (int c = threadIdx.x; c < d4; c += kPreThreads)
+            reinterpret_cast<float4 *>(a)[c] = reinterpret_cast<const float4 *>(A.img_emb + i * A.D)[c];
+        __syncthreads();
+        const unsigned long long t = thr[slot];
+        const float na = A.img_n2[i];
+        const uint64_t ik = A.img_key[i];
+        const int64_t j0 = sp * cols_per, j1 = min(A.M, j0 + cols_per);
+        for (int64_t j = j0 + 2 * warp; j < j1; j += 2 * (kPreThreads / 32)) {
+            const int64_t jb = j + 1 < j1 ? j + 1 : j;
+            float d0, d1;
+            warp_dot2(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(A.chk_emb + j * A.D),
+                      reinterpret_cast<const float4 *>(A.chk_emb + jb * A.D), d4, lane, d0, d1);
+            if (lane < 2) {
+                const int64_t jj = lane == 0 ? j : j + 1;
+                if (jj < j1 && !(ik != MMALIGN_NULL_KEY && A.chk_key[jj] == ik)) {  // same-page chunks enter through the pair index
+                    const unsigned long long k = ord64(sim_from_sums(lane == 0 ? d0 : d1, na, A.chk_n2[jj]));
+                    if (k >= t) {
+                        const int pos = atomicAdd(scan_cnt + slot, 1);
+                        if (pos < cap) { Key x; x.k = k; x.j = (int32_t)jj; x.e = 0; scan_buf[(int64_t)slot * cap + pos] = x; }
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kThreads)
-exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host)
+exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
+                  const Key *scan_buf, const int32_t *scan_cnt, int scan_cap, int scan_slots)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
@@ -456,7 +534,15 @@ exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int
         }
         const float na = A.img_n2[i];
         const uint64_t ik = A.img_key[i];
-        for (int64_t base = 0; base < A.M; base += kScanRound) {
+        // stage 1 already found every column that can matter?
+        const int pre = (scan_buf && b < scan_slots) ? scan_cnt[b] : -1;
+        const bool prefiltered = pre >= 0 && pre <= scan_cap && pre <= A.ent_cap;
+        if (prefiltered) {
+            for (int e = threadIdx.x; e < pre; e += kThreads) sm.buf[e] = scan_buf[b * scan_cap + e];
+            if (threadIdx.x == 0) s_cnt = pre;
+            __syncthreads();
+        }
+        for (int64_t base = prefiltered ? A.M : 0; base < A.M; base += kScanRound) {
             const unsigned long long thr = s_thr;
             const int thr_j = s_thr_j;
             float my_dot = 0.f;  // lane q keeps the dot product of column base + warp * 16 + q
@@ -536,9 +622,9 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
 
 cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
-                           int32_t *fail_rows, int32_t *fail_count, unsigned long long *cand_counter,
-                           int32_t *error_flag, const float *tau_global, int32_t *cert_count, RowRange range,
-                           cudaStream_t st)
+                           int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
+                           unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
+                           int32_t *cert_count, RowRange range, cudaStream_t st)
 {
     if (img.n == 0) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
@@ -552,13 +638,14 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     if (e != cudaSuccess) return e;
     int64_t grid = A.n_rows < 148 * 16 ? A.n_rows : 148 * 16;
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
-                                                           fail_count, cand_counter, tau_global, cert_count);
+                                                           fail_count, fail_thr, cand_counter, tau_global, cert_count);
     return cudaGetLastError();
 }
 
 cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex &px, const RunParams &rp,
                               const int32_t *rows, const int32_t *n_rows_dev, int64_t n_rows_host,
-                              const Outputs &out, int32_t *error_flag, RowRange range, cudaStream_t st)
+                              const Outputs &out, int32_t *error_flag, RowRange range, const ScanScratch *pre,
+                              cudaStream_t st)
 {
     if (img.n == 0 || (!n_rows_dev && n_rows_host == 0)) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
@@ -566,11 +653,24 @@ cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex 
     const size_t smem = row_smem_bytes(img.D, A.ent_cap, A.sp_cap);
     cudaError_t e = cudaFuncSetAttribute(exact_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    const bool two_stage = pre && pre->buf && pre->thr && n_rows_dev && rows && chk.n > 0;
+    if (two_stage) {
+        e = cudaMemsetAsync(pre->cnt, 0, sizeof(int32_t) * kScanSlots, st);
+        if (e != cudaSuccess) return e;
+        exact_prefilter_kernel<<<148 * 4, kPreThreads, (size_t)img.D * sizeof(float), st>>>(
+            A, rows, n_rows_dev, pre->thr, reinterpret_cast<Key *>(pre->buf), pre->cnt, kScanCap, kScanSlots);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     int64_t grid = 148 * 4;
     if (!n_rows_dev && n_rows_host < grid) grid = n_rows_host;
-    exact_scan_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, rows, n_rows_dev, n_rows_host);
+    exact_scan_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, rows, n_rows_dev, n_rows_host,
+                                                              two_stage ? reinterpret_cast<const Key *>(pre->buf) : nullptr,
+                                                              two_stage ? pre->cnt : nullptr, kScanCap, kScanSlots);
     return cudaGetLastError();
 }
+
+size_t scan_scratch_bytes() { return (size_t)kScanSlots * kScanCap * sizeof(Key); }
 
 // ---------------------------------------------------------------------------
 // `alignments` records: src/insert_clip_embeddings.py:369-414

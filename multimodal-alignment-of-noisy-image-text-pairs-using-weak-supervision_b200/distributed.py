@@ -156,14 +156,17 @@ class ShardedScorer:
             r["topk_row0"] = row0
             mark("rescore slab")
             S, nk = r["hits"].shape
+            st = r["stats"]
             packed = torch.tensor(np.concatenate([r["hits"].reshape(-1).astype(np.float64), r["rr_sum"],
-                                                  [r["sim_sum"], float(r["num_pairs"])]]),
+                                                  [r["sim_sum"], float(r["num_pairs"]), float(st["rows_rescanned"]),
+                                                   float(st["candidates_rescored"])]]),
                                   dtype=torch.float64, device=self.device)
             dist.all_reduce(packed)
             packed = packed.cpu().numpy()
             mark("metric sums")
             r["hits"] = np.rint(packed[:S * nk]).astype(np.int64).reshape(S, nk)
-            r["rr_sum"], r["sim_sum"], r["num_pairs"] = packed[S * nk:S * nk + S], float(packed[-2]), int(round(packed[-1]))
+            r["rr_sum"], r["sim_sum"], r["num_pairs"] = packed[S * nk:S * nk + S], float(packed[-4]), int(round(packed[-3]))
+            st["rows_rescanned"], st["candidates_rescored"] = int(round(packed[-2])), int(round(packed[-1]))  # whole job
             r["phases_ms"] = {b[0]: round(1e3 * (b[1] - a[1]), 2) for a, b in zip(marks, marks[1:])}
         r["metrics"] = metrics_from_sums(r["hits"], r["rr_sum"], r["sim_sum"], r["num_pairs"])
         r["d2h_bytes"] = sum(r[k].nbytes for k in ("topk_idx", "topk_score", "pair_rank", "pair_sim")) + 200 \

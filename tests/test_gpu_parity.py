@@ -170,6 +170,35 @@ def test_fused_path_with_ties_and_forced_rescan(oracle, eng, synthetic):
     assert r["stats"]["rows_rescanned"] > 0
 
 
+@pytest.mark.parametrize("N,M,D,cutoff", [(300, 20000, 128, 100), (2500, 3000, 64, 20), (64, 900, 64, 100)])
+def test_two_stage_exact_scan(oracle, eng, synthetic, N, M, D, cutoff):
+    """K' = the needed depth: (almost) no row can be certified, so every one goes through the exact scan --
+    stage 1 (whole-GPU prefilter against the failed attempt's threshold) for the first 2048 failed rows, the
+    streaming scan for the rest and for rows without a threshold."""
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=64, seed=13)
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 5, 10, 20), cutoff=cutoff,
+                             kprime=cutoff)
+    assert r["stats"]["rows_rescanned"] > N // 2
+
+
+@pytest.mark.parametrize("path,cand", [("auto", "all"), ("exact", "all"), ("auto", "same_page")])
+def test_row_slab(oracle, eng, synthetic, path, cand):
+    """mmalign_run restricted to image rows [row0, row0 + rows): outputs are the slab's slice of the full result."""
+    img, chk, _ = synthetic.make_numpy(500, 3000, 128, T=64, seed=17)
+    load(eng, img, chk, 64)
+    ks, cutoff, lam = (1, 5, 10), 30, (0.3, 0.2)
+    o = oracle.evaluate(img, chk, T=64, schema_mask=15, candidates=cand, lam=(lam[0], lam[1], lam[0] + lam[1]), kmax=10,
+                        cutoff=cutoff)
+    for r0, rows in [(0, 200), (200, 300), (128, 129), (499, 1), (500, 0)]:
+        r = eng.run(ALL4, candidates=cand, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, path=path, slab=(r0, rows))
+        p0, p1 = o["pair_offsets"][r0], o["pair_offsets"][r0 + rows]
+        assert r["num_pairs"] == p1 - p0
+        assert np.array_equal(r["topk_idx"], o["topk_idx"][:, r0:r0 + rows])
+        assert np.array_equal(r["topk_score"], o["topk_score"][:, r0:r0 + rows])
+        assert np.array_equal(r["pair_rank"], o["pair_rank"][:, p0:p1])
+        assert np.array_equal(r["pair_sim"], o["pair_sim"][p0:p1])
+
+
 def test_edge_shapes(oracle, eng, synthetic, pkg):
     img, chk, _ = synthetic.make_numpy(5, 64, 64, T=64, seed=1)
     empty = dict(emb=np.zeros((0, 64), np.float32), key=np.zeros(0, np.uint64), bbox=np.zeros((0, 4)), terms=None)
