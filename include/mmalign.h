@@ -79,7 +79,8 @@ typedef struct {
     int32_t path;          /* MMALIGN_PATH_* */
     int32_t kprime;        /* depth the fused kernel's candidate lists are complete to; 0 = auto */
     int32_t n_ranks;       /* sharded passes: number of GPUs the chunk table is sharded over; 0/1 = one */
-    int32_t reserved0;
+    float eps_scale;       /* multiplies the certificate's error bound eps; 0 = 1.0.  Values above 1 only make the
+                              certificate more conservative (more rows take the exact scan), never less exact */
     int64_t shard_col0;    /* mmalign_fused_pass: the contraction runs on chunk rows [shard_col0, shard_col0 + */
     int64_t shard_cols;    /*   shard_cols) of the table given to set_chunks; 0, 0 = the whole table          */
     int64_t slab_row0;     /* mmalign_rescore_slab: image rows [slab_row0, slab_row0 + slab_rows) are ranked;  */

@@ -23,7 +23,7 @@ class Params(C.Structure):
     _fields_ = [("schema_mask", C.c_uint32), ("candidates", C.c_int32), ("n_k", C.c_int32),
                 ("k_list", C.c_int32 * 8), ("mrr_cutoff", C.c_int32), ("lam_lex", C.c_double),
                 ("lam_pos", C.c_double), ("lam_comb", C.c_double), ("path", C.c_int32),
-                ("kprime", C.c_int32), ("n_ranks", C.c_int32), ("reserved0", C.c_int32),
+                ("kprime", C.c_int32), ("n_ranks", C.c_int32), ("eps_scale", C.c_float),
                 ("shard_col0", C.c_int64), ("shard_cols", C.c_int64), ("slab_row0", C.c_int64),
                 ("slab_rows", C.c_int64)]
 

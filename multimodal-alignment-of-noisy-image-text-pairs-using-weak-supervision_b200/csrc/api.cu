@@ -355,6 +355,8 @@ static int parse_params(mmalign_ctx *c, const mmalign_params *prm, RunParams *ou
     rp.lam_lex = prm->lam_lex; rp.lam_pos = prm->lam_pos; rp.lam_comb = prm->lam_comb;
     rp.n_terms = c->n_terms;
     rp.col_offset = c->col_offset;
+    if (prm->eps_scale < 0.f || prm->eps_scale > 1e6f) return fail(c, MMALIGN_EINVAL, "eps_scale=%g must be in 0..1e6 (0 = 1)", (double)prm->eps_scale);
+    rp.eps_scale = prm->eps_scale > 0.f ? prm->eps_scale : 1.f;
     const bool needs_terms = (prm->schema_mask & (MMALIGN_LEXICAL | MMALIGN_COMBINED)) != 0;
     if (needs_terms && !chk.terms && chk.n > 0) return fail(c, MMALIGN_EINVAL, "lexical schema requested but the chunks have no term sets");
     if (prm->path < 0 || prm->path > 2) return fail(c, MMALIGN_EINVAL, "path=%d unknown", prm->path);

@@ -51,6 +51,7 @@ struct RunParams {
     double lam_lex, lam_pos, lam_comb;
     int64_t n_terms;       // T = len(lexical_components)
     int64_t col_offset;    // global index of local chunk 0
+    float eps_scale;       // certificate margin multiplier (>= 1 in production)
 };
 
 struct Outputs {           // device pointers (api.cu stages host outputs)

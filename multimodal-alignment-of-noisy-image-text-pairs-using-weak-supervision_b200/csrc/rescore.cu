@@ -53,12 +53,13 @@ struct RowSmem {
     double *sp_lex, *sp_pos;    // [A.sp_cap] raw lexical / positional score of the same-page entries
     int32_t *sp_cols;           // [A.sp_cap] the row's same-page chunks (local index, increasing)
     int32_t *cols;              // [A.ent_cap]
+    float *approx;              // [A.ent_cap] approximate scores of the row's union of lists, sorted descending
     float *a;                   // [D]
 };
 
 __host__ __device__ inline size_t row_smem_bytes(int D, int ent_cap, int sp_cap)
 {
-    return (size_t)ent_cap * (sizeof(Key) + sizeof(double) + sizeof(int32_t)) +
+    return (size_t)ent_cap * (sizeof(Key) + sizeof(double) + sizeof(int32_t) + sizeof(float)) +
            (size_t)sp_cap * (3 * sizeof(double) + sizeof(unsigned long long) + sizeof(int32_t)) + (size_t)D * sizeof(float);
 }
 
@@ -81,6 +82,8 @@ __device__ __forceinline__ RowSmem carve(unsigned char *base, int ent_cap, int s
     base += (size_t)ent_cap * sizeof(int32_t);
     r.sp_cols = reinterpret_cast<int32_t *>(base);
     base += (size_t)sp_cap * sizeof(int32_t);
+    r.approx = reinterpret_cast<float *>(base);
+    base += (size_t)ent_cap * sizeof(float);
     r.a = reinterpret_cast<float *>(base);
     return r;
 }
@@ -111,60 +114,122 @@ __device__ __forceinline__ int next_pow2(int n)
     return p;
 }
 
-// Sorts buf[0, n) best-first; every thread of the block must call it.  Up to 256 keys the network runs in
-// registers (one key per thread; strides below 32 are warp shuffles, the six wider ones go through buf);
-// larger inputs use the classic shared-memory network over the next power of two.
-__device__ void sort_keys(Key *buf, int n)
+// ---------------------------------------------------------------------------
+// Block-wide sorts.  Bitonic networks with the keys in registers: strides below 32 are warp shuffles, wider ones
+// go through shared memory.  KPT = keys per thread: one (up to 128 keys; the network stops at the next power of
+// two >= n) or two (up to 256 keys).  Every thread of the block must call them.
+// ---------------------------------------------------------------------------
+struct KeyOps {        // exact ranking keys: (score desc, chunk index asc)
+    typedef Key T;
+    static __device__ __forceinline__ Key pad() { return key_pad(); }
+    static __device__ __forceinline__ bool before(const Key &a, const Key &b) { return key_before(a.k, a.j, b.k, b.j); }
+    static __device__ __forceinline__ Key shfl(const Key &x, int j)
+    {
+        Key o;
+        o.k = __shfl_xor_sync(0xFFFFFFFFu, x.k, j);
+        o.j = __shfl_xor_sync(0xFFFFFFFFu, x.j, j);
+        o.e = __shfl_xor_sync(0xFFFFFFFFu, x.e, j);
+        return o;
+    }
+};
+struct PackedOps {     // approximate scores: one 64-bit key, hi = ordered fp32 score, lo = ~column; descending
+    typedef unsigned long long T;
+    static __device__ __forceinline__ T pad() { return 0ull; }
+    static __device__ __forceinline__ bool before(T a, T b) { return a > b; }
+    static __device__ __forceinline__ T shfl(T x, int j) { return __shfl_xor_sync(0xFFFFFFFFu, x, j); }
+};
+__device__ __forceinline__ unsigned long long pack_approx(float score, uint32_t col)
 {
+    return ((unsigned long long)f32_ordered(score) << 32) | (unsigned long long)(0xFFFFFFFFu - col);
+}
+__device__ __forceinline__ float packed_score(unsigned long long k) { return f32_unordered((uint32_t)(k >> 32)); }
+__device__ __forceinline__ int32_t packed_col(unsigned long long k) { return (int32_t)(0xFFFFFFFFu - (uint32_t)k); }
+
+template <typename Ops>
+__device__ void sort_regs1(typename Ops::T *buf, int n)  // n <= kThreads
+{
+    typedef typename Ops::T T;
     const int tid = threadIdx.x;
-    if (n <= 2 * kThreads) {
-        // keys tid and tid + kThreads live in registers
-        Key me[2];
-        me[0] = tid < n ? buf[tid] : key_pad();
-        me[1] = tid + kThreads < n ? buf[tid + kThreads] : key_pad();
-        __syncthreads();
-        for (int k = 2; k <= 2 * kThreads; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                Key o[2];
-                if (j == kThreads) {
-                    o[0] = me[1]; o[1] = me[0];
-                } else if (j >= 32) {
-                    buf[tid] = me[0]; buf[tid + kThreads] = me[1];
-                    __syncthreads();
-                    o[0] = buf[tid ^ j]; o[1] = buf[(tid ^ j) + kThreads];
-                    __syncthreads();
-                } else {
+    int m = 32;
+    while (m < n) m <<= 1;
+    T me = tid < n ? buf[tid] : Ops::pad();
+    __syncthreads();
+    for (int k = 2; k <= m; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            T o;
+            if (j >= 32) {
+                buf[tid] = me;
+                __syncthreads();
+                o = buf[tid ^ j];
+                __syncthreads();
+            } else {
+                o = Ops::shfl(me, j);
+            }
+            const bool lower = (tid & j) == 0, up = (tid & k) == 0;
+            const bool o_first = Ops::before(o, me);
+            if ((lower == up) ? o_first : !o_first) me = o;
+        }
+    }
+    buf[tid] = me;
+    __syncthreads();
+}
+
+template <typename Ops>
+__device__ void sort_regs2(typename Ops::T *buf, int n)  // n <= 2 * kThreads; keys tid and tid + kThreads live in registers
+{
+    typedef typename Ops::T T;
+    const int tid = threadIdx.x;
+    T me[2];
+    me[0] = tid < n ? buf[tid] : Ops::pad();
+    me[1] = tid + kThreads < n ? buf[tid + kThreads] : Ops::pad();
+    __syncthreads();
+    for (int k = 2; k <= 2 * kThreads; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            T o[2];
+            if (j == kThreads) {
+                o[0] = me[1]; o[1] = me[0];
+            } else if (j >= 32) {
+                buf[tid] = me[0]; buf[tid + kThreads] = me[1];
+                __syncthreads();
+                o[0] = buf[tid ^ j]; o[1] = buf[(tid ^ j) + kThreads];
+                __syncthreads();
+            } else {
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-                        o[r].k = __shfl_xor_sync(0xFFFFFFFFu, me[r].k, j);
-                        o[r].j = __shfl_xor_sync(0xFFFFFFFFu, me[r].j, j);
-                        o[r].e = __shfl_xor_sync(0xFFFFFFFFu, me[r].e, j);
-                    }
-                }
+                for (int r = 0; r < 2; ++r) o[r] = Ops::shfl(me[r], j);
+            }
 #pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                    const int i = tid + r * kThreads;
-                    const bool lower = (i & j) == 0, up = (i & k) == 0;
-                    const bool o_first = key_before(o[r].k, o[r].j, me[r].k, me[r].j);
-                    if ((lower == up) ? o_first : !o_first) me[r] = o[r];
-                }
+            for (int r = 0; r < 2; ++r) {
+                const int i = tid + r * kThreads;
+                const bool lower = (i & j) == 0, up = (i & k) == 0;
+                const bool o_first = Ops::before(o[r], me[r]);
+                if ((lower == up) ? o_first : !o_first) me[r] = o[r];
             }
         }
-        buf[tid] = me[0]; buf[tid + kThreads] = me[1];
-        __syncthreads();
-        return;
     }
+    buf[tid] = me[0]; buf[tid + kThreads] = me[1];
+    __syncthreads();
+}
+
+// Sorts buf[0, n) best-first.  Up to 256 keys in registers; larger inputs (the exact scan's streaming buffer, very
+// long unions) use the classic shared-memory network over the next power of two (buf must have room for it).
+template <typename Ops>
+__device__ void sort_block(typename Ops::T *buf, int n)
+{
+    typedef typename Ops::T T;
+    const int tid = threadIdx.x;
+    if (n <= kThreads) { sort_regs1<Ops>(buf, n); return; }
+    if (n <= 2 * kThreads) { sort_regs2<Ops>(buf, n); return; }
     const int n2 = next_pow2(n);
-    for (int e = n + tid; e < n2; e += kThreads) buf[e] = key_pad();
+    for (int e = n + tid; e < n2; e += kThreads) buf[e] = Ops::pad();
     __syncthreads();
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < n2; t += kThreads) {
                 const int x = t ^ j;
                 if (x > t) {
-                    const Key a = buf[t], b = buf[x];
+                    const T a = buf[t], b = buf[x];
                     const bool first_half = (t & k) == 0;
-                    const bool b_first = key_before(b.k, b.j, a.k, a.j);
+                    const bool b_first = Ops::before(b, a);
                     if (first_half ? b_first : !b_first) { buf[t] = b; buf[x] = a; }
                 }
             }
@@ -172,28 +237,20 @@ __device__ void sort_keys(Key *buf, int n)
         }
     }
 }
+__device__ void sort_keys(Key *buf, int n) { sort_block<KeyOps>(buf, n); }
 
-// Row i: entries [0, n_ca) are candidate columns (cols[]), never same-page; the same-page chunks are
-// appended here.  The candidates are sorted once by exact cosine (every schema ranks them alike); each
-// schema then merges its same-page entries (cosine + weak-supervision bonus) by counting.
-// Returns false when the row is not certified.
-__device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n_ca, bool certify,
-                           float tau, float eps, int32_t *cert_count = nullptr)
+// Entries of image row i in shared memory: [0, c) its same-page chunks (the true pairs, sm.sp_cols), then
+// [c, c + n_ca) candidate columns, never same-page.
+//
+// score_same_page: raw weak-supervision terms and exact cosine of the same-page entries (schema-independent).
+__device__ void score_same_page(const RowArgs &A, const RowSmem &sm, int64_t i, int c)
 {
-    __shared__ double s_kth;
-    __shared__ int s_cert;
-    const double cert_thr = (double)tau + (double)eps;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
-    const int64_t p0 = A.offsets[i] - A.pair0;  // position of the row's first pair in the per-pair outputs
-    const int64_t io = i - A.row0;               // position of the row in the per-row outputs
-    const int n = n_ca + c;
     const int d4 = A.D >> 2;
     const RunParams &rp = A.rp;
-    // same-page entries: columns were staged by the caller (sm.sp_cols); their raw weak terms are schema-independent
     for (int p = threadIdx.x; p < c; p += kThreads) {
         const int j = sm.sp_cols[p];
-        sm.cols[n_ca + p] = j;
+        sm.cols[p] = j;
         double lex = 0.0, pos = 0.0;
         if (A.need_lex)
             lex = lexical_score(term_hits(A.chk_terms + (int64_t)j * A.term_words,
@@ -203,9 +260,76 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         sm.sp_pos[p] = pos;
     }
     __syncthreads();
-    // exact cosine of every entry
+    for (int e = warp; e < c; e += 2 * kWarps) {
+        const int e1 = e + kWarps;
+        const int j0 = sm.cols[e], j1 = e1 < c ? sm.cols[e1] : j0;
+        float d0, d1;
+        warp_dot2(reinterpret_cast<const float4 *>(sm.a), reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)j0 * A.D),
+                  reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)j1 * A.D), d4, lane, d0, d1);
+        if (lane == 0) sm.cosv[e] = (double)d0;
+        if (lane == 1 && e1 < c) sm.cosv[e1] = (double)d1;
+    }
+    __syncthreads();
     const float na = A.img_n2[i];
-    for (int e = warp; e < n; e += 2 * kWarps) {
+    const int64_t p0 = A.offsets[i] - A.pair0;
+    for (int e = threadIdx.x; e < c; e += kThreads) {
+        const double x = sim_from_sums((float)sm.cosv[e], na, A.chk_n2[sm.cols[e]]);
+        sm.cosv[e] = x;
+        if (A.out.pair_sim) A.out.pair_sim[p0 + e] = x;
+    }
+    __syncthreads();
+}
+
+// ranking score of same-page entry p in schema s (cosine + weighted alignment records)
+__device__ __forceinline__ double same_page_score(const RunParams &rp, const RowSmem &sm, int s, int p)
+{
+    double w = 0.0;
+    if (s != 0) {
+        double rec[3];
+        weak_records(schema_uses_lex(s), schema_uses_pos(s), schema_uses_lex(s) ? sm.sp_lex[p] : 0.0,
+                     schema_uses_pos(s) ? sm.sp_pos[p] : 0.0, rec);
+        w = rp.lam_lex * rec[0] + rp.lam_pos * rec[1] + rp.lam_comb * rec[2];
+    }
+    return sm.cosv[p] + w;
+}
+
+// Number of values > x in approx[0, n), sorted descending.
+__device__ __forceinline__ int count_above(const float *approx, int n, double x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((double)approx[mid] > x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// finish_row: exact cosine of the n_ca candidates, one sort of the candidates by exact cosine (every schema ranks
+// them alike), then per schema the same-page entries are merged by counting; top-K lists, true-pair ranks.
+// score_same_page() must have run.
+//
+// Certificate (`bound` > -inf): every column that was NOT re-scored has exact cosine <= bound.  The row is
+// certified when, in every schema, the kmax-th best score exceeds bound (the top-K list is final) and every true
+// pair either scores above bound (its rank among the re-scored entries is its rank), or already has kneed
+// entries ahead of it -- counting the un-re-scored candidates whose approximate score exceeds the pair's by more
+// than eps (approx[n_ca, n_approx), sorted descending): its rank is beyond the cutoff either way.
+// Returns false when the row is not certified.
+__device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n_ca, double bound, double eps,
+                           const float *approx, int n_approx, int32_t *cert_count = nullptr)
+{
+    __shared__ double s_kth;
+    __shared__ int s_cert, s_bad;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
+    const int64_t p0 = A.offsets[i] - A.pair0;  // position of the row's first pair in the per-pair outputs
+    const int64_t io = i - A.row0;               // position of the row in the per-row outputs
+    const int n = n_ca + c;
+    const int d4 = A.D >> 2;
+    const RunParams &rp = A.rp;
+    const bool certify = bound > -CUDART_INF;
+    // exact cosine of the candidates
+    const float na = A.img_n2[i];
+    for (int e = c + warp; e < n; e += 2 * kWarps) {
         const int e1 = e + kWarps;
         const int j0 = sm.cols[e], j1 = e1 < n ? sm.cols[e1] : j0;
         float d0, d1;
@@ -215,31 +339,21 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         if (lane == 1 && e1 < n) sm.cosv[e1] = (double)d1;
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < n; e += kThreads)
-        sm.cosv[e] = sim_from_sums((float)sm.cosv[e], na, A.chk_n2[sm.cols[e]]);
-    __syncthreads();
-    if (A.out.pair_sim)
-        for (int p = threadIdx.x; p < c; p += kThreads) A.out.pair_sim[p0 + p] = sm.cosv[n_ca + p];
-    for (int e = threadIdx.x; e < n_ca; e += kThreads) {
-        Key x; x.k = ord64(sm.cosv[e]); x.j = sm.cols[e]; x.e = e;
-        sm.buf[e] = x;
+    for (int e = c + threadIdx.x; e < n; e += kThreads) {
+        const double x = sim_from_sums((float)sm.cosv[e], na, A.chk_n2[sm.cols[e]]);
+        sm.cosv[e] = x;
+        Key k; k.k = ord64(x); k.j = sm.cols[e]; k.e = e;
+        sm.buf[e - c] = k;
     }
     __syncthreads();
     sort_keys(sm.buf, n_ca);
     bool ok = true;
     for (int si = 0; si < rp.S; ++si) {
         const int s = rp.schema[si];
-        if (threadIdx.x == 0) { s_kth = -CUDART_INF; s_cert = 0; }
+        if (threadIdx.x == 0) { s_kth = -CUDART_INF; s_cert = 0; s_bad = 0; }
         // ranking score of the same-page entries in this schema
         for (int p = threadIdx.x; p < c; p += kThreads) {
-            double w = 0.0;
-            if (s != 0) {
-                double rec[3];
-                weak_records(schema_uses_lex(s), schema_uses_pos(s), schema_uses_lex(s) ? sm.sp_lex[p] : 0.0,
-                             schema_uses_pos(s) ? sm.sp_pos[p] : 0.0, rec);
-                w = rp.lam_lex * rec[0] + rp.lam_pos * rec[1] + rp.lam_comb * rec[2];
-            }
-            const double sc = sm.cosv[n_ca + p] + w;
+            const double sc = same_page_score(rp, sm, s, p);
             sm.sp_s[p] = sc;
             sm.sp_k[p] = ord64(sc);
             if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P_out + p0 + p] = sc;
@@ -252,20 +366,28 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
             int j, pos;
             double sc;
             if (t < c) {  // a same-page entry: binary search in the sorted candidates, count the other same-page entries
-                k = sm.sp_k[t]; j = sm.cols[n_ca + t]; sc = sm.sp_s[t];
+                k = sm.sp_k[t]; j = sm.cols[t]; sc = sm.sp_s[t];
                 int lo = 0, hi = n_ca;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
                     if (key_before(sm.buf[mid].k, sm.buf[mid].j, k, j)) lo = mid + 1; else hi = mid;
                 }
                 pos = lo;
-                for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[n_ca + q], k, j);
-                if (pos < rp.kneed && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P_out + p0 + t] = pos + 1;
+                for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[q], k, j);
+                if (pos < rp.kneed) {
+                    bool known = true;  // pos is the pair's rank ...
+                    if (certify && !(sc > bound)) {  // ... unless a column that was not re-scored may beat it
+                        const int ahead = approx ? count_above(approx, n_approx, sc + eps) - n_ca : 0;
+                        known = false;
+                        if (pos + (ahead > 0 ? ahead : 0) < rp.kneed) s_bad = 1;  // else: beyond the cutoff either way
+                    }
+                    if (known && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P_out + p0 + t] = pos + 1;
+                }
             } else {      // a candidate: its sorted position + the same-page entries that beat it
                 const Key x = sm.buf[t - c];
                 k = x.k; j = x.j; sc = sm.cosv[x.e];
                 pos = t - c;
-                for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[n_ca + q], k, j);
+                for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[q], k, j);
             }
             if (pos < rp.kmax && A.out.topk_idx) {
                 A.out.topk_idx[o_top + pos] = (int64_t)j + rp.col_offset;
@@ -275,18 +397,18 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
                 A.out.deep_idx[o_deep + pos] = (int64_t)j + rp.col_offset;
                 A.out.deep_score[o_deep + pos] = sc;
             }
-            if (pos == rp.kneed - 1) s_kth = sc;
-            if (cert_count && sc > cert_thr) atomicAdd(&s_cert, 1);
+            if (pos == rp.kmax - 1) s_kth = sc;
+            if (cert_count && sc > bound) atomicAdd(&s_cert, 1);
         }
         for (int r = n + threadIdx.x; r < rp.kneed; r += kThreads) {  // fewer entries than the lists are wide
             if (r < rp.kmax && A.out.topk_idx) { A.out.topk_idx[o_top + r] = -1; A.out.topk_score[o_top + r] = -CUDART_INF; }
             if (A.out.deep_idx) { A.out.deep_idx[o_deep + r] = -1; A.out.deep_score[o_deep + r] = -CUDART_INF; }
         }
         __syncthreads();
-        if (certify && tau > -CUDART_INF_F) ok = ok && (n >= rp.kneed) && (s_kth > cert_thr);
-        // sharded runs certify globally: this rank's entries that are provably above every column it left out
+        if (certify && !cert_count) ok = ok && !s_bad && (s_kth > bound);
+        // fully sharded runs certify globally: this rank's entries that are provably above every column it left out
         // (counted among its best kneed + same-page entries, which is all the global test needs)
-        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.n_rows + io] = tau > -CUDART_INF_F ? s_cert : rp.kneed;
+        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.n_rows + io] = certify ? s_cert : rp.kneed;
         __syncthreads();
     }
     return ok;
@@ -328,6 +450,16 @@ __device__ __forceinline__ ListView list_view(const CandLists &L, int64_t i, int
 }
 
 // 64 registers -> 8 CTAs of 128 threads per SM (measured at config 5 with 256-thread CTAs: 110 ms at 64 registers against 128 / 161 ms at 80 / 124)
+//
+// Depth of the exact rescoring (lists mode).  The row's union of lists, sorted by approximate score a_(1) >= a_(2) ..,
+// is complete above tau_union, and |exact - approximate| <= eps.  Exact scores are needed only for candidates that
+// can change an output:
+//   * the top-Kmax lists: everything with a >= a_(Kmax) - 2 eps (the Kmax best by approximate score have exact
+//     cosine >= a_(Kmax) - eps, which whatever lies below that line cannot reach);
+//   * the rank of a true pair with ranking score y: everything with a >= y - eps -- unless kneed candidates have
+//     a > y + eps, in which case the pair is beyond the cutoff whatever their exact scores are.
+// theta = the lowest of these lines (never below tau_union): ~40 candidates per row instead of K' ~ 190 when no
+// true pair is near the cutoff.  finish_row() then proves the result with the row's certificate.
 __global__ void __launch_bounds__(kThreads, 8)
 rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_max,
                int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr, unsigned long long *cand_counter,
@@ -337,25 +469,28 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
     const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
     __shared__ int s_nca;
     __shared__ float s_tau;
+    __shared__ unsigned long long s_theta;  // ord64 of the lowest line, shared minimum
     __shared__ int s_lcnt[kMaxListsPerRow];
     __shared__ const uint64_t *s_lkeys[kMaxListsPerRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const RunParams &rp = A.rp;
+    unsigned long long *packed = reinterpret_cast<unsigned long long *>(sm.buf);  // the union, before it is re-scored
     for (int64_t b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
         const int64_t i = A.row0 + b;
         const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
-        if (threadIdx.x == 0) { s_nca = 0; s_tau = -CUDART_INF_F; }
+        if (threadIdx.x == 0) { s_nca = 0; s_tau = -CUDART_INF_F; s_theta = ~0ull; }
         stage_row(A, sm, i);
         __syncthreads();
-        bool overflow = c > A.sp_cap;
-        bool ok = !overflow;
-        int sorted_nca = 0;  // candidates (sorted by exact cosine in sm.buf) of the last attempt that was not certified
+        bool ok = c <= A.sp_cap;
+        unsigned long long thr = 0ull;  // lower bound of the row's kneed-th best exact cosine, for the exact scan
         if (!use_lists) {
             if (ok) {
                 if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)c);
-                finish_row(A, sm, i, 0, false, 0.f, 0.f);
+                score_same_page(A, sm, i, c);
+                finish_row(A, sm, i, 0, -CUDART_INF, 0.0, nullptr, 0);
             }
         } else if (ok) {
             const int n_l = lists_per_row(L);
-            const int lw = L.imp_keys ? ((L.imp_stride + 31) & ~31) : L.cap;  // >= entries of any list
             if (threadIdx.x < 32) {
                 float t = -CUDART_INF_F;
                 for (int l = threadIdx.x; l < n_l; l += 32) {
@@ -367,31 +502,23 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 for (int off = 16; off >= 1; off >>= 1) t = fmaxf(t, __shfl_xor_sync(0xFFFFFFFFu, t, off));
                 if (threadIdx.x == 0) s_tau = t;
             }
-            __syncthreads();
-            // the union of the lists is complete above this (sharded runs: the maximum over all ranks)
+            score_same_page(A, sm, i, c);  // (its barriers also publish s_tau / s_lcnt / s_lkeys)
+            // the union of the lists is complete above this (fully sharded runs: the maximum over all ranks)
             const float tau_union = tau_global ? fmaxf(tau_global[i], s_tau) : s_tau;
             if (tau_union == CUDART_INF_F) ok = false;
             const uint64_t ik = A.img_key[i];
-            const float eps = A.img_err[i] * 1.001f + eps_chunk_max[0] * 1.001f + (float)A.D * 2.4e-7f + 2e-6f;
-            // attempt 0: the best K' of the union by approximate score; attempt 1: the whole union
-            for (int attempt = 0; ok && attempt < 2; ++attempt) {
-                if (threadIdx.x == 0) { s_nca = 0; s_tau = tau_union; }
-                __syncthreads();
-                // all lists of the row in one flat sweep (list = x / lw, entry = x % lw), four loads in flight per thread
-                for (int x0 = threadIdx.x; x0 < n_l * lw; x0 += 4 * kThreads) {
-                    uint64_t kk[4];
-                    bool live[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int x = x0 + u * kThreads;
-                        const int l = x / lw, e = x - l * lw;
-                        live[u] = x < n_l * lw && e < s_lcnt[l];
-                        if (live[u]) kk[u] = s_lkeys[l][e];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (!live[u]) continue;
-                        const uint64_t k = kk[u];
+            const double eps = (double)rp.eps_scale *
+                               (double)(A.img_err[i] * 1.001f + eps_chunk_max[0] * 1.001f + (float)A.D * 2.4e-7f + 2e-6f);
+            if (ok) {
+                // few long lists (this GPU's fused kernel): the block sweeps one list at a time; many short ones
+                // (one per source rank): one list per warp, so their loads overlap
+                const bool per_warp = n_l >= kWarps;
+                const int l_step = per_warp ? kWarps : 1, e0 = per_warp ? lane : threadIdx.x, e_step = per_warp ? 32 : kThreads;
+                for (int l = per_warp ? warp : 0; l < n_l; l += l_step) {
+                    const int cnt = s_lcnt[l];
+                    const uint64_t *keys = s_lkeys[l];
+                    for (int e = e0; e < cnt; e += e_step) {
+                        const uint64_t k = keys[e];
                         const uint32_t col = cand_col(k);
                         const float sa = cand_score(k);
                         bool same_page = false;  // same-page chunks enter through the pair index, not through the lists
@@ -401,46 +528,53 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                         }
                         if (sa > tau_union && !same_page) {
                             const int pos = atomicAdd(&s_nca, 1);
-                            if (pos < A.ent_cap) { Key x; x.k = ord64((double)sa); x.j = (int32_t)col; x.e = (int32_t)__float_as_int(sa); sm.buf[pos] = x; }
+                            if (pos < A.ent_cap) packed[pos] = pack_approx(sa, col);
                         }
                     }
                 }
                 __syncthreads();
                 const int n_all = s_nca;
-                if (n_all + c > A.ent_cap) { ok = false; break; }
-                const bool truncate = !tau_global && attempt == 0 && n_all > L.kprime;
-                if (truncate) {
-                    sort_keys(sm.buf, n_all);
-                    // the union stays complete above the last kept approximate score
-                    if (threadIdx.x == 0) { s_nca = L.kprime; s_tau = __int_as_float(sm.buf[L.kprime - 1].e); }
+                if (n_all + c > A.ent_cap) ok = false;
+                if (ok) {
+                    sort_block<PackedOps>(packed, n_all);  // by approximate score, lower column first
+                    for (int e = threadIdx.x; e < n_all; e += kThreads) sm.approx[e] = packed_score(packed[e]);
                     __syncthreads();
+                    if (n_all >= rp.kneed) thr = ord64((double)sm.approx[rp.kneed - 1] - eps);
+                    int n_ca = n_all;
+                    if (!tau_global) {
+                        // lowest line that needs exact scores
+                        if (threadIdx.x == 0 && n_all >= rp.kmax)
+                            atomicMin(&s_theta, ord64((double)sm.approx[rp.kmax - 1] - 2.0 * eps));
+                        for (int t = threadIdx.x; t < c * rp.S; t += kThreads) {
+                            const double y = same_page_score(rp, sm, rp.schema[t / c], t % c);
+                            if (count_above(sm.approx, n_all, y + eps) < rp.kneed) atomicMin(&s_theta, ord64(y - eps));
+                        }
+                        __syncthreads();
+                        const unsigned long long theta = n_all >= rp.kmax ? s_theta : 0ull;
+                        // candidates at or above theta
+                        int lo = 0, hi = n_all;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (ord64((double)sm.approx[mid]) >= theta) lo = mid + 1; else hi = mid;
+                        }
+                        n_ca = lo;
+                    }
+                    // nothing that is not re-scored can have an exact cosine above this
+                    const double bound = (double)(n_ca < n_all ? fmaxf(sm.approx[n_ca], tau_union) : tau_union) + eps;
+                    for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[c + e] = packed_col(packed[e]);
+                    __syncthreads();
+                    if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)(n_ca + c));
+                    if (tau_global) finish_row(A, sm, i, n_ca, bound, eps, nullptr, 0, cert_count);  // certified after the cross-rank count
+                    else ok = finish_row(A, sm, i, n_ca, bound, eps, sm.approx, n_all);
                 }
-                const int n_ca = s_nca;
-                for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[e] = sm.buf[e].j;
-                __syncthreads();
-                if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)(n_ca + c));
-                if (tau_global) {  // certified after the cross-rank count, not here
-                    finish_row(A, sm, i, n_ca, false, s_tau, eps, cert_count);
-                    break;
-                }
-                ok = finish_row(A, sm, i, n_ca, true, s_tau, eps);
-                sorted_nca = ok ? 0 : n_ca;
-                if (ok || !truncate) break;
-                // not certified at depth K': clear this row's ranks and retry with everything the lists hold
-                if (A.out.pair_rank)
-                    for (int t = threadIdx.x; t < c * A.rp.S; t += kThreads)
-                        A.out.pair_rank[(int64_t)(t / c) * A.P_out + (A.offsets[i] - A.pair0) + (t % c)] = 0;
-                __syncthreads();
             }
         }
         if (!ok && threadIdx.x == 0) {
-            if (use_lists) {
+            if (use_lists && fail_rows) {
                 const int slot = atomicAdd(fail_count, 1);
                 fail_rows[slot] = (int32_t)i;
-                // The kneed-th best exact cosine among the candidates bounds the true kneed-th best from below:
-                // the exact scan only has to look at columns that reach it (exact_prefilter_kernel).
-                if (fail_thr) fail_thr[slot] = sorted_nca >= A.rp.kneed ? sm.buf[A.rp.kneed - 1].k : 0ull;
-            } else atomicExch(A.error_flag, 1);  // same-page mode: page larger than A.sp_cap
+                if (fail_thr) fail_thr[slot] = thr;  // the exact scan only looks at columns that reach it (exact_prefilter_kernel)
+            } else atomicExch(A.error_flag, 1);  // page larger than A.sp_cap (or, fully sharded, lists beyond capacity)
         }
         __syncthreads();
     }
@@ -579,9 +713,10 @@ exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int
         const int cnt = s_cnt;
         sort_keys(sm.buf, cnt);
         const int n_ca = cnt < kneed ? cnt : kneed;
-        for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[e] = sm.buf[e].j;
+        for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[c + e] = sm.buf[e].j;
         __syncthreads();
-        finish_row(A, sm, i, n_ca, false, 0.f, 0.f);
+        score_same_page(A, sm, i, c);
+        finish_row(A, sm, i, n_ca, -CUDART_INF, 0.0, nullptr, 0);
         __syncthreads();
     }
 }

@@ -119,10 +119,10 @@ class ShardedScorer:
 
     # -- one step --------------------------------------------------------------------------------------
     def run(self, *, schemas, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), kprime=0, host_outputs=False,
-            candidates="all", path="auto"):
+            candidates="all", path="auto", eps_scale=0.0):
         eng = self.eng
         kw = dict(candidates=candidates, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight,
-                  kprime=kprime, path=path)
+                  kprime=kprime, path=path, eps_scale=eps_scale)
         out_kw = dict(want=("topk", "pairs", "sums"), device_outputs=not host_outputs, pinned_outputs=host_outputs)
         if self.world == 1:
             r = eng.run(schemas, **out_kw, **kw)

@@ -150,7 +150,7 @@ class AlignmentEngine:
     # -- scoring ----------------------------------------------------------------
     @staticmethod
     def _params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime, n_ranks=0,
-                shard=None, slab=None):
+                shard=None, slab=None, eps_scale=0.0):
         mask = schema_mask(schemas)
         ks = [int(k) for k in k_values]
         prm = _native.Params()
@@ -165,6 +165,7 @@ class AlignmentEngine:
         prm.path = PATHS[path] if isinstance(path, str) else int(path)
         prm.kprime = int(kprime)
         prm.n_ranks = int(n_ranks)
+        prm.eps_scale = float(eps_scale)
         if shard is not None:  # (first chunk row, rows) the fused pass contracts against
             prm.shard_col0, prm.shard_cols = int(shard[0]), int(shard[1])
         if slab is not None:   # (first image row, rows) that are ranked
@@ -174,12 +175,12 @@ class AlignmentEngine:
     def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
             mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
             path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
-            pinned_outputs=False, deep=False, stream=None, slab=None, imported=None):
+            pinned_outputs=False, deep=False, stream=None, slab=None, imported=None, eps_scale=0.0):
         """slab=(row0, rows): rank only those image rows (outputs are sized by the slab).
         imported=(keys, count, tau): candidate lists received from the ranks' fused passes
         (mmalign_rescore_slab) instead of running the fused kernel here."""
         prm, mask, S, ks = self._params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime,
-                                        slab=slab)
+                                        slab=slab, eps_scale=eps_scale)
         kmax = max(ks) if ks else 0
         kneed = max(kmax, int(mrr_cutoff))
         if slab is None or tuple(slab) == (0, 0):

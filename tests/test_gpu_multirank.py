@@ -81,14 +81,15 @@ def _run_ranks(world, rank_main):
 
 
 @pytest.mark.parametrize("N,M,D,world,kprime", [(300, 2003, 128, 2, 0), (201, 5000, 512, 4, 0), (130, 4000, 64, 8, 0),
-                                                (700, 3000, 64, 3, 0), (5, 3, 64, 4, 0), (400, 6000, 64, 2, 101)])
+                                                (700, 3000, 64, 3, 0), (5, 3, 64, 4, 0), (400, 6000, 64, 2, -1)])
 def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic, N, M, D, world, kprime):
     """ShardedScorer: each rank ingests 1/G of both tables, contracts against its chunk columns, exchanges the
     candidate lists and owns the exact results of its query slab.  D=64 makes near-ties and rescans likely;
-    kprime=101 (barely above the needed depth 100) forces uncertified rows through the exact scan."""
+    kprime=-1 stands for eps_scale=100: an inflated error bound sends uncertified rows through the exact scan."""
     distributed = importlib.import_module(PKG_NAME + ".distributed")
     img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=43)
     ks, cutoff, lam = (1, 5, 10, 20), 100, (0.3, 0.2)
+    eps_scale, kprime = (100.0, 0) if kprime < 0 else (0.0, kprime)
     cut = lambda d, lo, hi: {k: (v[lo:hi] if v is not None else None) for k, v in d.items()}
 
     def rank_main(rank, dist):
@@ -96,7 +97,8 @@ def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic
         sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=dist)
         sc.load(cut(img, *distributed.slab_range(N, world, rank)), cut(chk, *distributed.shard_range(M, world, rank)),
                 N=N, M=M, n_terms=512)
-        r = sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True, kprime=kprime)
+        r = sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True, kprime=kprime,
+                   eps_scale=eps_scale)
         r = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in r.items()}
         eng.close()
         return r
@@ -118,7 +120,7 @@ def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic
                 assert r["hits"][si, q] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
         assert r["sim_sum"] == pytest.approx(float(o["pair_sim"].sum()), rel=1e-12)
         rescanned += r["stats"]["rows_rescanned"]
-    if kprime:
+    if eps_scale:
         assert rescanned > 0
 
 

@@ -28,10 +28,10 @@ def load(eng, img, chk, T=0):
 
 
 def check_against_oracle(oracle, eng, img, chk, T, *, schemas=ALL4, candidates, lam=(0.0, 0.0), ks=(1, 5, 10, 20),
-                         cutoff=100, path="auto", kprime=0):
+                         cutoff=100, path="auto", kprime=0, eps_scale=0.0):
     load(eng, img, chk, T)
     r = eng.run(schemas, candidates=candidates, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, path=path,
-                kprime=kprime)
+                kprime=kprime, eps_scale=eps_scale)
     mask = sum({"vanilla_clip": 1, "clip_lexical": 2, "clip_positional": 4, "clip_combined": 8}[s] for s in schemas)
     o = oracle.evaluate(img, chk, T=T, schema_mask=mask, candidates=candidates, lam=(lam[0], lam[1], lam[0] + lam[1]),
                         kmax=max(ks), cutoff=max(max(ks), cutoff))
@@ -170,15 +170,16 @@ def test_fused_path_with_ties_and_forced_rescan(oracle, eng, synthetic):
     assert r["stats"]["rows_rescanned"] > 0
 
 
-@pytest.mark.parametrize("N,M,D,cutoff", [(300, 20000, 128, 100), (2500, 3000, 64, 20), (64, 900, 64, 100)])
-def test_two_stage_exact_scan(oracle, eng, synthetic, N, M, D, cutoff):
-    """K' = the needed depth: (almost) no row can be certified, so every one goes through the exact scan --
-    stage 1 (whole-GPU prefilter against the failed attempt's threshold) for the first 2048 failed rows, the
-    streaming scan for the rest and for rows without a threshold."""
+@pytest.mark.parametrize("N,M,D,cutoff,eps_scale", [(300, 20000, 128, 100, 16.0), (2500, 3000, 64, 20, 16.0),
+                                                      (64, 900, 64, 100, 100.0), (200, 30000, 256, 100, 100.0)])
+def test_two_stage_exact_scan(oracle, eng, synthetic, N, M, D, cutoff, eps_scale):
+    """An inflated error bound (eps_scale) leaves (almost) no row certified, so every one goes through the exact
+    scan: stage 1 (whole-GPU prefilter against the row's threshold) for the first 2048 failed rows, the streaming
+    scan for the rest and for rows whose survivors overflow stage 1 (eps_scale=100: the threshold excludes nothing)."""
     img, chk, _ = synthetic.make_numpy(N, M, D, T=64, seed=13)
     r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 5, 10, 20), cutoff=cutoff,
-                             kprime=cutoff)
-    assert r["stats"]["rows_rescanned"] > N // 2
+                             eps_scale=eps_scale)
+    assert r["stats"]["rows_rescanned"] > (N // 2 if eps_scale >= 100 else 0)
 
 
 @pytest.mark.parametrize("path,cand", [("auto", "all"), ("exact", "all"), ("auto", "same_page")])
