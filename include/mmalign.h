@@ -213,6 +213,22 @@ int mmalign_reduce_metrics(mmalign_ctx *ctx, const int32_t *pair_rank, const dou
                            int32_t mrr_cutoff, int64_t *hits, double *rr_sum, double *sim_sum,
                            void *stream);
 
+/* Ingest: the chunks' lexical term sets, built on the GPU.  Replaces the substring scans of
+ * compute_lexical_alignment, src/insert_clip_embeddings.py:149-150
+ *     chunk_text_lower = text_chunk["text"].lower();  term in chunk_text_lower
+ * for the whole table at once.
+ *   text      the chunks' texts, ALREADY LOWER-CASED (str.lower() is Unicode-aware and stays with the caller),
+ *             UTF-8, concatenated; host or device pointer
+ *   text_off  [m + 1] byte offsets into text (text_off[0] = 0); host or device pointer
+ *   terms     the lexical components (src/insert_clip_embeddings.py:237-239), UTF-8, concatenated; HOST pointer
+ *   term_off  [n_terms + 1] byte offsets into terms; HOST pointer.  n_terms <= 4096
+ *   bits      [m][term_words] out: bit t of row j = term t is a substring of chunk j's text (an empty term is a
+ *             substring of every text, as in Python); term_words >= ceil(n_terms / 64); host or device pointer
+ * The result is what mmalign_set_chunks takes as `terms`. */
+int mmalign_term_bitsets(mmalign_ctx *ctx, const uint8_t *text, const int64_t *text_off, int64_t m,
+                         const uint8_t *terms, const int64_t *term_off, int32_t n_terms,
+                         int32_t term_words, uint64_t *bits, void *stream);
+
 /* validation hook: the raw bf16 x bf16 -> fp32 score tile matrix of the fused
  * kernel, out [N][m_local] fp32 (small sizes only). */
 int mmalign_debug_scores(mmalign_ctx *ctx, float *out, void *stream);

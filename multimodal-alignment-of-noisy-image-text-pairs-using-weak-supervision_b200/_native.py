@@ -11,7 +11,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libmmalign.so"
-SOURCES = ["api.cu", "prep.cu", "rescore.cu", "fused_tc.cu", "common.cuh"]
+SOURCES = ["api.cu", "prep.cu", "rescore.cu", "fused_tc.cu", "ingest.cu", "common.cuh"]
 
 NULL_KEY = 0xFFFFFFFFFFFFFFFF
 SCHEMA_BITS = {"vanilla_clip": 1, "clip_lexical": 2, "clip_positional": 4, "clip_combined": 8}
@@ -40,7 +40,7 @@ EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_
            "mmalign_run", "mmalign_alignments", "mmalign_merge_topk", "mmalign_count_beating",
            "mmalign_reduce_metrics", "mmalign_debug_scores", "mmalign_fused_pass", "mmalign_chunk_err_max",
            "mmalign_rescore_pass", "mmalign_rescan_rows", "mmalign_list_stride", "mmalign_export_lists",
-           "mmalign_rescore_slab", "mmalign_num_pairs_range"]
+           "mmalign_rescore_slab", "mmalign_num_pairs_range", "mmalign_term_bitsets"]
 ABI_VERSION = 2
 
 _lib = None
@@ -95,6 +95,7 @@ def load():
     L.mmalign_export_lists.argtypes = [vp, i32, i64, i32, vp, vp, vp, vp]
     L.mmalign_rescore_slab.argtypes = [vp, C.POINTER(Params), vp, vp, vp, i32, i64, i32, C.POINTER(Out), vp]
     L.mmalign_num_pairs_range.argtypes = [vp, i64, i64, C.POINTER(i64)]
+    L.mmalign_term_bitsets.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):

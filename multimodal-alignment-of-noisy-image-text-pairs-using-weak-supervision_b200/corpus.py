@@ -39,18 +39,23 @@ def bbox_array(records: Sequence[dict]) -> np.ndarray:
     return out
 
 
-def term_bitsets(chunks: Sequence[dict], terms: Sequence[str]) -> np.ndarray:
+_ENGINE = None
+
+
+def _engine():
+    global _ENGINE
+    if _ENGINE is None:
+        from .engine import AlignmentEngine
+        _ENGINE = AlignmentEngine(0)
+    return _ENGINE
+
+
+def term_bitsets(chunks: Sequence[dict], terms: Sequence[str], engine=None) -> np.ndarray:
     """bit t of row j = terms[t] occurs as a substring of chunk j's lower-cased text
-    (src/insert_clip_embeddings.py:149-150)."""
-    T = len(terms)
-    W = max(1, (T + 63) // 64)
-    out = np.zeros((len(chunks), W), np.uint64)
-    for j, c in enumerate(chunks):
-        text = c["text"].lower()
-        for t, term in enumerate(terms):
-            if term in text:
-                out[j, t >> 6] |= np.uint64(1) << np.uint64(t & 63)
-    return out
+    (src/insert_clip_embeddings.py:149-150).  str.lower() (Unicode-aware) runs here; the matching of every
+    (chunk, term) pair runs on the GPU (csrc/ingest.cu) -- there is no host fallback."""
+    eng = engine if engine is not None else _engine()
+    return eng.term_bitsets([c["text"].lower() for c in chunks], list(terms))
 
 
 @dataclass
@@ -71,7 +76,7 @@ class Corpus:
 
 
 def build_corpus(images: Sequence[dict], chunks: Sequence[dict], image_emb, chunk_emb,
-                 lexical_components: Optional[dict | Sequence[str]] = None) -> Corpus:
+                 lexical_components: Optional[dict | Sequence[str]] = None, engine=None) -> Corpus:
     if isinstance(lexical_components, dict):  # insert_clip_embeddings.py:237-239
         terms = [c["term"] for c in lexical_components.get("components", [])]
     else:
@@ -80,7 +85,7 @@ def build_corpus(images: Sequence[dict], chunks: Sequence[dict], image_emb, chun
     img = dict(emb=np.ascontiguousarray(image_emb, np.float32), key=page_keys(images, page_ids),
                bbox=bbox_array(images), terms=None)
     chk = dict(emb=np.ascontiguousarray(chunk_emb, np.float32), key=page_keys(chunks, page_ids),
-               bbox=bbox_array(chunks), terms=term_bitsets(chunks, terms))
+               bbox=bbox_array(chunks), terms=term_bitsets(chunks, terms, engine))
     c = Corpus(image_ids=[r["image_id"] for r in images], chunk_ids=[r["chunk_id"] for r in chunks],
                image_manual=[r.get("manual_id") for r in images], image_page=[r.get("page") for r in images],
                img=img, chk=chk, terms=terms)

@@ -75,6 +75,7 @@ struct mmalign_ctx {
     DevBuf list_keys, list_tau, list_count;
     DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;  // small: fail_count, cand_counter, error_flag, k_list, stats
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
+    DevBuf term_table, text_off, text_bytes;  // mmalign_term_bitsets: term table, uploads of host texts
     CandLists lists;               // written by the last fused pass
     bool lists_valid = false;
     int64_t lists_col0 = 0;        // first chunk row of the column range the lists were built on
@@ -150,7 +151,8 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     c->img.release();
     c->chk.release();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
-                      &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage};
+                      &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
+                      &c->term_table, &c->text_off, &c->text_bytes};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     delete c;
@@ -837,6 +839,73 @@ extern "C" int mmalign_reduce_metrics(mmalign_ctx *c, const int32_t *pair_rank, 
     CU(c, c->metrics_scratch.reserve(metrics_scratch_bytes(S, n_k)));
     CU(c, launch_reduce_metrics(pair_rank, pair_sim, S, P, k_list_dev, n_k, mrr_cutoff, d_hits, d_rr, d_sim,
                                 c->metrics_scratch.p, st));
+    if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+namespace mma {
+struct TermTableHost {
+    std::vector<int32_t> off, bucket_start, bucket_term;
+    std::vector<uint32_t> always;
+};
+int build_term_table(const uint8_t *terms, const int64_t *term_off, int n_terms, int term_words, TermTableHost *out);
+}
+
+extern "C" int mmalign_term_bitsets(mmalign_ctx *c, const uint8_t *text, const int64_t *text_off, int64_t m,
+                                    const uint8_t *terms, const int64_t *term_off, int32_t n_terms, int32_t term_words,
+                                    uint64_t *bits, void *stream)
+{
+    if (!c || !text_off || !bits || m < 0 || (n_terms > 0 && (!terms || !term_off)))
+        return fail(c, MMALIGN_EINVAL, "mmalign_term_bitsets: NULL argument");
+    if (n_terms < 0 || n_terms > 4096) return fail(c, MMALIGN_ELIMIT, "mmalign_term_bitsets: n_terms=%d must be in 0..4096", n_terms);
+    if (term_words < 1 || (int64_t)term_words * 64 < n_terms || term_words > 64)
+        return fail(c, MMALIGN_EINVAL, "mmalign_term_bitsets: term_words=%d does not hold %d terms (1..64 words)", term_words, n_terms);
+    if (is_device_ptr(terms) || is_device_ptr(term_off)) return fail(c, MMALIGN_EINVAL, "mmalign_term_bitsets: terms and term_off are host arrays");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    if (m == 0) return MMALIGN_OK;
+    // the term table: tiny, prepared on the host
+    TermTableHost h;
+    static const int64_t zero_off[1] = {0};
+    const int trc = build_term_table(terms, n_terms > 0 ? term_off : zero_off, n_terms, term_words, &h);
+    if (trc) return fail(c, MMALIGN_EINVAL, "mmalign_term_bitsets: bad term offsets (code %d)", trc);
+    const size_t tb = n_terms > 0 ? (size_t)term_off[n_terms] : 0;
+    const size_t o_off = (tb + 15) & ~(size_t)15, o_bs = o_off + h.off.size() * 4, o_bt = o_bs + h.bucket_start.size() * 4,
+                 o_al = o_bt + h.bucket_term.size() * 4, total = o_al + h.always.size() * 4;
+    CU(c, c->term_table.reserve(total));
+    char *d = (char *)c->term_table.p;
+    if (tb) CU(c, cudaMemcpyAsync(d, terms, tb, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d + o_off, h.off.data(), h.off.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d + o_bs, h.bucket_start.data(), h.bucket_start.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d + o_bt, h.bucket_term.data(), h.bucket_term.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d + o_al, h.always.data(), h.always.size() * 4, cudaMemcpyHostToDevice, st));
+    // the texts
+    const int64_t *d_off = text_off;
+    int64_t total_text = 0;
+    if (is_device_ptr(text_off)) {
+        CU(c, cudaMemcpyAsync(&total_text, text_off + m, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CU(c, cudaStreamSynchronize(st));
+    } else {
+        total_text = text_off[m];
+        CU(c, c->text_off.reserve(sizeof(int64_t) * (m + 1)));
+        CU(c, cudaMemcpyAsync(c->text_off.p, text_off, sizeof(int64_t) * (m + 1), cudaMemcpyHostToDevice, st));
+        d_off = (const int64_t *)c->text_off.p;
+    }
+    if (total_text < 0 || (total_text > 0 && !text)) return fail(c, MMALIGN_EINVAL, "mmalign_term_bitsets: bad text offsets");
+    const uint8_t *d_text = text;
+    if (total_text > 0 && !is_device_ptr(text)) {
+        CU(c, c->text_bytes.reserve((size_t)total_text));
+        CU(c, cudaMemcpyAsync(c->text_bytes.p, text, (size_t)total_text, cudaMemcpyHostToDevice, st));
+        d_text = (const uint8_t *)c->text_bytes.p;
+    }
+    Stager sg{c, st};
+    uint64_t *d_bits = nullptr;
+    sg.map(bits, (size_t)m * term_words, &d_bits);
+    int rc;
+    if ((rc = sg.commit())) return rc;
+    CU(c, launch_term_bitsets(d_text, d_off, m, (const uint8_t *)d, (const int32_t *)(d + o_off), (const int32_t *)(d + o_bs),
+                              (const int32_t *)(d + o_bt), (const uint32_t *)(d + o_al), term_words, d_bits, st));
     if ((rc = sg.copy_back())) return rc;
     CU(c, cudaStreamSynchronize(st));
     return MMALIGN_OK;

@@ -290,6 +290,11 @@ cudaError_t launch_merge_topk(const int64_t *in_idx, const double *in_score, int
 cudaError_t launch_count_beating(const int64_t *deep_idx, const double *deep_score, int64_t N, int S, int K,
                                  int64_t n_q, const int64_t *q_image, const int64_t *q_chunk,
                                  const double *q_score, int32_t *counts, cudaStream_t st);
+// ingest.cu
+struct TermTableHost;
+cudaError_t launch_term_bitsets(const uint8_t *text, const int64_t *text_off, int64_t m, const uint8_t *term_bytes,
+                                const int32_t *term_off, const int32_t *bucket_start, const int32_t *bucket_term,
+                                const uint32_t *always, int term_words, uint64_t *bits, cudaStream_t st);
 // fused_tc.cu
 struct FusedPlan {
     int64_t n_row_blocks;

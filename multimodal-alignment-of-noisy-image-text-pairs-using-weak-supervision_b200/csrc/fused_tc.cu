@@ -492,6 +492,7 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     else return -2;
     p.n_lists = p.n_row_blocks * p.n_splits * 256;
     p.a_resident = D <= 512;
+    if (const char *e = getenv("MMALIGN_A_RESIDENT")) p.a_resident = p.a_resident && atoi(e) != 0;  // tuning experiments
     const size_t a_bytes = p.a_resident ? (size_t)(D / BK) * kABlockBytes : 0;
     const size_t stage_bytes = kBStageBytes + (p.a_resident ? 0 : kABlockBytes);
     const size_t fixed = 1024 /*alignment slack*/ + a_bytes + 256 /*barriers*/;

@@ -259,6 +259,23 @@ class AlignmentEngine:
                                                rec.ctypes.data, None))
         return rec[:P]
 
+    def term_bitsets(self, texts_lower: Sequence[str], terms: Sequence[str], term_words: Optional[int] = None):
+        """The chunks' lexical term sets (mmalign_term_bitsets): bits [m, W] uint64, bit t of row j =
+        terms[t] is a substring of texts_lower[j] (src/insert_clip_embeddings.py:149-150; the caller lower-cases)."""
+        def pack(strings):
+            enc = [s.encode("utf-8") for s in strings]
+            off = np.zeros(len(enc) + 1, np.int64)
+            if enc:
+                np.cumsum([len(b) for b in enc], out=off[1:])
+            return np.frombuffer(b"".join(enc) or b"\0", np.uint8), off
+        tb, to = pack(texts_lower)
+        pb, po = pack(terms)
+        W = int(term_words or max(1, (len(terms) + 63) // 64))
+        bits = np.zeros((len(texts_lower), W), np.uint64)
+        self._check(self._L.mmalign_term_bitsets(self._ctx, tb.ctypes.data, to.ctypes.data, len(texts_lower),
+                                                 pb.ctypes.data, po.ctypes.data, len(terms), W, bits.ctypes.data, None))
+        return bits
+
     def debug_scores(self):
         out = np.zeros((self.N, self.M), np.float32)
         self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))

@@ -29,7 +29,7 @@ def _records(eng, images, chunks, img_key, chk_key, terms, schema, raw=False):
     f = np.zeros((len(chunks), 4), np.float32)
     f[:, 0] = 1.0
     eng.set_images(e, img_key, bbox_array(images), None)
-    eng.set_chunks(f, chk_key, bbox_array(chunks), term_bitsets(chunks, terms), n_terms=len(terms))
+    eng.set_chunks(f, chk_key, bbox_array(chunks), term_bitsets(chunks, terms, eng), n_terms=len(terms))
     return eng.alignments(schema, raw=raw)
 
 

@@ -374,3 +374,30 @@ int orc_alignments(const double *img_bbox, const uint64_t *img_terms, int64_t N,
         }
     return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* Lexical term sets: src/insert_clip_embeddings.py:149-150                  */
+/*     chunk_text_lower = text_chunk["text"].lower()                         */
+/*     ... for term in lexical_components if term in chunk_text_lower        */
+/* ------------------------------------------------------------------------ */
+/* text: the chunks' lower-cased UTF-8 texts, concatenated (text_off [m+1]); terms likewise (term_off [T+1]).
+ * bits [m][term_words]: bit t of row j = term t is a substring of text j (Python's `in`: an empty term occurs in
+ * every text; on valid UTF-8 a byte match is a code-point match).  Plain nested loops on purpose. */
+int orc_term_bitsets(const uint8_t *text, const int64_t *text_off, int64_t m, const uint8_t *terms,
+                     const int64_t *term_off, int T, int term_words, uint64_t *bits)
+{
+    if (term_words * 64 < T) return -1;
+    memset(bits, 0, (size_t)m * term_words * sizeof(uint64_t));
+    for (int64_t j = 0; j < m; ++j) {
+        const uint8_t *s = text + text_off[j];
+        const int64_t len = text_off[j + 1] - text_off[j];
+        for (int t = 0; t < T; ++t) {
+            const uint8_t *pat = terms + term_off[t];
+            const int64_t tl = term_off[t + 1] - term_off[t];
+            int found = tl == 0;
+            for (int64_t p = 0; !found && p + tl <= len; ++p) found = memcmp(s + p, pat, (size_t)tl) == 0;
+            if (found) bits[j * term_words + (t >> 6)] |= 1ull << (t & 63);
+        }
+    }
+    return 0;
+}

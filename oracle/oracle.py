@@ -60,6 +60,8 @@ def lib():
         L.orc_alignments.restype = C.c_int
         L.orc_alignments.argtypes = [dp, u64p, C.c_int64, dp, u64p, C.c_int, C.c_int64, C.c_int,
                                      i64p, i64p, dp]
+        L.orc_term_bitsets.restype = C.c_int
+        L.orc_term_bitsets.argtypes = [C.c_void_p, i64p, C.c_int64, C.c_void_p, i64p, C.c_int, C.c_int, u64p]
         _LIB = L
     return _LIB
 
@@ -169,6 +171,26 @@ def alignments(img, chk, *, T, schema: int):
                          _p(ct, C.c_uint64), W, int(T), schema, _p(off, C.c_int64),
                          _p(pcb, C.c_int64), _p(rec, C.c_double))
     return off, pc, rec[:P]
+
+
+def pack_strings(strings):
+    """UTF-8 bytes of `strings`, concatenated, with the [n+1] int64 offsets."""
+    enc = [s.encode("utf-8") if isinstance(s, str) else bytes(s) for s in strings]
+    off = np.zeros(len(enc) + 1, np.int64)
+    np.cumsum([len(b) for b in enc], out=off[1:])
+    return np.frombuffer(b"".join(enc) or b"\0", np.uint8).copy(), off
+
+
+def term_bitsets(texts, terms, term_words=None):
+    """bits [m, W] u64: bit t of row j = terms[t] in texts[j].lower()  (insert_clip_embeddings.py:149-150)."""
+    tb, to = pack_strings([t.lower() for t in texts])
+    pb, po = pack_strings(terms)
+    W = term_words or max(1, (len(terms) + 63) // 64)
+    bits = np.zeros((len(texts), W), np.uint64)
+    rc = lib().orc_term_bitsets(tb.ctypes.data, _p(to, C.c_int64), len(texts), pb.ctypes.data, _p(po, C.c_int64),
+                                len(terms), W, _p(bits, C.c_uint64))
+    assert rc == 0
+    return bits
 
 
 def metrics_from_ranks(pair_rank, pair_sim, k_values=(1, 5, 10), mrr_cutoff=100):

@@ -35,13 +35,40 @@ def oracle():
     return o
 
 
+class OracleIngest:
+    """Stand-in for the engine's ingest call in the CPU-only tests: the term sets come from the oracle.
+    (tests/test_gpu_parity.py::test_term_bitsets_* hold the GPU ingest to the same answers.)"""
+
+    def term_bitsets(self, texts_lower, terms, term_words=None):
+        from oracle import oracle as o
+        return o.term_bitsets(texts_lower, terms, term_words)
+
+
 @pytest.fixture(scope="session")
 def small_corpus(pkg):
     d = json.loads((GOLDEN / "small_corpus.json").read_text())
     z = np.load(GOLDEN / "small_corpus.npz")
-    corpus = pkg.build_corpus(d["images"], d["chunks"], z["img_emb"], z["chk_emb"], d["lexical_components"])
+    corpus = pkg.build_corpus(d["images"], d["chunks"], z["img_emb"], z["chk_emb"], d["lexical_components"],
+                              engine=OracleIngest())
     return d, corpus
 
 
 def unhex(x):
     return float.fromhex(x)
+
+
+def random_texts_and_terms(rng, m, T):
+    """Texts and terms over a small alphabet (so that matches are common) with multi-byte UTF-8, upper case,
+    empty strings, duplicates, terms longer than texts and terms that end exactly at the end of a text."""
+    alphabet = list("abcAB \n") + ["é", "ß", "Ж", "中", "😀"]
+    def word(lo, hi):
+        return "".join(rng.choice(alphabet, size=int(rng.integers(lo, hi + 1))))
+    texts = [word(0, 80) for _ in range(m)]
+    terms = [word(0, 4).lower() for _ in range(T)]
+    terms[0] = ""                                  # occurs everywhere
+    terms[1] = terms[2] = "ab"                     # duplicates count twice
+    terms[3] = "Ab"                                # never matches lower-cased text
+    terms[4] = texts[1][-3:].lower() if len(texts[1]) >= 3 else "zz"   # suffix of a text
+    terms[5] = "a" * 200                           # longer than every text
+    texts[0] = ""
+    return texts, terms

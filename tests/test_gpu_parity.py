@@ -8,7 +8,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, unhex
+from conftest import GOLDEN, random_texts_and_terms, unhex
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread")]
 
@@ -100,6 +100,44 @@ def test_small_corpus_alignment_records(pkg, small_corpus):
         got = ins.compute_alignment_records(corpus, ul, up)
         assert [(g[0], g[1], g[3]) for g in got] == [(w[0], w[1], w[3]) for w in want]
         assert all(g[2] == w[2] or abs(g[2] - w[2]) <= 2.3e-16 for g, w in zip(got, want))
+
+
+# ----------------------------------------------------------------------------- ingest: lexical term sets
+def test_term_bitsets_golden_and_random(oracle, eng):
+    """mmalign_term_bitsets against the reference's compute_lexical_alignment answers (golden), the oracle and
+    Python's `in` (src/insert_clip_embeddings.py:149-150), on strings with multi-byte UTF-8, empty terms and texts,
+    duplicate terms, terms longer than the text and matches that end at the last byte."""
+    cases = json.loads((GOLDEN / "weak_vectors.json").read_text())["lexical_text"]
+    for c in cases:
+        bits = eng.term_bitsets([c["text"].lower()], c["terms"])
+        assert np.array_equal(bits, oracle.term_bitsets([c["text"]], c["terms"]))
+        hits = int(np.unpackbits(bits.view(np.uint8)).sum())
+        assert oracle.lexical(hits, len(c["terms"])) == unhex(c["expect"]), c
+    for seed, m, T, W in [(1, 300, 150, None), (2, 1000, 64, None), (3, 50, 1, 4), (4, 2000, 700, None), (5, 7, 0, None)]:
+        texts, terms = random_texts_and_terms(np.random.default_rng(seed), m, max(T, 6))
+        terms = terms[:T]
+        bits = eng.term_bitsets([t.lower() for t in texts], terms, W)
+        assert np.array_equal(bits, oracle.term_bitsets(texts, terms, W)), (seed, m, T)
+        for j in range(0, m, 37):
+            low = texts[j].lower()
+            for t, term in enumerate(terms):
+                assert bool((int(bits[j, t >> 6]) >> (t & 63)) & 1) == (term in low), (j, t)
+    assert eng.term_bitsets([], ["a"]).shape == (0, 1)
+
+
+def test_term_bitsets_table_scale(oracle, eng, pkg, small_corpus):
+    """A 20k-chunk table of word-like text with 512 terms (device-side matching equals the oracle), and the
+    golden corpus ingested through build_corpus on the GPU."""
+    rng = np.random.default_rng(8)
+    vocab = ["".join(rng.choice(list("abcdefghijklmnopqrstuvwxyz"), size=int(rng.integers(2, 10)))) for _ in range(3000)]
+    texts = [" ".join(rng.choice(vocab, size=int(rng.integers(5, 120)))) for _ in range(20000)]
+    terms = list(rng.choice(vocab, size=500)) + ["valve seat", "o-ring", " ", "e", "zzzzzz", "a b", "the", "ing", "qu", "x", "tion", "er "]
+    bits = eng.term_bitsets(texts, terms)
+    assert np.array_equal(bits, oracle.term_bitsets(texts, terms))
+    d, c = small_corpus
+    z = np.load(GOLDEN / "small_corpus.npz")
+    g = pkg.build_corpus(d["images"], d["chunks"], z["img_emb"], z["chk_emb"], d["lexical_components"], engine=eng)
+    assert np.array_equal(g.chk["terms"], c.chk["terms"]) and g.n_terms == c.n_terms
 
 
 def test_weak_functions_known_answers(pkg):

@@ -6,7 +6,7 @@ import json
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, unhex
+from conftest import random_texts_and_terms, GOLDEN, unhex
 
 
 def test_positional_known_answers(oracle):
@@ -38,13 +38,21 @@ def test_lexical_known_answers(oracle):
     assert oracle.lexical(1, 200) == 0.05  # Appendix A L11: not > 0.05
 
 
-def test_lexical_substring_semantics(pkg):
+def test_lexical_substring_semantics(oracle):
+    """The oracle's term sets against the reference's own compute_lexical_alignment answers (golden), and against
+    Python's `in` on random unicode strings (what src/insert_clip_embeddings.py:150 evaluates)."""
     cases = json.loads((GOLDEN / "weak_vectors.json").read_text())["lexical_text"]
-    from oracle import oracle
     for c in cases:
-        bits = pkg.corpus.term_bitsets([{"text": c["text"]}], c["terms"])
+        bits = oracle.term_bitsets([c["text"]], c["terms"])
         hits = int(np.unpackbits(bits.view(np.uint8)).sum())
         assert oracle.lexical(hits, len(c["terms"])) == unhex(c["expect"]), c
+    texts, terms = random_texts_and_terms(np.random.default_rng(5), 60, 150)
+    bits = oracle.term_bitsets(texts, terms)
+    for j, text in enumerate(texts):
+        low = text.lower()
+        for t, term in enumerate(terms):
+            assert bool((int(bits[j, t >> 6]) >> (t & 63)) & 1) == (term in low), (j, t)
+    assert bits.shape == (60, 3) and not (bits[:, 2] >> np.uint64(150 - 128)).any()  # no bits beyond T
 
 
 def test_cosine_orders_agree(oracle):
