@@ -297,7 +297,11 @@ def run_ours(args):
     def dev_step():
         r = step(img, chk, False)
         fused_us.append(r["stats"]["fused_us"]); resc_us.append(r["stats"]["rescore_us"])
-        scan_us.append(r["stats"]["exact_scan_us"]); launches.append(r["stats"]["kernel_launches"] + 6)
+        scan_us.append(r["stats"]["exact_scan_us"])
+        # kernels of the library per step (profiles/r1c_launches_summary.txt): K0 + error max of both tables (4), pair index
+        # (iota, 10 CUB radix-sort/scan launches, page ranges, offsets scan: 14), then what mmalign_run counts itself
+        # (fused, rescore, prefilter, scan, 2 metric kernels), + the list export when sharded
+        launches.append(18 + r["stats"]["kernel_launches"] - 2 + (1 if world > 1 else 0))
         return r
     t_begin = time.time()
     ms, res = timed(dev_step, args.steps)
@@ -331,8 +335,16 @@ def run_ours(args):
     t_fused = float(np.mean(fused_us)) * 1e-6
     flops_launch = 2.0 * N * (r1 - r0) * D  # algorithmic: 2*M_local*D per query x N queries per launch
     achieved = flops_launch / t_fused / 1e12 if t_fused > 0 else 0.0
+    traffic = None  # DRAM bytes of one launch, from the committed ncu --set full capture of this very configuration
+    tf = ROOT / "profiles" / "r1c_traffic.json"
+    if tf.exists():
+        t = json.loads(tf.read_text())["fused_score_topk_kernel"]
+        if (t["N"], t["M"], t["D"]) == (N, r1 - r0, D):
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
     roof = {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": P["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": achieved / P["bf16_sustained"], "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved / P["bf16_sustained"], "traffic": traffic,
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1c_fused_score_topk_kernel.txt); "
+                            "the kernel is tensor-bound: 2*N*M*D flop against (N+M)*D*2 algorithmic operand bytes",
             "peak_source": f"{P['src']} bf16_tflops_sustained (kernel runs ~{t_fused * 1e3:.0f} ms inside the step)",
             "frac_of_burst_peak": achieved / P["bf16"], "ms_per_launch": t_fused * 1e3,
             "share_of_step": t_fused / (ms_per_step / 1000.0),
