@@ -146,6 +146,7 @@ struct FusedArgs {
 // Thread (row, half) owns list `ubase + off0`; `n` entries are live.
 // ---------------------------------------------------------------------------
 constexpr int kSlack = kListSlack;  // a compaction may keep up to K' + kSlack entries (saves bisection steps)
+constexpr int kCompactMargin = 72;  // routine compaction when fewer than this many slots are free (one tile adds <= 128 - ...)
 
 // Warp-cooperative compaction of the lists of the lanes that ask for it: keeps the best ~K'
 // entries and raises the lane's threshold tau to the smallest kept score.
@@ -419,8 +420,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     // global-memory latency is off the MMA critical path (the check inside process_chunk only fires
                     // when a single tile overflows the remaining room, i.e. in the first tiles of a sweep).
                     __syncwarp();
-                    if (__any_sync(0xFFFFFFFFu, n > CAP - 72))
-                        compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > CAP - 72);
+                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
+                        compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > CAP - kCompactMargin);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
@@ -473,6 +474,7 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     if (p.kprime < kneed) p.kprime = kneed;
     // A row has 2 * n_splits lists over disjoint columns on each of the n_ranks GPUs; the union of their best
     // k entries is complete to a depth of about n_lists * k, so each list keeps its share plus 15 % for imbalance.
+    if (const char *e = getenv("MMALIGN_PLAN_RANKS")) n_ranks = atoi(e);  // tuning experiments: size the lists as for a sharded run
     const int lists_per_row = 2 * p.n_splits * (n_ranks > 1 ? n_ranks : 1);
     // The union is complete above the LARGEST of the lists' thresholds.  A list's k-th best score sits at
     // global rank ~ L*k with relative spread 1/sqrt(k), and the largest of L of them about z_L = sqrt(2 ln L)
@@ -485,7 +487,13 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     }
     if (p.kprime_list > p.kprime) p.kprime_list = p.kprime;
     if (p.kprime_list < 16) p.kprime_list = 16;
-    const int need = p.kprime_list + p.kprime_list / 2 + 40;  // kept + refill room + one chunk + slack
+    // A list is compacted back to kprime_list (+ kSlack) entries when fewer than kCompactMargin slots are free after a
+    // tile; the room between those two marks is how many insertions one compaction buys.  Measured (K1 alone): 6 slots
+    // of room (the 4-GPU share in 128-entry lists) cost 6.5 % against 64; 300 slots in 512-entry lists gain nothing.
+    int room = 64;
+    if (const char *e = getenv("MMALIGN_CAP_ROOM")) room = atoi(e);  // tuning experiments
+    int need = p.kprime_list + kSlack + kCompactMargin + room;
+    if (need > 512) need = p.kprime_list + kSlack + kCompactMargin + 32;
     if (need <= 128) p.cap = 128;
     else if (need <= 256) p.cap = 256;
     else if (need <= 512) p.cap = 512;
