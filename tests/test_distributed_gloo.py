@@ -155,3 +155,128 @@ def test_shard_range(pkg):
         for G in (1, 2, 4, 8):
             r = [d.shard_range(M, G, k) for k in range(G)]
             assert r[0][0] == 0 and r[-1][1] == M and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# ShardedScorer (default exchange): ingest all-gather with ragged shards, candidate-list all-to-all, slab ownership
+# ------------------------------------------------------------------------------------------------------------------
+class OracleSlabEngine:
+    """Stand-in for the engine calls ShardedScorer makes.  The 'fused pass' keeps EVERY column of the rank's shard
+    (complete above -inf), so the exchange must deliver, for every row of a slab, every global column exactly once;
+    the stand-in for mmalign_rescore_slab checks that and answers from the oracle."""
+
+    def __init__(self, oracle, T):
+        self.o, self.T, self.device = oracle, T, 0
+
+    @staticmethod
+    def _np(x, dt):
+        return None if x is None else np.ascontiguousarray(x.numpy() if hasattr(x, "numpy") else x).view(dt) \
+            if dt == np.uint64 else (None if x is None else np.ascontiguousarray(x.numpy() if hasattr(x, "numpy") else x, dtype=dt))
+
+    def set_images(self, emb, key, bbox=None, terms=None):
+        self.img = dict(emb=self._np(emb, np.float32), key=self._np(key, np.uint64), bbox=self._np(bbox, np.float64), terms=None)
+        self.N = len(self.img["key"])
+
+    def set_chunks(self, emb, key, bbox=None, terms=None, n_terms=0, col_offset=0):
+        assert col_offset == 0  # every rank holds the whole table
+        self.chk = dict(emb=self._np(emb, np.float32), key=self._np(key, np.uint64), bbox=self._np(bbox, np.float64),
+                        terms=self._np(terms, np.uint64))
+        self.M = len(self.chk["key"])
+
+    def fused_pass(self, schemas, *, shard, **_):
+        self.shard = shard
+
+    def list_stride(self):
+        return max(1, self.shard[1])
+
+    def export_lists(self, n_dest, slab_rows, stride):
+        lo, n = self.shard
+        keys = torch.zeros((n_dest, slab_rows, stride), dtype=torch.int64)
+        keys[:, :, :n] = torch.arange(lo, lo + n)  # score bits 0 in the high half
+        count = torch.full((n_dest, slab_rows), n, dtype=torch.int32)
+        count.view(-1)[self.N:] = 0                                     # padding rows beyond N
+        tau = torch.full((n_dest, slab_rows), float("-inf"))
+        return keys, count, tau
+
+    def run(self, schemas, *, slab, imported, k_values, mrr_cutoff, weak_weight, **_):
+        keys, count, tau = imported
+        row0, rows = slab
+        for r in range(rows):  # every global column exactly once, from the rank that owns it
+            cols = torch.cat([keys[g, r, :int(count[g, r])] for g in range(keys.shape[0])]).numpy() & 0xFFFFFFFF
+            assert np.array_equal(np.sort(cols), np.arange(self.M)), (row0, r)
+        assert torch.isinf(tau[:, :rows]).all()
+        lam = (weak_weight[0], weak_weight[1], weak_weight[0] + weak_weight[1])
+        kmax, kneed = max(k_values), max(max(k_values), mrr_cutoff)
+        o = self.o.evaluate(self.img, self.chk, T=self.T, schema_mask=MASK, candidates="all", lam=lam, kmax=kmax, cutoff=kneed)
+        p0, p1 = o["pair_offsets"][row0], o["pair_offsets"][row0 + rows]
+        pr, ps = o["pair_rank"][:, p0:p1], o["pair_sim"][p0:p1]
+        hits = np.array([[np.count_nonzero((pr[s] >= 1) & (pr[s] <= k)) for k in k_values] for s in range(4)], np.int64)
+        rr = np.array([sum(1.0 / x for x in pr[s].tolist() if 1 <= x <= mrr_cutoff) for s in range(4)])
+        return dict(topk_idx=o["topk_idx"][:, row0:row0 + rows], topk_score=o["topk_score"][:, row0:row0 + rows],
+                    pair_rank=pr, pair_sim=ps, hits=hits, rr_sum=rr, sim_sum=float(ps.sum()), num_pairs=int(p1 - p0),
+                    stats=dict(rows_rescanned=0, candidates_rescored=0))
+
+
+def slab_worker(rank, world, port, q, N, M):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle
+    synthetic = importlib.import_module(PKG_NAME + ".synthetic")
+    distributed = importlib.import_module(PKG_NAME + ".distributed")
+    img, chk, _ = synthetic.make_numpy(N, M, 64, T=64, seed=33)
+    cut = lambda d, lo, hi: {k: (v[lo:hi] if v is not None else None) for k, v in d.items()}
+    sc = distributed.ShardedScorer(OracleSlabEngine(oracle, 64), world, rank, None, dist=dist)
+    sc.load(cut(img, *distributed.slab_range(N, world, rank)), cut(chk, *distributed.shard_range(M, world, rank)),
+            N=N, M=M, n_terms=64)
+    r = sc.run(schemas=None, k_values=KS, mrr_cutoff=CUTOFF, weak_weight=LAM[:2], host_outputs=True)
+    q.put((rank, r["topk_row0"], r["topk_idx"], r["topk_score"], r["pair_rank"], r["hits"], r["rr_sum"], r["sim_sum"],
+           r["num_pairs"], r["metrics"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,N,M", [(2, 300, 203), (3, 130, 50)])
+def test_slab_exchange_equals_single_process(oracle, synthetic, world, N, M):
+    """N=300 over 2 ranks: slabs of 256 and 44 rows (whole 128-row blocks); N=130 over 3 ranks: the third slab is
+    empty; M=203 / 50: ragged chunk shards, padded in the all-gather."""
+    distributed = importlib.import_module(PKG_NAME + ".distributed")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=slab_worker, args=(r, world, port, q, N, M)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    img, chk, _ = synthetic.make_numpy(N, M, 64, T=64, seed=33)
+    o = oracle.evaluate(img, chk, T=64, schema_mask=MASK, candidates="all", lam=LAM, kmax=max(KS), cutoff=CUTOFF)
+    covered = 0
+    for rank, row0, ti, ts, pr, hits, rr, sim, P, metrics in got:
+        lo, hi = distributed.slab_range(N, world, rank)
+        assert row0 == lo and ti.shape[1] == hi - lo
+        assert np.array_equal(ti, o["topk_idx"][:, lo:hi]) and np.array_equal(ts, o["topk_score"][:, lo:hi])
+        p0, p1 = o["pair_offsets"][lo], o["pair_offsets"][hi]
+        assert np.array_equal(pr, o["pair_rank"][:, p0:p1])
+        covered += hi - lo
+        # the metric sums are the whole job's on every rank
+        assert P == len(o["pair_chunk"]) and metrics["num_pairs"] == P
+        for si in range(4):
+            for qi, k in enumerate(KS):
+                assert hits[si, qi] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
+            want_rr = sum(1.0 / x for x in o["pair_rank"][si].tolist() if 1 <= x <= CUTOFF)
+            assert rr[si] == pytest.approx(want_rr, rel=1e-12)
+        assert sim == pytest.approx(float(o["pair_sim"].sum()), rel=1e-12)
+    assert covered == N
+
+
+def test_slab_range(pkg):
+    d = importlib.import_module(PKG_NAME + ".distributed")
+    for N in (0, 1, 127, 128, 129, 1000, 1000000):
+        for G in (1, 2, 3, 8):
+            r = [d.slab_range(N, G, k) for k in range(G)]
+            assert r[0][0] == 0 and r[-1][1] == N and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert all(a[0] % 128 == 0 or a[0] == N for a in r) and d.slab_size(N, G) * G >= N
