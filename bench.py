@@ -54,9 +54,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kprime", type=int, default=0)
-    ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather"],
+    ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather", "none"],
                     help="multi-GPU: alltoall = contraction sharded by chunk columns, rescoring by query rows (default); "
-                         "allgather = fully sharded variant (distributed.AllGatherScorer)")
+                         "allgather = fully sharded variant (distributed.AllGatherScorer); none = contraction and "
+                         "rescoring both sharded by query rows (no list exchange)")
     return ap.parse_args()
 
 
@@ -199,9 +200,15 @@ def run_reference(args):
 
 
 def workload(args, G):
-    how = (f"each of {G} GPU(s) ingests 1/{G} of the images and chunks (NVLink all-gather replicates them inside the step); "
-           "contraction sharded by chunk columns, exact rescoring by query rows" if getattr(args, "exchange", "alltoall") == "alltoall"
-           else f"chunks sharded over {G} GPU(s), images replicated")
+    ex = getattr(args, "exchange", "alltoall")
+    if G == 1:
+        how = "one GPU"
+    elif ex == "allgather":
+        how = f"chunks sharded over {G} GPUs, images replicated (fully sharded variant)"
+    else:
+        how = (f"each of {G} GPUs ingests 1/{G} of the images and of the chunks (an NVLink all-gather inside the step replicates "
+               "them); " + ("contraction sharded by chunk columns, exact rescoring by query rows" if ex == "alltoall"
+                            else "contraction and exact rescoring sharded by query rows"))
     return {"workload": f"BASELINE config 5: {args.N} images x {args.M} chunks, D={args.D}, all four schemas in one pass, "
                         f"K in {list(K_VALUES)} + MRR@{MRR_CUTOFF}, candidates=all, weak_weight={WEAK}",
             "N": args.N, "M": args.M, "D": args.D, "schemas": 4, "k_values": list(K_VALUES), "mrr_cutoff": MRR_CUTOFF,
@@ -231,12 +238,12 @@ def run_ours(args):
     eng = pkg.AlignmentEngine(local)
     run_kw = dict(schemas=SCHEMAS, k_values=K_VALUES, mrr_cutoff=MRR_CUTOFF, weak_weight=WEAK, kprime=args.kprime)
     phase_ms, step_ms = {}, {}
-    if args.exchange == "alltoall" or world == 1:
+    if args.exchange in ("alltoall", "none") or world == 1:
         # every rank ingests its slab of the images and its shard of the chunks
         i0, i1 = distributed.slab_range(N, world, rank)
         img, chk, meta = synthetic.make_torch(N, M, D, T=T_TERMS, device=dev, row0=r0, rows=r1 - r0, img_row0=i0,
                                               img_rows=i1 - i0)
-        sharded = distributed.ShardedScorer(eng, world, rank, dev)
+        sharded = distributed.ShardedScorer(eng, world, rank, dev, contraction="rows" if args.exchange == "none" else "columns")
 
         def step(im, ck, host_out):
             t0 = time.perf_counter()
@@ -334,6 +341,8 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (K1), timed with CUDA events inside the library
     t_fused = float(np.mean(fused_us)) * 1e-6
     flops_launch = 2.0 * N * (r1 - r0) * D  # algorithmic: 2*M_local*D per query x N queries per launch
+    if world > 1 and args.exchange == "none":
+        flops_launch = 2.0 * (i1 - i0) * M * D  # this rank's query slab against every chunk
     achieved = flops_launch / t_fused / 1e12 if t_fused > 0 else 0.0
     traffic = None  # DRAM bytes of one launch, from the committed ncu --set full capture of this very configuration
     tf = ROOT / "profiles" / "r1c_traffic.json"

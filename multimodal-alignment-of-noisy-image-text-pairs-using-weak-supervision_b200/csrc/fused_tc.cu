@@ -144,6 +144,8 @@ struct FusedArgs {
     int32_t *count;
     int kprime;
     float *dump;           // debug: write raw scores [N][M] instead of lists
+    float tau_init;        // -inf; tuning experiments start the lists at a threshold (MMALIGN_TAU_INIT)
+    int skip_final;        // tuning experiments: no end-of-unit compaction (MMALIGN_SKIP_FINAL)
 };
 
 // ---------------------------------------------------------------------------
@@ -378,7 +380,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             // uniform base of this unit's 256 lists + a 32-bit per-thread offset
             const char *ubase = reinterpret_cast<const char *>(P.keys + (list_id - (half * 128 + r)) * CAP);
             const uint32_t off0 = (uint32_t)(half * 128 + r) * (uint32_t)(CAP * 8);
-            float tau = -CUDART_INF_F;
+            float tau = P.tau_init;
             int n = 0;
             const int64_t row = rb * BM + r;
             for (int64_t t = t0; t < t1; ++t) {
@@ -430,7 +432,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
-            if (!P.dump) {  // leave at most K' + slack entries per list for the rescoring kernel
+            if (!P.dump && !P.skip_final) {  // leave at most K' + slack entries per list for the rescoring kernel
                 __syncwarp();
                 if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
                     compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > P.kprime + kSlack);
@@ -578,6 +580,9 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     a.keys = lists.keys; a.tau = lists.tau; a.count = lists.count;
     a.kprime = plan.kprime_list;
     a.dump = dump;
+    a.tau_init = -INFINITY;
+    if (const char *e = getenv("MMALIGN_TAU_INIT")) a.tau_init = (float)atof(e);
+    a.skip_final = getenv("MMALIGN_SKIP_FINAL") != nullptr;
     const CUtensorMap &ta = *reinterpret_cast<const CUtensorMap *>(tmap_a);
     const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;

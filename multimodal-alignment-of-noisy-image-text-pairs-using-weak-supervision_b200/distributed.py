@@ -66,8 +66,15 @@ class ShardedScorer:
     """Contraction sharded by chunk columns, rescoring by query rows (module docstring)."""
     FIELDS = ("emb", "key", "bbox", "terms")
 
-    def __init__(self, engine, world: int = 1, rank: int = 0, device=None, dist=None):
+    def __init__(self, engine, world: int = 1, rank: int = 0, device=None, dist=None, contraction: str = "columns"):
+        """contraction="columns" (default): the fused pass of rank g covers every image row against chunk shard g,
+        the candidate lists are exchanged.  contraction="rows": rank g contracts its own query slab against the
+        whole chunk table -- no list exchange, and the lists of a row warm up 2*splits times instead of 2*splits*G
+        times (the fused kernel's per-list warm-up is the one cost that grows with G in the column layout)."""
         self.eng, self.world, self.rank, self.device = engine, world, rank, device
+        if contraction not in ("columns", "rows"):
+            raise ValueError("contraction must be 'columns' or 'rows'")
+        self.contraction = contraction
         if dist is None and world > 1:
             import torch.distributed as dist
         self.dist = dist
@@ -137,24 +144,28 @@ class ShardedScorer:
                 if torch.cuda.is_available():
                     torch.cuda.synchronize()
                 marks.append((name, time.perf_counter()))
-            lo, hi = shard_range(M, G, self.rank)
-            eng.fused_pass(schemas, shard=(lo, hi - lo), k_values=k_values, mrr_cutoff=mrr_cutoff,
-                           weak_weight=weak_weight, kprime=kprime, n_ranks=G)
-            mark("fused_pass")
-            per = slab_size(N, G)
-            stride = torch.tensor([eng.list_stride()], dtype=torch.int32, device=self.device)
-            dist.all_reduce(stride, op=self.MAX)
-            stride = int(stride.item())
-            keys, count, tau = eng.export_lists(G, per, stride)
-            rk, rc, rt = torch.empty_like(keys), torch.empty_like(count), torch.empty_like(tau)
-            dist.all_to_all_single(rk, keys)
-            dist.all_to_all_single(rc, count)
-            dist.all_to_all_single(rt, tau)
-            mark("list exchange")
             row0, row1 = slab_range(N, G, self.rank)
-            r = eng.run(schemas, slab=(row0, row1 - row0), imported=(rk, rc, rt), **out_kw, **kw)
+            if self.contraction == "rows":
+                r = eng.run(schemas, slab=(row0, row1 - row0), **out_kw, **kw)
+                mark("fused + rescore slab")
+            else:
+                lo, hi = shard_range(M, G, self.rank)
+                eng.fused_pass(schemas, shard=(lo, hi - lo), k_values=k_values, mrr_cutoff=mrr_cutoff,
+                               weak_weight=weak_weight, kprime=kprime, n_ranks=G)
+                mark("fused_pass")
+                per = slab_size(N, G)
+                stride = torch.tensor([eng.list_stride()], dtype=torch.int32, device=self.device)
+                dist.all_reduce(stride, op=self.MAX)
+                stride = int(stride.item())
+                keys, count, tau = eng.export_lists(G, per, stride)
+                rk, rc, rt = torch.empty_like(keys), torch.empty_like(count), torch.empty_like(tau)
+                dist.all_to_all_single(rk, keys)
+                dist.all_to_all_single(rc, count)
+                dist.all_to_all_single(rt, tau)
+                mark("list exchange")
+                r = eng.run(schemas, slab=(row0, row1 - row0), imported=(rk, rc, rt), **out_kw, **kw)
+                mark("rescore slab")
             r["topk_row0"] = row0
-            mark("rescore slab")
             S, nk = r["hits"].shape
             st = r["stats"]
             packed = torch.tensor(np.concatenate([r["hits"].reshape(-1).astype(np.float64), r["rr_sum"],

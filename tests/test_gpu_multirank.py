@@ -80,9 +80,10 @@ def _run_ranks(world, rank_main):
     return results
 
 
+@pytest.mark.parametrize("contraction", ["columns", "rows"])
 @pytest.mark.parametrize("N,M,D,world,kprime", [(300, 2003, 128, 2, 0), (201, 5000, 512, 4, 0), (130, 4000, 64, 8, 0),
                                                 (700, 3000, 64, 3, 0), (5, 3, 64, 4, 0), (400, 6000, 64, 2, -1)])
-def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic, N, M, D, world, kprime):
+def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic, N, M, D, world, kprime, contraction):
     """ShardedScorer: each rank ingests 1/G of both tables, contracts against its chunk columns, exchanges the
     candidate lists and owns the exact results of its query slab.  D=64 makes near-ties and rescans likely;
     kprime=-1 stands for eps_scale=100: an inflated error bound sends uncertified rows through the exact scan."""
@@ -94,7 +95,7 @@ def test_column_sharded_contraction_row_sharded_rescoring(pkg, oracle, synthetic
 
     def rank_main(rank, dist):
         eng = pkg.AlignmentEngine(0)
-        sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=dist)
+        sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=dist, contraction=contraction)
         sc.load(cut(img, *distributed.slab_range(N, world, rank)), cut(chk, *distributed.shard_range(M, world, rank)),
                 N=N, M=M, n_terms=512)
         r = sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True, kprime=kprime,
