@@ -54,10 +54,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kprime", type=int, default=0)
-    ap.add_argument("--exchange", default="alltoall", choices=["alltoall", "allgather", "none"],
-                    help="multi-GPU: alltoall = contraction sharded by chunk columns, rescoring by query rows (default); "
-                         "allgather = fully sharded variant (distributed.AllGatherScorer); none = contraction and "
-                         "rescoring both sharded by query rows (no list exchange)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "alltoall", "allgather", "none"],
+                    help="multi-GPU: none = contraction and rescoring both sharded by query rows (no list exchange); "
+                         "alltoall = contraction sharded by chunk columns, rescoring by query rows; auto (default) = none "
+                         "when every rank's query slab fills the GPU, else alltoall; allgather = fully sharded variant "
+                         "(distributed.AllGatherScorer)")
     return ap.parse_args()
 
 
@@ -238,6 +239,8 @@ def run_ours(args):
     eng = pkg.AlignmentEngine(local)
     run_kw = dict(schemas=SCHEMAS, k_values=K_VALUES, mrr_cutoff=MRR_CUTOFF, weak_weight=WEAK, kprime=args.kprime)
     phase_ms, step_ms = {}, {}
+    if args.exchange == "auto":
+        args.exchange = "none" if distributed.slab_size(N, world) >= 148 * 128 else "alltoall"
     if args.exchange in ("alltoall", "none") or world == 1:
         # every rank ingests its slab of the images and its shard of the chunks
         i0, i1 = distributed.slab_range(N, world, rank)
