@@ -39,6 +39,7 @@ K_VALUES = (1, 5, 10, 20)
 MRR_CUTOFF = 100
 WEAK = (0.3, 0.2)
 T_TERMS = 512
+METRIC = "top-10 retrieval queries/s at 1M x 1M, D=512 (all four schemas, K<=20 + MRR@100)"
 
 
 def parse():
@@ -167,6 +168,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.exchange == "auto":  # the same config line as the GPU arm prints for this --gpus
+        distributed = importlib.import_module(PKG + ".distributed")
+        args.exchange = "none" if distributed.slab_size(args.N, args.gpus) >= 148 * 128 else "alltoall"
     import torch
     synthetic = importlib.import_module(PKG + ".synthetic")
     from oracle import numpy_port
@@ -187,11 +191,11 @@ def run_reference(args):
     t = sum(d for _, d in times)
     value = q / t
     line = {
-        "impl": "reference", "metric": "top-K retrieval queries/s (CPU port of the reference scoring+ranking path)",
+        "impl": "reference", "metric": METRIC,
         "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload(args, 1),
+        "config": workload(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
                          "sample": f"{times[-1][0]} query rows per step x all {args.M} chunks, D={args.D}, 4 schemas, "
                                    f"K<=20 + MRR@100; numpy sgemm ({numpy_port.blas_info()}) + argpartition/lexsort"},
@@ -364,7 +368,7 @@ def run_ours(args):
                                 "exact_scan_kernel": float(np.mean(scan_us)) / 1e3}}
     m = res["metrics"]
     line = {
-        "metric": "top-10 retrieval queries/s at 1M x 1M, D=512 (all four schemas, K<=20 + MRR@100)",
+        "metric": METRIC,
         "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": workload(args, world), "clocks": clocks,
