@@ -286,3 +286,47 @@ def test_large_run_properties(eng, synthetic):
     eng.set_images(sub["emb"], sub["key"], sub["bbox"], None)
     e = eng.run(ALL4, candidates="all", k_values=(1, 5, 10, 20), mrr_cutoff=100, weak_weight=(0.3, 0.2), path="exact")
     assert np.array_equal(e["topk_idx"], idx[:, rows]) and np.array_equal(e["topk_score"], sc[:, rows])
+
+
+# ----------------------------------------------------------------------------- documented limits
+def _page_heavy_corpus(synthetic, n_on_page):
+    """3 images, 700 chunks: n_on_page chunks share page (7, 3) with image 0; image 1 has a NULL page."""
+    img, chk, _ = synthetic.make_numpy(3, 700, 64, T=64, seed=21)
+    key = lambda manual, page: np.uint64((manual << 32) | page)
+    chk["key"][:] = [key(1000 + j, 1) for j in range(700)]          # every chunk alone on its page ...
+    chk["key"][50:50 + n_on_page] = key(7, 3)                       # ... except one crowded page
+    img["key"][:] = [key(7, 3), np.uint64(0xFFFFFFFFFFFFFFFF), key(1000 + 5, 1)]
+    return img, chk
+
+
+@pytest.mark.parametrize("cand", ["same_page", "all"])
+def test_page_with_512_chunks_is_the_limit(oracle, eng, synthetic, pkg, cand):
+    img, chk = _page_heavy_corpus(synthetic, 512)
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates=cand, lam=(0.3, 0.2), ks=(1, 5, 10, 20), cutoff=100)
+    assert r["num_pairs"] == 513
+    img, chk = _page_heavy_corpus(synthetic, 513)
+    load(eng, img, chk, 64)
+    with pytest.raises(pkg.MMAlignError) as e:
+        eng.run(ALL4, candidates=cand, k_values=(1, 5, 10), mrr_cutoff=100)
+    assert e.value.code == -5 and "512 same-page chunks" in str(e.value)
+
+
+def test_widest_lists_k256_and_cutoff256(oracle, eng, synthetic, pkg):
+    """Kmax = mrr_cutoff = 256 (the documented maximum): K' = 491."""
+    img, chk, _ = synthetic.make_numpy(300, 6000, 64, T=64, seed=23)
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 256), cutoff=256)
+    assert r["stats"]["kprime"] == 491 and r["topk_idx"].shape == (4, 300, 256)
+    load(eng, img, chk, 64)
+    for bad in (dict(k_values=(257,)), dict(mrr_cutoff=257)):
+        with pytest.raises(pkg.MMAlignError):
+            eng.run(ALL4, candidates="all", **bad)
+
+
+def test_512_entry_lists(oracle, eng, synthetic):
+    """K' = 2000 makes every list keep > 113 entries, which selects the 512-entry list variant of the fused kernel;
+    the union of a row's lists then exceeds what the rescoring kernel holds per row, so those rows take the exact
+    scan -- the result is still the oracle's."""
+    img, chk, _ = synthetic.make_numpy(400, 20000, 64, T=64, seed=25)
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 5, 10, 20), cutoff=100,
+                             kprime=2000)
+    assert r["stats"]["kprime"] == 2000
