@@ -276,6 +276,24 @@ class AlignmentEngine:
                                                  pb.ctypes.data, po.ctypes.data, len(terms), W, bits.ctypes.data, None))
         return bits
 
+    def term_bitsets_device(self, text, text_off, terms: Sequence[str], bits):
+        """mmalign_term_bitsets on device-resident tensors: text uint8 [bytes], text_off int64 [m + 1],
+        bits int64 [m, W] (out).  The term table (tiny) goes up with the call."""
+        enc = [s.encode("utf-8") for s in terms]
+        po = np.zeros(len(enc) + 1, np.int64)
+        if enc:
+            np.cumsum([len(b) for b in enc], out=po[1:])
+        pb = np.frombuffer(b"".join(enc) or b"\0", np.uint8)
+        m, W = int(bits.shape[0]), int(bits.shape[1])
+        self._check(self._L.mmalign_term_bitsets(self._ctx, text.data_ptr(), text_off.data_ptr(), m, pb.ctypes.data,
+                                                 po.ctypes.data, len(terms), W, bits.data_ptr(), None))
+        return bits
+
+    def alignments_device(self, schema: str, rec, raw: bool = False):
+        """mmalign_alignments into a device tensor rec float64 [P, 3]."""
+        self._check(self._L.mmalign_alignments(self._ctx, SCHEMA_BITS[schema] | (0x100 if raw else 0), rec.data_ptr(), None))
+        return rec
+
     def debug_scores(self):
         out = np.zeros((self.N, self.M), np.float32)
         self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))
