@@ -844,14 +844,6 @@ extern "C" int mmalign_reduce_metrics(mmalign_ctx *c, const int32_t *pair_rank, 
     return MMALIGN_OK;
 }
 
-namespace mma {
-struct TermTableHost {
-    std::vector<int32_t> off, bucket_start, bucket_term;
-    std::vector<uint32_t> always;
-};
-int build_term_table(const uint8_t *terms, const int64_t *term_off, int n_terms, int term_words, TermTableHost *out);
-}
-
 extern "C" int mmalign_term_bitsets(mmalign_ctx *c, const uint8_t *text, const int64_t *text_off, int64_t m,
                                     const uint8_t *terms, const int64_t *term_off, int32_t n_terms, int32_t term_words,
                                     uint64_t *bits, void *stream)
@@ -871,15 +863,23 @@ extern "C" int mmalign_term_bitsets(mmalign_ctx *c, const uint8_t *text, const i
     const int trc = build_term_table(terms, n_terms > 0 ? term_off : zero_off, n_terms, term_words, &h);
     if (trc) return fail(c, MMALIGN_EINVAL, "mmalign_term_bitsets: bad term offsets (code %d)", trc);
     const size_t tb = n_terms > 0 ? (size_t)term_off[n_terms] : 0;
-    const size_t o_off = (tb + 15) & ~(size_t)15, o_bs = o_off + h.off.size() * 4, o_bt = o_bs + h.bucket_start.size() * 4,
-                 o_al = o_bt + h.bucket_term.size() * 4, total = o_al + h.always.size() * 4;
+    // one packed upload: term bytes | hash (8-byte slots) | offsets | short-term buckets | groups | empty-term mask
+    auto pad16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o_hash = pad16(tb), o_off = pad16(o_hash + h.hash.size() * 4), o_bs = pad16(o_off + h.off.size() * 4),
+                 o_bt = pad16(o_bs + h.bucket_start.size() * 4), o_gt = pad16(o_bt + h.bucket_term.size() * 4),
+                 o_al = pad16(o_gt + h.group_term.size() * 4), total = o_al + h.always.size() * 4;
+    std::vector<char> packed(total, 0);
+    if (tb) memcpy(packed.data(), terms, tb);
+    memcpy(packed.data() + o_hash, h.hash.data(), h.hash.size() * 4);
+    memcpy(packed.data() + o_off, h.off.data(), h.off.size() * 4);
+    memcpy(packed.data() + o_bs, h.bucket_start.data(), h.bucket_start.size() * 4);
+    memcpy(packed.data() + o_bt, h.bucket_term.data(), h.bucket_term.size() * 4);
+    memcpy(packed.data() + o_gt, h.group_term.data(), h.group_term.size() * 4);
+    memcpy(packed.data() + o_al, h.always.data(), h.always.size() * 4);
     CU(c, c->term_table.reserve(total));
     char *d = (char *)c->term_table.p;
-    if (tb) CU(c, cudaMemcpyAsync(d, terms, tb, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(d + o_off, h.off.data(), h.off.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(d + o_bs, h.bucket_start.data(), h.bucket_start.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(d + o_bt, h.bucket_term.data(), h.bucket_term.size() * 4, cudaMemcpyHostToDevice, st));
-    CU(c, cudaMemcpyAsync(d + o_al, h.always.data(), h.always.size() * 4, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(d, packed.data(), total, cudaMemcpyHostToDevice, st));
+    CU(c, cudaStreamSynchronize(st));  // `packed` is pageable host memory that goes out of scope
     // the texts
     const int64_t *d_off = text_off;
     int64_t total_text = 0;
@@ -905,7 +905,8 @@ extern "C" int mmalign_term_bitsets(mmalign_ctx *c, const uint8_t *text, const i
     int rc;
     if ((rc = sg.commit())) return rc;
     CU(c, launch_term_bitsets(d_text, d_off, m, (const uint8_t *)d, (const int32_t *)(d + o_off), (const int32_t *)(d + o_bs),
-                              (const int32_t *)(d + o_bt), (const uint32_t *)(d + o_al), term_words, d_bits, st));
+                              (const int32_t *)(d + o_bt), (const uint32_t *)(d + o_hash), h.hash_bits,
+                              (const int32_t *)(d + o_gt), (const uint32_t *)(d + o_al), term_words, d_bits, st));
     if ((rc = sg.copy_back())) return rc;
     CU(c, cudaStreamSynchronize(st));
     return MMALIGN_OK;

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <vector>
 #include "../../include/mmalign.h"
 
 namespace mma {
@@ -291,9 +292,15 @@ cudaError_t launch_count_beating(const int64_t *deep_idx, const double *deep_sco
                                  int64_t n_q, const int64_t *q_image, const int64_t *q_chunk,
                                  const double *q_score, int32_t *counts, cudaStream_t st);
 // ingest.cu
-struct TermTableHost;
+struct TermTableHost {  // the lexical terms, indexed on the host for term_bitsets_kernel (T terms: tiny)
+    std::vector<int32_t> off, bucket_start, bucket_term, group_term;
+    std::vector<uint32_t> always, hash;  // hash: 2 words per slot
+    int hash_bits = 6;
+};
+int build_term_table(const uint8_t *terms, const int64_t *term_off, int n_terms, int term_words, TermTableHost *out);
 cudaError_t launch_term_bitsets(const uint8_t *text, const int64_t *text_off, int64_t m, const uint8_t *term_bytes,
                                 const int32_t *term_off, const int32_t *bucket_start, const int32_t *bucket_term,
+                                const uint32_t *hash, int hash_bits, const int32_t *group_term,
                                 const uint32_t *always, int term_words, uint64_t *bits, cudaStream_t st);
 // fused_tc.cu
 struct FusedPlan {

@@ -8,10 +8,12 @@
 // kernels popcount (rescore.cu: term_hits).  Matching is on UTF-8 bytes; UTF-8 is self-synchronising, so a byte
 // match of a valid pattern in a valid text is a code-point match, exactly Python's `in` on str.
 //
-// One warp per chunk.  Lane l looks at text positions l, l + 32, ...: the byte there selects a bucket of terms
-// (terms grouped by first byte, index in shared memory), and each of those few terms is compared byte by byte.
-// HBM-bound work in principle (each text byte is read from HBM once, L1 serves the re-reads of a comparison);
-// in practice bounded by the byte comparisons.  Algorithmic bytes per chunk: its text length + 8 * term_words.
+// One warp per chunk, lane l on text positions l, l + 32, ...  The three bytes at a position (two of them come
+// from the neighbouring lanes by shuffle) are looked up in a hash table of the terms' first three bytes, held in
+// shared memory: almost every position misses and costs one probe; a hit compares the rest of the few terms of
+// that group byte by byte.  Two-byte terms sit in the same table under their two bytes (a second probe per
+// position, no comparison needed on a hit); one-byte terms go through a first-byte bucket list.  Each text byte is
+// read from HBM once.  Algorithmic bytes per chunk: its text length + 8 * term_words.
 #include "common.cuh"
 #include <algorithm>
 #include <vector>
@@ -25,35 +27,87 @@ constexpr int kMaxTermWords = 64;  // T <= 4096 terms
 struct TermTable {
     const uint8_t *bytes;        // concatenated terms
     const int32_t *off;          // [T + 1]
-    const int32_t *bucket_start; // [257] terms grouped by first byte
-    const int32_t *bucket_term;  // [T_nonempty] term ids, bucket by bucket, increasing id inside a bucket
+    const int32_t *bucket_start; // [257] one-byte terms, grouped by that byte
+    const int32_t *bucket_term;  //       their ids, bucket by bucket
+    const uint2 *hash;           // [hash_size] terms of >= 3 bytes by their first three bytes, x = 1 + (b0 | b1 << 8 |
+                                 //   b2 << 16); two-byte terms by x = kTwoByteKey + (b0 | b1 << 8); 0 = empty slot;
+                                 //   y = group start | count << 16
+    const int32_t *group_term;   // term ids, group by group, increasing id inside a group
+    int hash_bits;               // hash_size = 1 << hash_bits
 };
+
+constexpr uint32_t kTwoByteKey = 0x02000001u;
+__host__ __device__ __forceinline__ uint32_t trigram_slot(uint32_t key, int bits)
+{
+    return (key * 2654435761u) >> (32 - bits);
+}
 
 __global__ void __launch_bounds__(kIngestThreads)
 term_bitsets_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict__ text_off, int64_t m, TermTable tt,
                     int term_words, const uint32_t *__restrict__ always, uint64_t *__restrict__ bits)
 {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *s_hash = reinterpret_cast<uint2 *>(smem_raw);
     __shared__ int32_t s_bucket[257];
     __shared__ uint32_t s_bits[kIngestWarps][2 * kMaxTermWords];
+    const int hash_size = 1 << tt.hash_bits;
     for (int b = threadIdx.x; b < 257; b += kIngestThreads) s_bucket[b] = tt.bucket_start[b];
+    for (int b = threadIdx.x; b < hash_size; b += kIngestThreads) s_hash[b] = tt.hash[b];
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *mine = s_bits[warp];
     const int words32 = 2 * term_words;
+    const uint32_t hmask = (uint32_t)hash_size - 1u;
     for (int64_t j = blockIdx.x * (int64_t)kIngestWarps + warp; j < m; j += (int64_t)gridDim.x * kIngestWarps) {
         for (int w = lane; w < words32; w += 32) mine[w] = always[w];  // empty terms occur in every text
         __syncwarp();
         const int64_t t0 = text_off[j], len = text_off[j + 1] - t0;
         const uint8_t *s = text + t0;
-        for (int64_t p = lane; p < len; p += 32) {
-            const int c0 = s[p];
-            const int b0 = s_bucket[c0], b1 = s_bucket[c0 + 1];
-            for (int b = b0; b < b1; ++b) {
+        for (int64_t base = 0; base < len; base += 32) {
+            const int64_t p = base + lane;
+            // this position's byte and the two after it: from the neighbouring lanes, and for the last two lanes
+            // from the first two bytes of the next batch (fetched by lanes 0 and 1)
+            const uint32_t c0 = p < len ? s[p] : 0u;
+            const uint32_t nx = (lane < 2 && p + 32 < len) ? s[p + 32] : 0u;
+            uint32_t c1 = __shfl_down_sync(0xFFFFFFFFu, c0, 1), c2 = __shfl_down_sync(0xFFFFFFFFu, c0, 2);
+            const uint32_t n0 = __shfl_sync(0xFFFFFFFFu, nx, 0), n1 = __shfl_sync(0xFFFFFFFFu, nx, 1);
+            if (lane == 31) { c1 = n0; c2 = n1; }
+            if (lane == 30) c2 = n0;
+            if (p >= len) continue;
+            // one-byte terms
+            for (int b = s_bucket[c0]; b < s_bucket[c0 + 1]; ++b) {
                 const int t = tt.bucket_term[b];
+                atomicOr(&mine[t >> 5], 1u << (t & 31));
+            }
+            // two-byte terms: the key is the whole term
+            if (p + 2 > len) continue;
+            {
+                const uint32_t key2 = kTwoByteKey + (c0 | (c1 << 8));
+                uint32_t h2 = trigram_slot(key2, tt.hash_bits);
+                uint2 e2 = s_hash[h2];
+                while (e2.x != 0u && e2.x != key2) { h2 = (h2 + 1u) & hmask; e2 = s_hash[h2]; }
+                if (e2.x != 0u) {
+                    const int a0 = (int)(e2.y & 0xFFFFu), a1 = a0 + (int)(e2.y >> 16);
+                    for (int g = a0; g < a1; ++g) {
+                        const int t = tt.group_term[g];
+                        if (!(mine[t >> 5] & (1u << (t & 31)))) atomicOr(&mine[t >> 5], 1u << (t & 31));
+                    }
+                }
+            }
+            // terms of three bytes and more
+            if (p + 3 > len) continue;
+            const uint32_t key = 1u + (c0 | (c1 << 8) | (c2 << 16));
+            uint32_t h = trigram_slot(key, tt.hash_bits);
+            uint2 e = s_hash[h];
+            while (e.x != 0u && e.x != key) { h = (h + 1u) & hmask; e = s_hash[h]; }
+            if (e.x == 0u) continue;
+            const int g0 = (int)(e.y & 0xFFFFu), g1 = g0 + (int)(e.y >> 16);
+            for (int g = g0; g < g1; ++g) {
+                const int t = tt.group_term[g];
                 if (mine[t >> 5] & (1u << (t & 31))) continue;  // found earlier (a stale read only costs a re-match)
                 const int o = tt.off[t], tl = tt.off[t + 1] - o;
                 if (p + tl > len) continue;
-                int q = 1;
+                int q = 3;
                 while (q < tl && s[p + q] == tt.bytes[o + q]) ++q;
                 if (q == tl) atomicOr(&mine[t >> 5], 1u << (t & 31));
             }
@@ -66,13 +120,9 @@ term_bitsets_kernel(const uint8_t *__restrict__ text, const int64_t *__restrict_
     }
 }
 
-// Host side of the term table: offsets as int32, terms grouped by first byte (counting sort), the bit mask of
-// empty terms.  The table is tiny (T terms); this is plumbing, the matching itself runs in the kernel above.
-struct TermTableHost {  // (also declared in api.cu, its only user)
-    std::vector<int32_t> off, bucket_start, bucket_term;
-    std::vector<uint32_t> always;
-};
-
+// Host side of the term table: offsets as int32, one-byte terms grouped by their byte (counting sort), two-byte
+// terms grouped by their two bytes and longer ones by their first three bytes behind one open-addressing hash
+// table (load factor <= 1/2), the bit mask of empty terms.  The table is tiny (T terms); this is plumbing, the matching itself runs in the kernel above.
 int build_term_table(const uint8_t *terms, const int64_t *term_off, int n_terms, int term_words, TermTableHost *out)
 {
     if (n_terms < 0 || term_words < 1 || term_words > kMaxTermWords || (int64_t)term_words * 64 < n_terms) return -1;
@@ -81,30 +131,63 @@ int build_term_table(const uint8_t *terms, const int64_t *term_off, int n_terms,
     h.off.assign(n_terms + 1, 0);
     h.bucket_start.assign(257, 0);
     h.always.assign(2 * term_words, 0u);
+    std::vector<std::pair<uint32_t, int32_t>> longs;  // (hash key, term id)
     for (int t = 0; t < n_terms; ++t) {
         if (term_off[t + 1] < term_off[t]) return -2;
         h.off[t + 1] = (int32_t)term_off[t + 1];
-        if (term_off[t + 1] == term_off[t]) h.always[t >> 5] |= 1u << (t & 31);
-        else h.bucket_start[terms[term_off[t]] + 1]++;
+        const int64_t tl = term_off[t + 1] - term_off[t];
+        const uint8_t *b = terms + term_off[t];
+        if (tl == 0) h.always[t >> 5] |= 1u << (t & 31);
+        else if (tl == 1) h.bucket_start[b[0] + 1]++;
+        else if (tl == 2) longs.push_back({kTwoByteKey + ((uint32_t)b[0] | ((uint32_t)b[1] << 8)), t});
+        else longs.push_back({1u + ((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16)), t});
     }
     for (int b = 0; b < 256; ++b) h.bucket_start[b + 1] += h.bucket_start[b];
     h.bucket_term.assign(std::max(1, h.bucket_start[256]), 0);
     std::vector<int32_t> fill(h.bucket_start.begin(), h.bucket_start.end() - 1);
-    for (int t = 0; t < n_terms; ++t)
-        if (term_off[t + 1] > term_off[t]) h.bucket_term[fill[terms[term_off[t]]]++] = t;
+    for (int t = 0; t < n_terms; ++t) {
+        const int64_t tl = term_off[t + 1] - term_off[t];
+        if (tl == 1) h.bucket_term[fill[terms[term_off[t]]]++] = t;
+    }
+    std::sort(longs.begin(), longs.end());
+    h.group_term.assign(std::max<size_t>(1, longs.size()), 0);
+    size_t groups = 0;
+    for (size_t i = 0; i < longs.size(); ++i) {
+        h.group_term[i] = longs[i].second;
+        if (i == 0 || longs[i].first != longs[i - 1].first) ++groups;
+    }
+    h.hash_bits = 6;
+    while ((size_t)1 << h.hash_bits < 2 * groups) ++h.hash_bits;
+    const uint32_t mask = (1u << h.hash_bits) - 1u;
+    h.hash.assign((size_t)2 << h.hash_bits, 0u);
+    for (size_t i = 0; i < longs.size();) {
+        size_t e = i;
+        while (e < longs.size() && longs[e].first == longs[i].first) ++e;
+        const uint32_t key = longs[i].first;
+        uint32_t slot = trigram_slot(key, h.hash_bits);
+        while (h.hash[2 * slot] != 0u) slot = (slot + 1u) & mask;
+        h.hash[2 * slot] = key;
+        h.hash[2 * slot + 1] = (uint32_t)i | ((uint32_t)(e - i) << 16);
+        i = e;
+    }
     return 0;
 }
 
 cudaError_t launch_term_bitsets(const uint8_t *text, const int64_t *text_off, int64_t m, const uint8_t *term_bytes,
                                 const int32_t *term_off, const int32_t *bucket_start, const int32_t *bucket_term,
+                                const uint32_t *hash, int hash_bits, const int32_t *group_term,
                                 const uint32_t *always, int term_words, uint64_t *bits, cudaStream_t st)
 {
     if (m == 0) return cudaSuccess;
     TermTable tt;
     tt.bytes = term_bytes; tt.off = term_off; tt.bucket_start = bucket_start; tt.bucket_term = bucket_term;
+    tt.hash = reinterpret_cast<const uint2 *>(hash); tt.group_term = group_term; tt.hash_bits = hash_bits;
+    const size_t smem = (size_t)8 << hash_bits;  // <= 64 KiB (4096 groups)
+    cudaError_t e = cudaFuncSetAttribute(term_bitsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int64_t grid = (m + kIngestWarps - 1) / kIngestWarps;
     if (grid > 148 * 8) grid = 148 * 8;
-    term_bitsets_kernel<<<(unsigned)grid, kIngestThreads, 0, st>>>(text, text_off, m, tt, term_words, always, bits);
+    term_bitsets_kernel<<<(unsigned)grid, kIngestThreads, smem, st>>>(text, text_off, m, tt, term_words, always, bits);
     return cudaGetLastError();
 }
 

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=400_000)
     ap.add_argument("--terms", type=int, default=512)
     ap.add_argument("--pairs-images", type=int, default=1_000_000)
+    ap.add_argument("--skip-alignments", action="store_true")
     a = ap.parse_args()
     import torch
     pkg = importlib.import_module(PKG)
@@ -89,6 +90,9 @@ def main():
                                        "sample": f"{len(sample)} chunks x {a.terms} terms, oracle/mmalign_oracle.c: orc_term_bitsets"}}),
           flush=True)
 
+    if a.skip_alignments:
+        eng.close()
+        return
     # ---- alignments: the records of all same-page pairs of the synthetic corpus (8 pairs per image)
     N = a.pairs_images
     img, chk, _ = synthetic.make_torch(N, N, 64, T=512, device=dev)
