@@ -30,9 +30,13 @@ struct Trace {
     }
 };
 
-struct DevBuf {  // growable device scratch
+struct DevBuf {  // growable device scratch; frees itself (locals on error paths, context members on destroy)
     void *p = nullptr;
     size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
     cudaError_t reserve(size_t n)
     {
         if (n <= bytes) return cudaSuccess;
