@@ -198,13 +198,14 @@ class OracleSlabEngine:
         tau = torch.full((n_dest, slab_rows), float("-inf"))
         return keys, count, tau
 
-    def run(self, schemas, *, slab, imported, k_values, mrr_cutoff, weak_weight, **_):
-        keys, count, tau = imported
+    def run(self, schemas, *, slab, k_values, mrr_cutoff, weak_weight, imported=None, **_):
         row0, rows = slab
-        for r in range(rows):  # every global column exactly once, from the rank that owns it
-            cols = torch.cat([keys[g, r, :int(count[g, r])] for g in range(keys.shape[0])]).numpy() & 0xFFFFFFFF
-            assert np.array_equal(np.sort(cols), np.arange(self.M)), (row0, r)
-        assert torch.isinf(tau[:, :rows]).all()
+        if imported is not None:  # column layout: every global column exactly once, from the rank that owns it
+            keys, count, tau = imported
+            for r in range(rows):
+                cols = torch.cat([keys[g, r, :int(count[g, r])] for g in range(keys.shape[0])]).numpy() & 0xFFFFFFFF
+                assert np.array_equal(np.sort(cols), np.arange(self.M)), (row0, r)
+            assert torch.isinf(tau[:, :rows]).all()
         lam = (weak_weight[0], weak_weight[1], weak_weight[0] + weak_weight[1])
         kmax, kneed = max(k_values), max(max(k_values), mrr_cutoff)
         o = self.o.evaluate(self.img, self.chk, T=self.T, schema_mask=MASK, candidates="all", lam=lam, kmax=kmax, cutoff=kneed)
@@ -217,7 +218,7 @@ class OracleSlabEngine:
                     stats=dict(rows_rescanned=0, candidates_rescored=0))
 
 
-def slab_worker(rank, world, port, q, N, M):
+def slab_worker(rank, world, port, q, N, M, contraction):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle
@@ -225,7 +226,7 @@ def slab_worker(rank, world, port, q, N, M):
     distributed = importlib.import_module(PKG_NAME + ".distributed")
     img, chk, _ = synthetic.make_numpy(N, M, 64, T=64, seed=33)
     cut = lambda d, lo, hi: {k: (v[lo:hi] if v is not None else None) for k, v in d.items()}
-    sc = distributed.ShardedScorer(OracleSlabEngine(oracle, 64), world, rank, None, dist=dist)
+    sc = distributed.ShardedScorer(OracleSlabEngine(oracle, 64), world, rank, None, dist=dist, contraction=contraction)
     sc.load(cut(img, *distributed.slab_range(N, world, rank)), cut(chk, *distributed.shard_range(M, world, rank)),
             N=N, M=M, n_terms=64)
     r = sc.run(schemas=None, k_values=KS, mrr_cutoff=CUTOFF, weak_weight=LAM[:2], host_outputs=True)
@@ -235,8 +236,8 @@ def slab_worker(rank, world, port, q, N, M):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,N,M", [(2, 300, 203), (3, 130, 50)])
-def test_slab_exchange_equals_single_process(oracle, synthetic, world, N, M):
+@pytest.mark.parametrize("world,N,M,contraction", [(2, 300, 203, "columns"), (3, 130, 50, "auto"), (2, 300, 203, "rows")])
+def test_slab_exchange_equals_single_process(oracle, synthetic, world, N, M, contraction):
     """N=300 over 2 ranks: slabs of 256 and 44 rows (whole 128-row blocks); N=130 over 3 ranks: the third slab is
     empty; M=203 / 50: ragged chunk shards, padded in the all-gather."""
     distributed = importlib.import_module(PKG_NAME + ".distributed")
@@ -245,7 +246,7 @@ def test_slab_exchange_equals_single_process(oracle, synthetic, world, N, M):
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=slab_worker, args=(r, world, port, q, N, M)) for r in range(world)]
+    procs = [ctx.Process(target=slab_worker, args=(r, world, port, q, N, M, contraction)) for r in range(world)]
     for p in procs:
         p.start()
     got = sorted([q.get(timeout=240) for _ in procs], key=lambda x: x[0])
