@@ -136,6 +136,20 @@ class ClockSampler:
                 "source": "NVML: SM clock every 200 ms, throttle reasons and power every 2 s"}
 
 
+REJECT = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+
+
+def clocks_rejected(clocks) -> bool:
+    """True when the timed region saw a hardware / thermal slowdown, or SM clocks far below the maximum with no
+    throttle reason at all (a leftover clock lock).  sw_power_cap alone is normal for a dense GEMM on a 1 kW part."""
+    if not clocks or clocks.get("sm_mhz") is None:
+        return False
+    reasons = clocks.get("reasons") or []
+    if any(r in REJECT for r in reasons):
+        return True
+    return not reasons and clocks["sm_mhz"] < 0.6 * (clocks.get("sm_max_mhz") or 0)
+
+
 # ------------------------------------------------------------------------------------------- reference arm
 def cpu_sample(img_h, chk_h, rows, budget_note):
     """The CPU port on `rows` query rows against the full chunk table; returns (queries/s, seconds)."""
@@ -320,6 +334,23 @@ def run_ours(args):
     t_begin = time.time()
     ms, res = timed(dev_step, args.steps)
     clocks = sampler.stop(t_begin, time.time()) if rank == 0 else None
+    # a throttled (or clock-locked) run is measured again, once; rank 0 saw the clocks, every rank has to follow
+    redo = torch.tensor([1 if (rank == 0 and clocks_rejected(clocks)) else 0], device=dev)
+    if world > 1:
+        dist.broadcast(redo, 0)
+    if int(redo.item()):
+        first = clocks
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        step(img, chk, False)
+        for l_ in (fused_us, resc_us, scan_us, launches):
+            l_.clear()
+        t_begin = time.time()
+        ms, res = timed(dev_step, args.steps)
+        if rank == 0:
+            clocks = sampler.stop(t_begin, time.time())
+            clocks["remeasured_after"] = first
     ms_per_step = ms / args.steps
     value = N / (ms_per_step / 1000.0)
 

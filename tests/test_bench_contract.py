@@ -31,3 +31,17 @@ def test_ranks_other_than_zero_stay_silent_in_the_reference_arm():
     out = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--gpus", "2", "--N", "600", "--M", "2000"],
                          cwd=ROOT, capture_output=True, text=True, env=env, check=True)
     assert out.stdout.strip() == ""
+
+
+def test_throttled_runs_are_rejected():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    ok = {"sm_mhz": 1575.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"]}
+    assert not b.clocks_rejected(ok) and not b.clocks_rejected(None)
+    assert not b.clocks_rejected({"sm_mhz": 1950.0, "sm_max_mhz": 1965.0, "reasons": []})
+    assert b.clocks_rejected(dict(ok, reasons=["sw_power_cap", "hw_thermal_slowdown"]))
+    assert b.clocks_rejected(dict(ok, reasons=["sw_thermal_slowdown"])) and b.clocks_rejected(dict(ok, reasons=["hw_slowdown"]))
+    assert b.clocks_rejected({"sm_mhz": 900.0, "sm_max_mhz": 1965.0, "reasons": []})      # clock lock left behind
+    assert not b.clocks_rejected({"sm_mhz": None, "sm_max_mhz": 1965.0, "reasons": ["no samples: x"]})
