@@ -64,3 +64,36 @@ def test_oracle_fuzz_against_the_live_reference():
         bits = oracle.term_bitsets([text], terms) if terms else np.zeros((1, 1), np.uint64)
         hits = int(np.unpackbits(bits.view(np.uint8)).sum())
         assert oracle.lexical(hits, len(terms)) == want, (text, terms)
+
+
+def test_metric_functions_on_random_corpora(tmp_path):
+    """The unmodified compute_top_k_accuracy / compute_mrr / compute_average_similarity over the fake pgvector
+    against the oracle's same-page evaluation, on random corpora with NULL pages, empty pages, duplicated embeddings
+    (ties) and un-normalised rows -- beyond the one committed golden corpus."""
+    import numpy as np
+    from oracle import oracle
+    for seed in range(6):
+        rng = np.random.default_rng(100 + seed)
+        N, M, D = int(rng.integers(5, 30)), int(rng.integers(20, 120)), 8
+        n_pages = max(1, M // 6)
+        ce = rng.standard_normal((M, D)).astype(np.float32)
+        ce[rng.integers(0, M, 6)] = ce[0]                                   # duplicates -> ties
+        ie = rng.standard_normal((N, D)).astype(np.float32) * rng.uniform(0.5, 3.0, (N, 1)).astype(np.float32)
+        cpage = [None if rng.random() < 0.05 else int(rng.integers(0, n_pages)) for _ in range(M)]
+        ipage = [None if rng.random() < 0.1 else int(rng.integers(0, n_pages + 2)) for _ in range(N)]
+        cman = [f"m{(p or 0) % 3}" for p in cpage]
+        iman = [f"m{(p or 0) % 3}" for p in ipage]
+        t = dict(image_ids=[f"i{i}" for i in range(N)], image_manual=iman, image_page=ipage, image_emb=ie,
+                 chunk_ids=[f"c{j}" for j in range(M)], chunk_manual=cman, chunk_page=cpage, chunk_emb=ce, alignments=[])
+        db = rh.FakeDB({"vanilla_clip": t})
+        ev, _ = rh.load_reference(db, output_dir=tmp_path)
+        s = "vanilla_clip"
+        want = (ev.compute_top_k_accuracy(s, [1, 5, 10]), ev.compute_mrr(s), ev.compute_average_similarity(s))
+        ids, null = {}, np.uint64(0xFFFFFFFFFFFFFFFF)
+        key = lambda man, page: null if page is None else np.uint64(ids.setdefault((man, page), len(ids)))
+        img = dict(emb=ie, key=np.array([key(m, p) for m, p in zip(iman, ipage)], np.uint64), bbox=None, terms=None)
+        chk = dict(emb=ce, key=np.array([key(m, p) for m, p in zip(cman, cpage)], np.uint64), bbox=None, terms=None)
+        o = oracle.evaluate(img, chk, schema_mask=1, candidates="same_page", kmax=10, cutoff=100)
+        got = oracle.metrics_from_ranks(o["pair_rank"][0], o["pair_sim"])
+        assert len(ev.get_image_text_pairs(s)) == got["num_pairs"], seed
+        assert want[0] == got["top_k"] and want[1] == got["mrr"] and want[2] == got["avg_similarity"], seed
