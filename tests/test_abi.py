@@ -46,3 +46,14 @@ def test_product_does_not_import_the_oracle():
     for f in list(pkg_dir.rglob("*.py")) + list(pkg_dir.rglob("*.cu")) + list(pkg_dir.rglob("*.cuh")):
         text = f.read_text()
         assert "oracle" not in text.replace("oracle/mmalign_oracle.c: orc_dot", ""), f
+
+
+def test_integration_md_stub_matches_the_abi(pkg):
+    """The ctypes structs shown to maintainers in INTEGRATION.md are the real ones (same fields, same size)."""
+    text = (ROOT / "INTEGRATION.md").read_text()
+    ns = {"C": C}
+    exec(text[text.index("class Params(C.Structure):"):text.index("def check(ctx, rc):")], ns)
+    for name in ("Params", "Out"):
+        doc, real = ns[name], getattr(pkg._native, name)
+        assert [f[0] for f in doc._fields_] == [f[0] for f in real._fields_], name
+        assert C.sizeof(doc) == C.sizeof(real), name
