@@ -34,12 +34,27 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 PKG = "multimodal-alignment-of-noisy-image-text-pairs-using-weak-supervision_b200"
-SCHEMAS = ["vanilla_clip", "clip_lexical", "clip_positional", "clip_combined"]
-K_VALUES = (1, 5, 10, 20)
+ALL4 = ["vanilla_clip", "clip_lexical", "clip_positional", "clip_combined"]
 MRR_CUTOFF = 100
 WEAK = (0.3, 0.2)
 T_TERMS = 512
-METRIC = "top-10 retrieval queries/s at 1M x 1M, D=512 (all four schemas, K<=20 + MRR@100)"
+METRIC5 = "top-10 retrieval queries/s at 1M x 1M, D=512 (all four schemas, K<=20 + MRR@100)"
+VERIFY_ROWS = 64
+
+# BASELINE.json `configs`, in order.  Config 5 is the one `metric` is quoted on (the default); config 1 is the
+# reference's own CPU-runnable case: the same-page candidates of its SQL join, its K values, no ranking weights.
+CONFIGS = {
+    1: dict(N=1_000, M=5_000, D=512, schemas=["vanilla_clip"], candidates="same_page", k_values=(1, 5, 10), weak=(0.0, 0.0),
+            name="ViT-B-32 (D=512) vanilla_clip scoring, 1k images x 5k text chunks, same-page candidates (the reference's SQL join)"),
+    2: dict(N=100_000, M=500_000, D=512, schemas=["clip_combined"], candidates="all", k_values=(1, 5, 10, 20), weak=WEAK,
+            name="ViT-B-32 clip_combined (cos + lexical + positional), 100k x 500k"),
+    3: dict(N=1_000_000, M=1_000_000, D=768, schemas=["clip_lexical"], candidates="all", k_values=(1, 5, 10, 20), weak=WEAK,
+            name="ViT-L-14 (D=768) clip_lexical, 1M x 1M"),
+    4: dict(N=2_000_000, M=4_000_000, D=1024, schemas=["clip_positional"], candidates="all", k_values=(1, 5, 10, 20), weak=WEAK,
+            name="ViT-H-14 (D=1024) clip_positional, 2M images x 4M chunks"),
+    5: dict(N=1_000_000, M=1_000_000, D=512, schemas=ALL4, candidates="all", k_values=(1, 5, 10, 20), weak=WEAK,
+            name="all four schemas in one pass, K in {1,5,10,20} + MRR, 1M x 1M at D=512"),
+}
 
 
 def parse():
@@ -48,19 +63,42 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--N", type=int, default=1_000_000)
-    ap.add_argument("--M", type=int, default=1_000_000)
-    ap.add_argument("--D", type=int, default=512)
+    ap.add_argument("--config", type=int, default=5, choices=sorted(CONFIGS), help="BASELINE.json config (default 5, the metric's)")
+    ap.add_argument("--schemas", default=None, help="comma-separated schema names (default: the config's)")
+    ap.add_argument("--N", type=int, default=None, help="override the config's image count (the line is then labelled custom)")
+    ap.add_argument("--M", type=int, default=None)
+    ap.add_argument("--D", type=int, default=None)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--kprime", type=int, default=0)
+    ap.add_argument("--pipeline-rows", type=int, default=0, help="query rows per pipeline slab of mmalign_run (0 = auto)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "alltoall", "allgather", "none"],
                     help="multi-GPU: none = contraction and rescoring both sharded by query rows (no list exchange); "
                          "alltoall = contraction sharded by chunk columns, rescoring by query rows; auto (default) = none "
                          "when every rank's query slab fills the GPU, else alltoall; allgather = fully sharded variant "
                          "(distributed.AllGatherScorer)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    cfg = CONFIGS[a.config]
+    a.custom = any(getattr(a, k) is not None and getattr(a, k) != cfg[k] for k in ("N", "M", "D")) or a.schemas is not None
+    for k in ("N", "M", "D"):
+        if getattr(a, k) is None:
+            setattr(a, k, cfg[k])
+    a.schema_list = [x.strip() for x in a.schemas.split(",")] if a.schemas else list(cfg["schemas"])
+    for x in a.schema_list:
+        if x not in ALL4:
+            ap.error(f"unknown schema {x!r}")
+    a.schema_list = [x for x in ALL4 if x in a.schema_list]
+    a.candidates, a.k_values, a.weak, a.cfg_name = cfg["candidates"], tuple(cfg["k_values"]), tuple(cfg["weak"]), cfg["name"]
+    return a
+
+
+def metric_name(a):
+    if a.config == 5 and not a.custom:
+        return METRIC5
+    return (f"top-10 retrieval queries/s at {a.N} x {a.M}, D={a.D} ({'+'.join(a.schema_list)}, K<={max(a.k_values)} + "
+            f"MRR@{MRR_CUTOFF}, candidates={a.candidates})")
 
 
 def peaks():
@@ -151,14 +189,49 @@ def clocks_rejected(clocks) -> bool:
 
 
 # ------------------------------------------------------------------------------------------- reference arm
-def cpu_sample(img_h, chk_h, rows, budget_note):
+def blas_threads_all():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is entitled to every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def schema_ids(args):
+    return tuple(ALL4.index(x) for x in args.schema_list)
+
+
+def cpu_sample(args, img_h, chk_h, rows):
     """The CPU port on `rows` query rows against the full chunk table; returns (queries/s, seconds)."""
-    from oracle import numpy_port
+    lam = (args.weak[0], args.weak[1], args.weak[0] + args.weak[1])
     t0 = time.perf_counter()
-    numpy_port.evaluate(img_h, chk_h, T=T_TERMS, schemas=(0, 1, 2, 3), lam=(WEAK[0], WEAK[1], WEAK[0] + WEAK[1]),
-                        kmax=max(K_VALUES), cutoff=MRR_CUTOFF, rows=rows)
+    if args.candidates == "all":
+        from oracle import numpy_port
+        numpy_port.evaluate(img_h, chk_h, T=T_TERMS, schemas=schema_ids(args), lam=lam, kmax=max(args.k_values),
+                            cutoff=MRR_CUTOFF, rows=rows)
+    else:  # the reference's same-page join: the C restatement (pthreads over the rows)
+        from oracle import oracle
+        sub = {k: (v[rows] if v is not None else None) for k, v in img_h.items()}
+        oracle.evaluate(sub, chk_h, T=T_TERMS, schema_mask=sum(1 << i for i in schema_ids(args)), candidates="same_page",
+                        lam=lam, kmax=max(args.k_values), cutoff=MRR_CUTOFF)
     dt = time.perf_counter() - t0
     return len(rows) / dt, dt
+
+
+def cpu_kind(args):
+    if args.candidates == "all":
+        from oracle import numpy_port
+        return (f"oracle/numpy_port.py: numpy sgemm [{numpy_port.blas_info()}] in column slabs, fp32 argpartition on a thread "
+                "pool, fp64 exact scores of the kept candidates, lexsort")
+    return "oracle/mmalign_oracle.c: the C restatement of the reference's same-page SQL ranking, pthreads over the rows"
+
+
+def reference_as_written():
+    """Wall time of the UNMODIFIED reference metric functions at config 1, recorded in the build container (the
+    reference tree does not travel to the GPU box): tools/time_reference_config1.py -> profiles/bench/."""
+    f = ROOT / "profiles" / "bench" / "r2_reference_as_written_config1.json"
+    return json.loads(f.read_text()) if f.exists() else None
 
 
 def host_corpus(args, synthetic, device):
@@ -178,25 +251,29 @@ def host_corpus(args, synthetic, device):
     return img, chk
 
 
+def resolve_exchange(args, distributed):
+    if args.exchange == "auto":
+        args.exchange = "none" if distributed.slab_size(args.N, args.gpus) >= 148 * 128 else "alltoall"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.exchange == "auto":  # the same config line as the GPU arm prints for this --gpus
-        distributed = importlib.import_module(PKG + ".distributed")
-        args.exchange = "none" if distributed.slab_size(args.N, args.gpus) >= 148 * 128 else "alltoall"
+    blas_threads_all()
+    distributed = importlib.import_module(PKG + ".distributed")
+    resolve_exchange(args, distributed)  # the same config line as the GPU arm prints for this --gpus
     import torch
     synthetic = importlib.import_module(PKG + ".synthetic")
-    from oracle import numpy_port
     dev = "cuda" if torch.cuda.is_available() else None
     img, chk = host_corpus(args, synthetic, dev)
     cores = os.cpu_count()
-    rows_n = args.cpu_rows or 256
+    rows_n = args.cpu_rows or min(256, args.N)
     rng = np.random.default_rng(0)
     times = []
     for it in range(args.warmup + args.steps):
         rows = np.sort(rng.choice(args.N, size=min(rows_n, args.N), replace=False))
-        qps, dt = cpu_sample(img, chk, rows, "")
+        qps, dt = cpu_sample(args, img, chk, rows)
         if it == 0 and not args.cpu_rows:  # size the sample so that one step is ~5 s
             rows_n = int(max(64, min(args.N, rows_n * 5.0 / max(dt, 1e-3))))
         if it >= args.warmup:
@@ -205,14 +282,15 @@ def run_reference(args):
     t = sum(d for _, d in times)
     value = q / t
     line = {
-        "impl": "reference", "metric": METRIC,
+        "impl": "reference", "metric": metric_name(args),
         "value": value, "unit": "queries/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * t / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port",
-                         "sample": f"{times[-1][0]} query rows per step x all {args.M} chunks, D={args.D}, 4 schemas, "
-                                   f"K<=20 + MRR@100; numpy sgemm ({numpy_port.blas_info()}) + argpartition/lexsort"},
+                         "sample": f"{times[-1][0]} query rows per step x all {args.M} chunks, D={args.D}, "
+                                   f"{len(args.schema_list)} schema(s), K<={max(args.k_values)} + MRR@{MRR_CUTOFF}; {cpu_kind(args)}",
+                         "reference_as_written": reference_as_written()},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -224,18 +302,77 @@ def workload(args, G):
         how = "one GPU"
     elif ex == "allgather":
         how = f"chunks sharded over {G} GPUs, images replicated (fully sharded variant)"
-    else:
+    elif ex == "alltoall":
         how = (f"each of {G} GPUs ingests 1/{G} of the images and of the chunks (an NVLink all-gather inside the step replicates "
-               "them); " + ("contraction sharded by chunk columns, exact rescoring by query rows" if ex == "alltoall"
-                            else "contraction and exact rescoring sharded by query rows"))
-    return {"workload": f"BASELINE config 5: {args.N} images x {args.M} chunks, D={args.D}, all four schemas in one pass, "
-                        f"K in {list(K_VALUES)} + MRR@{MRR_CUTOFF}, candidates=all, weak_weight={WEAK}",
-            "N": args.N, "M": args.M, "D": args.D, "schemas": 4, "k_values": list(K_VALUES), "mrr_cutoff": MRR_CUTOFF,
-            "sharding": how,
-            "l2": "inputs (2 x %.1f GB bf16 operands) are far larger than the 126 MB L2" % (args.N * args.D * 2 / 1e9)}
+               "them); contraction sharded by chunk columns, exact rescoring by query rows")
+    else:
+        how = (f"each of {G} GPUs ingests 1/{G} of the images and of the chunks and prepares its chunk shard; the prepared operands "
+               "are all-gathered over NVLink inside the step (fp32 master rows on a side stream); contraction and exact "
+               "rescoring sharded by query rows")
+    label = f"BASELINE config {args.config}: {args.cfg_name}" if not args.custom else \
+        f"custom shape (NOT a BASELINE config; nearest: config {args.config})"
+    return {"workload": f"{label} -- {args.N} images x {args.M} chunks, D={args.D}, schemas={args.schema_list}, "
+                        f"K in {list(args.k_values)} + MRR@{MRR_CUTOFF}, candidates={args.candidates}, weak_weight={tuple(args.weak)}",
+            "baseline_config": None if args.custom else args.config,
+            "N": args.N, "M": args.M, "D": args.D, "schemas": args.schema_list, "k_values": list(args.k_values),
+            "mrr_cutoff": MRR_CUTOFF, "candidates": args.candidates, "sharding": how,
+            "l2": "inputs (%.2f + %.2f GB of bf16 operands, %.2f + %.2f GB of fp32 rows) against a 126 MB L2; nothing is flushed "
+                  "between steps because nothing of that size stays" % (args.N * args.D * 2 / 1e9, args.M * args.D * 2 / 1e9,
+                                                                         args.N * args.D * 4 / 1e9, args.M * args.D * 4 / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------- our arm
+def verify_rows(args, eng, sharded, img, chk, res, world, rank, dev):
+    """After the timed region: VERIFY_ROWS sampled query rows of the timed result against the CPU oracle (bit-exact:
+    top-K indices and scores, true-pair ranks and similarities).  Rank 0 checks rows of its own slab."""
+    import torch
+    from oracle import oracle
+    to_np = lambda t: None if t is None else (t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t))
+    n_local = int(res["topk_idx"].shape[1])
+    if n_local == 0:
+        return {"rows": 0, "ok": True}
+    rng = np.random.default_rng(12345)
+    rows = np.sort(rng.choice(n_local, size=min(VERIFY_ROWS, n_local), replace=False))
+    if world > 1 and getattr(sharded, "mode", "") == "rows":     # the engine holds the slab; the chunk table is gathered
+        full = {f: sharded._full.get(("chk", f)) for f in ("emb", "key", "bbox", "terms")}
+        chk_h = {f: (to_np(v[:args.M]) if v is not None else None) for f, v in full.items()}
+        img_rows = rows                                          # positions within this rank's slab (img is the slab)
+    elif world > 1:
+        full = {f: sharded._full.get(("chk", f)) for f in ("emb", "key", "bbox", "terms")}
+        chk_h = {f: (to_np(v[:args.M]) if v is not None else None) for f, v in full.items()}
+        img_rows = rows
+    else:
+        chk_h = {f: to_np(chk[f]) for f in ("emb", "key", "bbox", "terms")}
+        img_rows = rows
+    ridx = torch.as_tensor(img_rows, device=img["emb"].device) if hasattr(img["emb"], "device") else img_rows
+    sub = {f: (to_np(img[f][ridx]) if img.get(f) is not None else None) for f in ("emb", "key", "bbox", "terms")}
+    for d in (sub, chk_h):
+        d["key"] = d["key"].view(np.uint64)
+        if d["terms"] is not None:
+            d["terms"] = d["terms"].view(np.uint64)
+    t0 = time.perf_counter()
+    o = oracle.evaluate(sub, chk_h, T=T_TERMS, schema_mask=sum(1 << ALL4.index(x) for x in args.schema_list),
+                        candidates=args.candidates, lam=(args.weak[0], args.weak[1], args.weak[0] + args.weak[1]),
+                        kmax=max(args.k_values), cutoff=MRR_CUTOFF)
+    dt = time.perf_counter() - t0
+    tk_i, tk_s = to_np(res["topk_idx"][:, rows]), to_np(res["topk_score"][:, rows])
+    off = to_np(res["pair_offsets_local"])
+    sel = np.concatenate([np.arange(off[r], off[r + 1]) for r in rows]) if len(rows) else np.zeros(0, np.int64)
+    pr, ps = to_np(res["pair_rank"])[:, sel], to_np(res["pair_sim"])[sel]
+    bad = []
+    if not np.array_equal(tk_i, o["topk_idx"]):
+        bad.append("topk_idx")
+    if not np.array_equal(tk_s, o["topk_score"]):
+        bad.append("topk_score")
+    if not np.array_equal(pr, o["pair_rank"]):
+        bad.append("pair_rank")
+    if not np.array_equal(ps, o["pair_sim"]):
+        bad.append("pair_sim")
+    return {"rows": int(len(rows)), "pairs": int(len(sel)), "ok": not bad, "mismatch": bad, "oracle_seconds": round(dt, 1),
+            "checked": "top-K indices and scores, true-pair ranks and similarities of the last timed step, bit for bit "
+                       "against oracle/mmalign_oracle.c on the same rows (rank 0's slab)"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -253,15 +390,16 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     P = peaks()
     N, M, D = args.N, args.M, args.D
+    args.gpus = world
     r0, r1 = distributed.shard_range(M, world, rank)
     eng = pkg.AlignmentEngine(local)
-    run_kw = dict(schemas=SCHEMAS, k_values=K_VALUES, mrr_cutoff=MRR_CUTOFF, weak_weight=WEAK, kprime=args.kprime)
+    run_kw = dict(schemas=args.schema_list, k_values=args.k_values, mrr_cutoff=MRR_CUTOFF, weak_weight=args.weak,
+                  kprime=args.kprime, candidates=args.candidates)
     phase_ms, step_ms = {}, {}
-    if args.exchange == "auto":
-        args.exchange = "none" if distributed.slab_size(N, world) >= 148 * 128 else "alltoall"
+    resolve_exchange(args, distributed)
+    i0, i1 = distributed.slab_range(N, world, rank)
     if args.exchange in ("alltoall", "none") or world == 1:
         # every rank ingests its slab of the images and its shard of the chunks
-        i0, i1 = distributed.slab_range(N, world, rank)
         img, chk, meta = synthetic.make_torch(N, M, D, T=T_TERMS, device=dev, row0=r0, rows=r1 - r0, img_row0=i0,
                                               img_rows=i1 - i0)
         sharded = distributed.ShardedScorer(eng, world, rank, dev, contraction="rows" if args.exchange == "none" else "columns")
@@ -270,7 +408,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             sharded.load(im, ck, N=N, M=M, n_terms=T_TERMS)
             t2 = time.perf_counter()
-            out = sharded.run(host_outputs=host_out, **run_kw)
+            out = sharded.run(host_outputs=host_out, pipeline_rows=args.pipeline_rows, **run_kw)
             t3 = time.perf_counter()
             step_ms.setdefault("host" if host_out else "device", []).append(round(1e3 * (t3 - t0), 1))
             phase_ms["host" if host_out else "device"] = dict(load=1e3 * (t2 - t0), run=1e3 * (t3 - t2),
@@ -321,15 +459,17 @@ def run_ours(args):
     for _ in range(args.warmup):
         res = step(img, chk, False)
     fused_us, resc_us, scan_us, launches = [], [], [], []
+    fused_path = args.candidates == "all"
 
     def dev_step():
         r = step(img, chk, False)
         fused_us.append(r["stats"]["fused_us"]); resc_us.append(r["stats"]["rescore_us"])
         scan_us.append(r["stats"]["exact_scan_us"])
-        # kernels of the library per step (profiles/r1c_launches_summary.txt): K0 + error max of both tables (4), pair index
-        # (iota, 10 CUB radix-sort/scan launches, page ranges, offsets scan: 14), then what mmalign_run counts itself
-        # (fused, rescore, prefilter, scan, 2 metric kernels), + the list export when sharded
-        launches.append(18 + r["stats"]["kernel_launches"] - 2 + (1 if world > 1 else 0))
+        # kernels of the library per step: K0 + error max of the chunk table (2; the image K0 launches are counted by
+        # mmalign_run, one per slab), pair index (iota, 10 CUB radix-sort/scan launches, page ranges, offsets scan: 14),
+        # then what mmalign_run counts itself (K0 per slab, fused, rescore, prefilter, scan, 2 metric kernels), + the
+        # list export when the contraction is sharded by columns
+        launches.append(16 + r["stats"]["kernel_launches"] + (1 if world > 1 and args.exchange == "alltoall" else 0))
         return r
     t_begin = time.time()
     ms, res = timed(dev_step, args.steps)
@@ -354,6 +494,17 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = N / (ms_per_step / 1000.0)
 
+    # ---- the timed result, checked row by row against the oracle (rank 0, its slab)
+    verified = None
+    if rank == 0 and not args.no_verify and args.exchange != "allgather":
+        off, _ = eng.pairs_device()
+        q0 = res.get("topk_row0", 0) if (world > 1 and sharded.mode != "rows") else 0
+        res["pair_offsets_local"] = (off[q0:q0 + res["topk_idx"].shape[1] + 1] - off[q0]).cpu()
+        vimg = img
+        verified = verify_rows(args, eng, sharded, vimg, chk, res, world, rank, dev)
+    if world > 1:
+        dist.barrier()
+
     # ---- end-to-end arm: host (pinned) inputs, host outputs
     e2e = None
     if not args.no_e2e:
@@ -367,7 +518,9 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(io)  # bytes of the whole job: every rank copies its own shard in and its own results out
         e2e = {"value": N / (ms_h / args.steps / 1000.0), "unit": "queries/s", "h2d_bytes_per_step": int(io[0].item()),
-               "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_h / args.steps}
+               "d2h_bytes_per_step": int(io[1].item()), "ms_per_step": ms_h / args.steps,
+               "pipeline_slabs": res_h["stats"].get("slabs"),
+               "same_result_as_device_arm": bool(np.array_equal(res_h["hits"], res["hits"]) and res_h["num_pairs"] == res["num_pairs"])}
         del img_h, chk_h
 
     if os.environ.get("MMALIGN_BENCH_RANKS"):  # every rank's view of its last step
@@ -376,61 +529,75 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- roofline of the dominant kernel (K1), timed with CUDA events inside the library
-    t_fused = float(np.mean(fused_us)) * 1e-6
-    flops_launch = 2.0 * N * (r1 - r0) * D  # algorithmic: 2*M_local*D per query x N queries per launch
-    if world > 1 and args.exchange == "none":
-        flops_launch = 2.0 * (i1 - i0) * M * D  # this rank's query slab against every chunk
-    achieved = flops_launch / t_fused / 1e12 if t_fused > 0 else 0.0
-    traffic = None  # DRAM bytes of one launch, from the committed ncu --set full capture of this very configuration
-    tf = ROOT / "profiles" / "r1c_traffic.json"
-    if tf.exists():
-        t = json.loads(tf.read_text())["fused_score_topk_kernel"]
-        if (t["N"], t["M"], t["D"]) == (N, r1 - r0, D):
-            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
-    roof = {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": P["bf16_sustained"],
-            "unit": "TFLOP/s", "frac": achieved / P["bf16_sustained"], "traffic": traffic,
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r1c_fused_score_topk_kernel.txt); "
-                            "the kernel is tensor-bound: 2*N*M*D flop against (N+M)*D*2 algorithmic operand bytes",
-            "peak_source": f"{P['src']} bf16_tflops_sustained (kernel runs ~{t_fused * 1e3:.0f} ms inside the step)",
-            "frac_of_burst_peak": achieved / P["bf16"], "ms_per_launch": t_fused * 1e3,
-            "share_of_step": t_fused / (ms_per_step / 1000.0),
-            "other_phases_ms": {"rescore_kernel": float(np.mean(resc_us)) / 1e3,
-                                "exact_scan_kernel": float(np.mean(scan_us)) / 1e3}}
+    # ---- roofline of the dominant kernel, timed with CUDA events inside the library
+    other = {"rescore_kernel": float(np.mean(resc_us)) / 1e3, "exact_scan_kernel": float(np.mean(scan_us)) / 1e3}
+    if fused_path:
+        t_fused = float(np.mean(fused_us)) * 1e-6
+        flops_launch = 2.0 * N * (r1 - r0) * D  # algorithmic: 2*M_local*D per query x N queries
+        if world > 1 and args.exchange == "none":
+            flops_launch = 2.0 * (i1 - i0) * M * D  # this rank's query slab against every chunk
+        achieved = flops_launch / t_fused / 1e12 if t_fused > 0 else 0.0
+        traffic = None  # DRAM bytes of the kernel per step, from the committed ncu --set full capture of this configuration
+        tf = ROOT / "profiles" / "r2_traffic.json"
+        if tf.exists():
+            t = json.loads(tf.read_text()).get("fused_score_topk_kernel", {})
+            if (t.get("N"), t.get("M"), t.get("D")) == (N, r1 - r0, D):
+                traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+        n_fused = max(1, int(res["stats"]["fused_launches"]))
+        roof = {"bound": "tensor", "kernel": "fused_score_topk_kernel", "achieved": achieved, "peak": P["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": achieved / P["bf16_sustained"], "traffic": traffic,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the kernel over one step (profiles/); "
+                                "the kernel is tensor-bound: 2*N*M*D flop against (N+M)*D*2 algorithmic operand bytes",
+                "peak_source": f"{P['src']} bf16_tflops_sustained (the kernel runs {t_fused * 1e3:.0f} ms of every step)",
+                "frac_of_burst_peak": achieved / P["bf16"], "launches_per_step": n_fused,
+                "ms_per_launch": t_fused * 1e3 / n_fused, "ms_per_step": t_fused * 1e3,
+                "share_of_step": t_fused / (ms_per_step / 1000.0), "other_phases_ms": other}
+    else:  # same-page candidates (config 1): the exact rescoring kernel alone, HBM row gathers
+        t_resc = max(float(np.mean(resc_us)) * 1e-6, 1e-9)
+        cand = res["stats"]["candidates_rescored"]
+        bytes_launch = (cand + N) * D * 4.0
+        roof = {"bound": "hbm", "kernel": "rescore_kernel", "achieved": bytes_launch / t_resc / 1e9, "peak": P["hbm"],
+                "unit": "GB/s", "frac": bytes_launch / t_resc / 1e9 / P["hbm"], "traffic": None,
+                "peak_source": f"{P['src']} hbm_gbs", "ms_per_launch": t_resc * 1e3,
+                "note": f"{cand} same-page row gathers + {N} query rows of 4*D bytes; at this size the step is launch latency, "
+                        "not bandwidth", "share_of_step": t_resc / (ms_per_step / 1000.0), "other_phases_ms": other}
     m = res["metrics"]
     line = {
-        "metric": METRIC,
+        "metric": metric_name(args),
         "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic", "config": workload(args, world), "clocks": clocks,
-        "e2e": e2e, "gpu_launches": int(np.sum(launches)), "roofline": roof,
-        "quality": {"top1_vanilla": m["top_k"][0][0], "top10_vanilla": m["top_k"][0][2], "mrr_vanilla": m["mrr"][0],
-                    "mrr_combined": m["mrr"][-1], "num_pairs": m["num_pairs"],
+        "e2e": e2e, "gpu_launches": int(np.sum(launches)), "roofline": roof, "verified_rows": verified,
+        "quality": {"top1": m["top_k"][0][0], "top10": m["top_k"][0][min(2, len(args.k_values) - 1)], "mrr_first_schema": m["mrr"][0],
+                    "mrr_last_schema": m["mrr"][-1], "num_pairs": m["num_pairs"],
                     "rows_rescanned": res["stats"]["rows_rescanned"], "kprime": res["stats"]["kprime"],
+                    "eps_violations": res["stats"].get("eps_violations"),
                     "candidates_rescored_per_row": res["stats"]["candidates_rescored"] / max(N, 1)},
     }
     if world == 1 and not args.no_cpu_baseline:
+        blas_threads_all()
         to_np = lambda d: {k: (v.cpu().numpy() if v is not None else None) for k, v in d.items()}
         ih, ch = to_np(img), to_np(chk)
         for d_ in (ih, ch):
             d_["key"] = d_["key"].view(np.uint64)
             if d_["terms"] is not None:
                 d_["terms"] = d_["terms"].view(np.uint64)
-        from oracle import numpy_port
         rng = np.random.default_rng(0)
         rows = np.sort(rng.choice(N, size=min(128, N), replace=False))
-        qps, dt = cpu_sample(ih, ch, rows, "")
+        qps, dt = cpu_sample(args, ih, ch, rows)
         n2 = int(max(64, min(N, 128 * 12.0 / max(dt, 1e-3))))
         rows = np.sort(rng.choice(N, size=n2, replace=False))
-        qps, dt = cpu_sample(ih, ch, rows, "")
+        qps, dt = cpu_sample(args, ih, ch, rows)
         line["cpu_baseline"] = {"value": qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{n2} query rows x all {M} chunks in {dt:.1f} s (oracle/numpy_port.py: numpy sgemm "
-                                          f"[{numpy_port.blas_info()}] + argpartition/lexsort, same workload)"}
+                                "sample": f"{n2} query rows x all {M} chunks in {dt:.1f} s ({cpu_kind(args)}; same workload)",
+                                "reference_as_written": reference_as_written()}
     print("wall ms of every step (warm-up included):", json.dumps(step_ms), file=sys.stderr)
     print("phase wall times of the last step (ms; *_us from CUDA events):", json.dumps(phase_ms), file=sys.stderr)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if verified is not None and not verified["ok"]:
+        raise SystemExit(f"verified_rows FAILED: {verified['mismatch']}")
 
 
 if __name__ == "__main__":

@@ -13,9 +13,20 @@
  *   - all array arguments may be HOST or DEVICE pointers (detected with
  *     cudaPointerGetAttributes).  Host inputs are uploaded into buffers owned by
  *     the context; device inputs are BORROWED and must stay valid until the next
- *     set_* call or mmalign_destroy.  Host outputs are filled with a
- *     device-to-host copy before the call returns.
- *   - one context per (process, device); calls are ordered on the stream passed
+ *     set_* call or mmalign_destroy.  Host outputs are filled with
+ *     device-to-host copies before the call returns.
+ *   - set_images / set_chunks are ASYNCHRONOUS: they queue their uploads (a copy
+ *     stream of the context) and the operand preparation behind them and return.
+ *     Pageable host inputs have been consumed when the call returns; PAGE-LOCKED
+ *     host inputs (cudaHostAlloc / cudaHostRegister) are borrowed like device
+ *     inputs until the next call that waits for them: mmalign_run and every other
+ *     entry point that reads the tables, or mmalign_sync.  Device inputs must be
+ *     complete on the legacy default stream when set_* is called.
+ *   - mmalign_run overlaps what it can: with host embeddings and/or host outputs it
+ *     cuts the query rows into slabs, so that the upload of slab s+1 and the
+ *     download of slab s-1's results run beside the kernels of slab s (copy
+ *     engines, separate streams); the results are the same bytes either way.
+ *   - one context per (process, device); kernels are ordered on the stream passed
  *     to mmalign_run (a cudaStream_t, NULL = default stream); not thread-safe per
  *     context.
  *   - there is NO CPU fallback: a device that is not sm_100 is an error.
@@ -32,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MMALIGN_ABI_VERSION 2
+#define MMALIGN_ABI_VERSION 3
 #define MMALIGN_NULL_KEY 0xFFFFFFFFFFFFFFFFull
 
 enum {
@@ -85,6 +96,8 @@ typedef struct {
     int64_t shard_cols;    /*   shard_cols) of the table given to set_chunks; 0, 0 = the whole table          */
     int64_t slab_row0;     /* mmalign_rescore_slab: image rows [slab_row0, slab_row0 + slab_rows) are ranked;  */
     int64_t slab_rows;     /*   0, 0 = every image                                                             */
+    int32_t pipeline_rows; /* mmalign_run: query rows per pipeline slab; 0 = auto (4 waves of 128-row blocks when    */
+    int32_t reserved;      /*   inputs or outputs live on the host, else one slab), -1 = never cut; reserved = 0     */
 } mmalign_params;
 
 /* Any pointer may be NULL (output not wanted).  S = popcount(schema_mask),
@@ -102,10 +115,12 @@ typedef struct {
     double *pair_score;   /* [S][P] ranking score of each true pair (multi-GPU rank step)   */
     int64_t *deep_idx;    /* [S][N][max(Kmax, mrr_cutoff)] lists to the full exact depth    */
     double *deep_score;   /*        (multi-GPU rank step; see mmalign_count_beating)        */
-    int64_t *stats;       /* [8] 0: rows rescanned exactly, 1: candidates rescored,
-                             2: fused-kernel launches, 3: kernels launched in total,
+    int64_t *stats;       /* [16] 0: rows rescanned exactly, 1: candidates rescored,
+                             2: fused-kernel launches, 3: kernels launched by the call,
                              4: K' used, 5/6/7: microseconds (CUDA events) of the fused
-                             kernel / the rescoring kernel / the exact rescan */
+                             kernel / the rescoring kernel / the exact rescan, 8: rows whose
+                             re-scored candidates broke the certificate's error bound (they were
+                             rescanned exactly), 9: pipeline slabs of the run, 10..15: 0 */
 } mmalign_out;
 
 int mmalign_abi_version(void);
@@ -131,6 +146,10 @@ int mmalign_set_images(mmalign_ctx *ctx, const float *emb, const uint64_t *page_
 int mmalign_set_chunks(mmalign_ctx *ctx, const float *emb, const uint64_t *page_key,
                        const double *bbox, const uint64_t *terms, int64_t m_local, int32_t D,
                        int32_t term_words, int64_t n_terms, int64_t col_offset);
+
+/* waits for every upload and preparation queued by set_images / set_chunks (after it, page-locked host
+ * inputs may be reused or freed) */
+int mmalign_sync(mmalign_ctx *ctx);
 
 /* replaces get_image_text_pairs(): src/evaluate_alignments.py:48-69.  Pairs are
  * ordered by (image index, chunk index).  pair_offsets [N+1], pair_chunk [P]
@@ -183,6 +202,27 @@ int mmalign_rescan_rows(mmalign_ctx *ctx, const mmalign_params *params, const in
  *                            -> all-reduce(sum) of hits / rr_sum / sim_sum / num_pairs
  * Device pointers for keys / count / tau. */
 int mmalign_list_stride(mmalign_ctx *ctx, int32_t *stride);
+
+/* Sharded run, query-row layout (distributed.py::ShardedScorer, contraction="rows"): rank g ranks its own
+ * query slab against the WHOLE chunk table.  Each rank prepares its own chunk shard and the prepared operands
+ * travel, so that the contraction can start after the small exchange while the fp32 master rows (needed by the
+ * exact rescoring only) are still in flight:
+ *   1. mmalign_prep_rows           K0 (src/insert_clip_embeddings.py:113-115 normalisation, bf16 rounding, sum of
+ *                                  squares, rounding-error norm) of this rank's shard into its slot of the gathered
+ *                                  buffers; device pointers     -> all-gather of bf16 / norm2 / err / page keys
+ *   2. mmalign_set_chunks_prepared the gathered table: fp32 rows, keys, boxes, term sets and the prepared operands
+ *                                  (all DEVICE pointers, borrowed)
+ *   3. mmalign_rescore_after       the event (cudaEvent_t) after which the fp32 rows, boxes and term sets are
+ *                                  complete -- the all-gather of those runs on a side stream; the next mmalign_run
+ *                                  makes its exact rescoring (not the contraction) wait for it
+ *   4. mmalign_set_images (own slab) + mmalign_run                -> all-reduce(sum) of the metric sums */
+int mmalign_prep_rows(mmalign_ctx *ctx, const float *emb, int64_t n, int32_t D, void *bf16_out, float *norm2_out,
+                      float *err_out, void *stream);
+int mmalign_set_chunks_prepared(mmalign_ctx *ctx, const float *emb, const uint64_t *page_key, const double *bbox,
+                                const uint64_t *terms, const void *bf16, const float *norm2, const float *err,
+                                int64_t m, int32_t D, int32_t term_words, int64_t n_terms, int64_t col_offset,
+                                void *stream);
+int mmalign_rescore_after(mmalign_ctx *ctx, void *event);
 int mmalign_export_lists(mmalign_ctx *ctx, int32_t n_dest, int64_t slab_rows, int32_t stride,
                          uint64_t *keys, int32_t *count, float *tau, void *stream);
 int mmalign_rescore_slab(mmalign_ctx *ctx, const mmalign_params *params, const uint64_t *keys,
@@ -232,6 +272,9 @@ int mmalign_term_bitsets(mmalign_ctx *ctx, const uint8_t *text, const int64_t *t
 /* validation hook: the raw bf16 x bf16 -> fp32 score tile matrix of the fused
  * kernel, out [N][m_local] fp32 (small sizes only). */
 int mmalign_debug_scores(mmalign_ctx *ctx, float *out, void *stream);
+/* validation hook: the bf16 operands K0 prepared (L2-normalised rows, rounded to nearest even), [N][D] and
+ * [m_local][D] 16-bit values; either may be NULL; host or device pointers. */
+int mmalign_debug_operands(mmalign_ctx *ctx, void *img_bf16, void *chk_bf16, void *stream);
 
 #ifdef __cplusplus
 }

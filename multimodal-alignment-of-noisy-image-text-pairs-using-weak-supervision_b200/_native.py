@@ -25,7 +25,7 @@ class Params(C.Structure):
                 ("lam_pos", C.c_double), ("lam_comb", C.c_double), ("path", C.c_int32),
                 ("kprime", C.c_int32), ("n_ranks", C.c_int32), ("eps_scale", C.c_float),
                 ("shard_col0", C.c_int64), ("shard_cols", C.c_int64), ("slab_row0", C.c_int64),
-                ("slab_rows", C.c_int64)]
+                ("slab_rows", C.c_int64), ("pipeline_rows", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Out(C.Structure):
@@ -40,8 +40,9 @@ EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_
            "mmalign_run", "mmalign_alignments", "mmalign_merge_topk", "mmalign_count_beating",
            "mmalign_reduce_metrics", "mmalign_debug_scores", "mmalign_fused_pass", "mmalign_chunk_err_max",
            "mmalign_rescore_pass", "mmalign_rescan_rows", "mmalign_list_stride", "mmalign_export_lists",
-           "mmalign_rescore_slab", "mmalign_num_pairs_range", "mmalign_term_bitsets"]
-ABI_VERSION = 2
+           "mmalign_rescore_slab", "mmalign_num_pairs_range", "mmalign_term_bitsets", "mmalign_sync",
+           "mmalign_prep_rows", "mmalign_set_chunks_prepared", "mmalign_rescore_after", "mmalign_debug_operands"]
+ABI_VERSION = 3
 
 _lib = None
 
@@ -96,6 +97,11 @@ def load():
     L.mmalign_rescore_slab.argtypes = [vp, C.POINTER(Params), vp, vp, vp, i32, i64, i32, C.POINTER(Out), vp]
     L.mmalign_num_pairs_range.argtypes = [vp, i64, i64, C.POINTER(i64)]
     L.mmalign_term_bitsets.argtypes = [vp, vp, vp, i64, vp, vp, i32, i32, vp, vp]
+    L.mmalign_sync.argtypes = [vp]
+    L.mmalign_prep_rows.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp]
+    L.mmalign_set_chunks_prepared.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i64, i64, vp]
+    L.mmalign_rescore_after.argtypes = [vp, vp]
+    L.mmalign_debug_operands.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):

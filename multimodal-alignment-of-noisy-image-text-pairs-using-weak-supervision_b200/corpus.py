@@ -15,16 +15,21 @@ import numpy as np
 NULL_KEY = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
-def page_keys(records: Sequence[dict], page_ids: Dict[tuple, int]) -> np.ndarray:
-    """(manual_id, page) -> dense 64-bit key; page None is SQL NULL and never joins
-    (the join of src/evaluate_alignments.py:61)."""
+def page_keys(records: Sequence[dict], page_ids: Dict[tuple, int], python_join: bool = False) -> np.ndarray:
+    """(manual_id, page) -> dense 64-bit key.
+
+    SQL join (default; src/evaluate_alignments.py:61 `i.manual_id = t.manual_id AND i.page = t.page`): a NULL
+    manual or page never joins, so it becomes MMALIGN_NULL_KEY.
+    python_join=True: the alignment loop of insert_embeddings() compares with `!=`
+    (src/insert_clip_embeddings.py:377-380), for which None equals None -- every (manual_id, page) tuple,
+    None included, gets a real key."""
     out = np.empty(len(records), np.uint64)
     for i, r in enumerate(records):
         page = r.get("page")
-        if page is None or r.get("manual_id") is None:
+        if not python_join and (page is None or r.get("manual_id") is None):
             out[i] = NULL_KEY
         else:
-            out[i] = page_ids.setdefault((r["manual_id"], page), len(page_ids))
+            out[i] = page_ids.setdefault((r.get("manual_id"), page), len(page_ids))
     return out
 
 
@@ -64,8 +69,8 @@ class Corpus:
     chunk_ids: List[str]
     image_manual: List[str]
     image_page: list
-    img: dict                 # emb, key, bbox, terms(None)
-    chk: dict                 # emb, key, bbox, terms
+    img: dict                 # emb, key, bbox, terms(None), key_py (keys of the Python-side join, see page_keys)
+    chk: dict                 # emb, key, bbox, terms, key_py
     terms: List[str] = field(default_factory=list)
     image_index: Dict[str, int] = field(default_factory=dict)
     chunk_index: Dict[str, int] = field(default_factory=dict)
@@ -86,6 +91,9 @@ def build_corpus(images: Sequence[dict], chunks: Sequence[dict], image_emb, chun
                bbox=bbox_array(images), terms=None)
     chk = dict(emb=np.ascontiguousarray(chunk_emb, np.float32), key=page_keys(chunks, page_ids),
                bbox=bbox_array(chunks), terms=term_bitsets(chunks, terms, engine))
+    py_ids: Dict[tuple, int] = {}
+    img["key_py"] = page_keys(images, py_ids, python_join=True)
+    chk["key_py"] = page_keys(chunks, py_ids, python_join=True)
     c = Corpus(image_ids=[r["image_id"] for r in images], chunk_ids=[r["chunk_id"] for r in chunks],
                image_manual=[r.get("manual_id") for r in images], image_page=[r.get("page") for r in images],
                img=img, chk=chk, terms=terms)

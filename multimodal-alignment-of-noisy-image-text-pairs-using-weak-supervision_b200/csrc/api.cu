@@ -54,9 +54,18 @@ struct SideStore {
     Side s;
     DevBuf up[4];               // uploads of host inputs: emb, key, bbox, terms (reused across set_* calls)
     DevBuf bf16, norm2, err, errmax;
-    float *err_max = nullptr;   // [1] max rounding-error norm over the rows
+    float *err_max = nullptr;   // [1] max rounding-error norm over the rows (chunks)
     alignas(64) CUtensorMap tmap;
     bool ready = false;
+    // asynchronous ingest: host embedding rows arrive in pieces on the context's copy stream
+    int64_t piece_rows = 0;
+    int n_pieces = 0;                    // 0 = the rows were on the device already
+    std::vector<cudaEvent_t> ev_piece;   // [>= n_pieces] piece p is on the device (recorded on the copy stream)
+    cudaEvent_t ev_small = nullptr;      // keys / boxes / term sets are on the device (copy stream)
+    cudaEvent_t ev_caller = nullptr;     // whatever the caller had queued on the legacy default stream at set_* time
+    cudaEvent_t ev_ready = nullptr;      // the K0 launches queued so far have run (chunks: all rows, at set_* time)
+    bool ev_ready_set = false;
+    int64_t prep_lo = 0, prep_hi = 0;    // rows whose K0 outputs (bf16, norm2, err) are queued or done
     void release()
     {
         for (DevBuf &b : up) b.release();
@@ -64,8 +73,19 @@ struct SideStore {
         s = Side();
         err_max = nullptr;
         ready = false;
+        n_pieces = 0; prep_lo = prep_hi = 0; ev_ready_set = false;
+    }
+    void destroy_events()
+    {
+        for (cudaEvent_t e : ev_piece) if (e) cudaEventDestroy(e);
+        ev_piece.clear();
+        for (cudaEvent_t *e : {&ev_small, &ev_caller, &ev_ready}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
     }
 };
+
+constexpr int kMaxSlabs = 512;          // slabs of one mmalign_run (their failure counters live in `small`)
+constexpr int kSlabWaves = 4;           // auto slab = this many waves of 128-row blocks over the SMs
+constexpr size_t kSmallBytes = 8192;    // 0: fail_count | 8: cand_counter | 16: error_flag | 24: eps violations | 64: k_list | 128: eps | 1024: slab counters
 
 struct mmalign_ctx {
     int device = 0;
@@ -77,14 +97,20 @@ struct mmalign_ctx {
     bool px_ready = false;
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
-    DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;  // small: fail_count, cand_counter, error_flag, k_list, stats
+    DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     DevBuf term_table, text_off, text_bytes;  // mmalign_term_bitsets: term table, uploads of host texts
     CandLists lists;               // written by the last fused pass
     bool lists_valid = false;
     int64_t lists_col0 = 0;        // first chunk row of the column range the lists were built on
+    int64_t lists_rows = 0, lists_cols = 0;  // image rows / chunk columns the lists cover
     int64_t last_fused_us = 0;     // CUDA-event time of the last mmalign_fused_pass
-    cudaEvent_t ev[5] = {};        // run start, after fused, after rescore, after exact scan, after metrics
+    cudaEvent_t ev[5] = {};        // fused pass / rescore pass timing
+    // streams of the context (non-blocking): uploads, chunk preparation, pair index, downloads
+    cudaStream_t s_in = nullptr, s_prep = nullptr, s_idx = nullptr, s_out = nullptr;
+    cudaEvent_t ev_tmp = nullptr;
+    std::vector<cudaEvent_t> ev_slab;  // 4 per slab: start, after fused, after rescore, after exact scan (= slab done)
+    cudaEvent_t resc_wait = nullptr;   // mmalign_rescore_after: one-shot
 };
 
 static int fail(mmalign_ctx *c, int code, const char *fmt, ...)
@@ -107,17 +133,22 @@ static int fail(mmalign_ctx *c, int code, const char *fmt, ...)
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-static bool is_device_ptr(const void *p)
+enum PtrKind { kPtrNull, kPtrDevice, kPtrPinned, kPtrPageable };
+static PtrKind ptr_kind(const void *p)
 {
-    if (!p) return false;
+    if (!p) return kPtrNull;
     cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return kPtrPageable; }
+    if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return kPtrDevice;
+    return a.type == cudaMemoryTypeHost ? kPtrPinned : kPtrPageable;
 }
+static bool is_device_ptr(const void *p) { return ptr_kind(p) == kPtrDevice; }
 
 extern "C" int mmalign_abi_version(void) { return MMALIGN_ABI_VERSION; }
 
 extern "C" const char *mmalign_last_error(const mmalign_ctx *ctx) { return ctx ? ctx->err : g_err; }
+
+extern "C" void mmalign_destroy(mmalign_ctx *c);
 
 extern "C" int mmalign_create(mmalign_ctx **out, int device)
 {
@@ -140,9 +171,15 @@ extern "C" int mmalign_create(mmalign_ctx **out, int device)
     mmalign_ctx *c = new mmalign_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (c->small.reserve(4096) != cudaSuccess) { delete c; return fail(nullptr, MMALIGN_ECUDA, "cudaMalloc failed"); }
-    for (cudaEvent_t &e : c->ev)
-        if (cudaEventCreate(&e) != cudaSuccess) { delete c; return fail(nullptr, MMALIGN_ECUDA, "cudaEventCreate failed"); }
+    bool ok = c->small.reserve(kSmallBytes) == cudaSuccess;
+    for (cudaEvent_t &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    for (cudaStream_t *s : {&c->s_in, &c->s_prep, &c->s_idx, &c->s_out})
+        ok = ok && cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming) == cudaSuccess;
+    for (SideStore *ss : {&c->img, &c->chk})
+        for (cudaEvent_t *ev : {&ss->ev_small, &ss->ev_caller, &ss->ev_ready})
+            ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { mmalign_destroy(c); return fail(nullptr, MMALIGN_ECUDA, "creating the context's streams / events / scratch failed"); }
     *out = c;
     return MMALIGN_OK;
 }
@@ -154,14 +191,28 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     cudaDeviceSynchronize();
     c->img.release();
     c->chk.release();
+    c->img.destroy_events();
+    c->chk.destroy_events();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
                       &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
                       &c->term_table, &c->text_off, &c->text_bytes};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_slab) if (e) cudaEventDestroy(e);
+    if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
+    for (cudaStream_t s : {c->s_in, c->s_prep, c->s_idx, c->s_out}) if (s) cudaStreamDestroy(s);
     delete c;
 }
 
+extern "C" int mmalign_sync(mmalign_ctx *c)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_sync: ctx is NULL");
+    CU(c, cudaSetDevice(c->device));
+    for (cudaStream_t s : {c->s_in, c->s_prep, c->s_idx, c->s_out}) CU(c, cudaStreamSynchronize(s));
+    return MMALIGN_OK;
+}
+
+// host array -> the side's upload buffer (copy stream); device array: borrowed
 template <typename T>
 static int adopt(mmalign_ctx *c, DevBuf &buf, const T *src, size_t count, const T **dst, cudaStream_t st)
 {
@@ -174,8 +225,18 @@ static int adopt(mmalign_ctx *c, DevBuf &buf, const T *src, size_t count, const 
     return MMALIGN_OK;
 }
 
+// `b` waits for what `a` has queued so far
+static int order_after(mmalign_ctx *c, cudaStream_t b, cudaStream_t a)
+{
+    CU(c, cudaEventRecord(c->ev_tmp, a));
+    CU(c, cudaStreamWaitEvent(b, c->ev_tmp, 0));
+    return MMALIGN_OK;
+}
+
+constexpr size_t kPieceBytes = (size_t)64 << 20;  // embedding rows travel in pieces of about this size
+
 static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint64_t *key, const double *bbox,
-                    const uint64_t *terms, int64_t n, int D, int term_words, int box_rows, const char *what)
+                    const uint64_t *terms, int64_t n, int D, int term_words, int box_rows, const char *what, bool is_chunks)
 {
     if (!c) return fail(nullptr, MMALIGN_EINVAL, "%s: ctx is NULL", what);
     CU(c, cudaSetDevice(c->device));
@@ -183,40 +244,84 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
     if (D <= 0 || D % 4 != 0 || D > 4096) return fail(c, MMALIGN_EINVAL, "%s: D=%d must be a multiple of 4 in 4..4096", what, D);
     if (n > 0 && (!emb || !key)) return fail(c, MMALIGN_EINVAL, "%s: emb and page_key are required", what);
     if (term_words < 0 || (terms && term_words == 0)) return fail(c, MMALIGN_EINVAL, "%s: bad term_words", what);
-    cudaStream_t st = 0;
     Trace tr(what);
-    CU(c, cudaStreamSynchronize(st));
+    int rc;
+    // the side's buffers may still be read by preparation / index work queued by an earlier set_* call
+    if ((rc = order_after(c, c->s_in, c->s_prep))) return rc;
+    if ((rc = order_after(c, c->s_in, c->s_idx))) return rc;
+    CU(c, cudaEventRecord(ss.ev_caller, 0));  // device inputs: complete on the legacy default stream (include/mmalign.h)
     ss.ready = false;
     c->px_ready = false;
     c->lists_valid = false;
     ss.s = Side();
     Side &s = ss.s;
     s.n = n; s.D = D; s.term_words = term_words;
-    int rc;
-    if ((rc = adopt(c, ss.up[0], emb, (size_t)n * D, &s.emb, st))) return rc;
-    if ((rc = adopt(c, ss.up[1], key, (size_t)n, &s.key, st))) return rc;
-    if ((rc = adopt(c, ss.up[3], terms, (size_t)n * term_words, &s.terms, st))) return rc;
+    cudaStream_t sin = c->s_in;
+    if ((rc = adopt(c, ss.up[1], key, (size_t)n, &s.key, sin))) return rc;
+    if ((rc = adopt(c, ss.up[3], terms, (size_t)n * term_words, &s.terms, sin))) return rc;
     if (bbox) {
-        if ((rc = adopt(c, ss.up[2], bbox, (size_t)n * 4, &s.bbox, st))) return rc;
+        if ((rc = adopt(c, ss.up[2], bbox, (size_t)n * 4, &s.bbox, sin))) return rc;
     } else if (n > 0) {  // missing boxes: all zero -> positional score 0 (insert_clip_embeddings.py:161)
         CU(c, ss.up[2].reserve((size_t)n * 4 * sizeof(double)));
-        CU(c, cudaMemsetAsync(ss.up[2].p, 0, (size_t)n * 4 * sizeof(double), st));
+        CU(c, cudaMemsetAsync(ss.up[2].p, 0, (size_t)n * 4 * sizeof(double), sin));
         s.bbox = static_cast<const double *>(ss.up[2].p);
     }
+    CU(c, cudaEventRecord(ss.ev_small, sin));
     const size_t nn = n > 0 ? (size_t)n : 1;
     CU(c, ss.bf16.reserve(nn * D * sizeof(__nv_bfloat16))); s.emb_bf16 = (__nv_bfloat16 *)ss.bf16.p;
     CU(c, ss.norm2.reserve(nn * sizeof(float))); s.norm2 = (float *)ss.norm2.p;
     CU(c, ss.err.reserve(nn * sizeof(float))); s.err = (float *)ss.err.p;
     CU(c, ss.errmax.reserve(sizeof(float))); ss.err_max = (float *)ss.errmax.p;
-    CU(c, launch_prep(s, st));
-    CU(c, reduce_max_float(s.err, n, ss.err_max, st));
+    // embedding rows: borrowed on the device, or uploaded piece by piece (each piece announces itself with an event)
+    ss.n_pieces = 0;
+    ss.prep_lo = ss.prep_hi = 0;
+    ss.ev_ready_set = false;
+    if (n > 0 && is_device_ptr(emb)) {
+        s.emb = emb;
+    } else if (n > 0) {
+        CU(c, ss.up[0].reserve((size_t)n * D * sizeof(float)));
+        s.emb = static_cast<const float *>(ss.up[0].p);
+        int64_t pr = (int64_t)(kPieceBytes / ((size_t)D * sizeof(float)));
+        pr = pr < 128 ? 128 : pr / 128 * 128;
+        ss.piece_rows = pr;
+        ss.n_pieces = (int)((n + pr - 1) / pr);
+        while ((int)ss.ev_piece.size() < ss.n_pieces) {
+            cudaEvent_t e = nullptr;
+            CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ss.ev_piece.push_back(e);
+        }
+        for (int p = 0; p < ss.n_pieces; ++p) {
+            const int64_t r0 = (int64_t)p * pr, r1 = r0 + pr < n ? r0 + pr : n;
+            CU(c, cudaMemcpyAsync((float *)ss.up[0].p + r0 * D, emb + r0 * D, (size_t)(r1 - r0) * D * sizeof(float),
+                                  cudaMemcpyHostToDevice, sin));
+            CU(c, cudaEventRecord(ss.ev_piece[p], sin));
+        }
+    }
     if (n > 0 && D % 64 == 0) {
         char msg[256];
         if (encode_tensor_map(&ss.tmap, s.emb_bf16, n, D, box_rows, msg, sizeof msg))
             return fail(c, MMALIGN_ECUDA, "%s: %s", what, msg);
     }
-    CU(c, cudaStreamSynchronize(st));
-    tr.mark("upload + prep");
+    // chunks: K0 runs now, piece by piece behind the uploads.  Images: K0 runs in the consumer (mmalign_run prepares
+    // slab s just before it contracts it, so that the upload of later slabs overlaps the kernels of earlier ones).
+    if (is_chunks) {
+        cudaStream_t sp = c->s_prep;
+        CU(c, cudaStreamWaitEvent(sp, ss.ev_caller, 0));
+        if (ss.n_pieces == 0) {
+            CU(c, launch_prep(s, 0, n, c->sm_count, sp));
+        } else {
+            for (int p = 0; p < ss.n_pieces; ++p) {
+                const int64_t r0 = (int64_t)p * ss.piece_rows, r1 = r0 + ss.piece_rows < n ? r0 + ss.piece_rows : n;
+                CU(c, cudaStreamWaitEvent(sp, ss.ev_piece[p], 0));
+                CU(c, launch_prep(s, r0, r1 - r0, c->sm_count, sp));
+            }
+        }
+        CU(c, reduce_max_float(s.err, n, ss.err_max, sp));
+        CU(c, cudaEventRecord(ss.ev_ready, sp));
+        ss.ev_ready_set = true;
+        ss.prep_lo = 0; ss.prep_hi = n;
+    }
+    tr.mark("queued upload + prep");
     ss.ready = true;
     return MMALIGN_OK;
 }
@@ -225,7 +330,7 @@ extern "C" int mmalign_set_images(mmalign_ctx *c, const float *emb, const uint64
                                   const uint64_t *terms, int64_t n, int32_t D, int32_t term_words)
 {
     if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_set_images: ctx is NULL");
-    return set_side(c, c->img, emb, key, bbox, terms, n, D, term_words, 128, "mmalign_set_images");
+    return set_side(c, c->img, emb, key, bbox, terms, n, D, term_words, 128, "mmalign_set_images", false);
 }
 
 extern "C" int mmalign_set_chunks(mmalign_ctx *c, const float *emb, const uint64_t *key, const double *bbox,
@@ -236,11 +341,120 @@ extern "C" int mmalign_set_chunks(mmalign_ctx *c, const float *emb, const uint64
     if (n_terms < 0 || n_terms > (int64_t)term_words * 64)
         return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks: n_terms=%lld does not fit %d term words", (long long)n_terms, term_words);
     if (col_offset < 0) return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks: negative col_offset");
-    int rc = set_side(c, c->chk, emb, key, bbox, terms, m, D, term_words, 256, "mmalign_set_chunks");
+    int rc = set_side(c, c->chk, emb, key, bbox, terms, m, D, term_words, 256, "mmalign_set_chunks", true);
     if (rc) return rc;
     c->n_terms = n_terms;
     c->col_offset = col_offset;
     return MMALIGN_OK;
+}
+
+extern "C" int mmalign_prep_rows(mmalign_ctx *c, const float *emb, int64_t n, int32_t D, void *bf16_out, float *norm2_out,
+                                 float *err_out, void *stream)
+{
+    if (!c || (n > 0 && (!emb || !bf16_out || !norm2_out || !err_out))) return fail(c, MMALIGN_EINVAL, "mmalign_prep_rows: NULL argument");
+    if (n < 0 || D <= 0 || D % 4 != 0 || D > 4096) return fail(c, MMALIGN_EINVAL, "mmalign_prep_rows: bad n / D");
+    if (n == 0) return MMALIGN_OK;
+    if (!is_device_ptr(emb) || !is_device_ptr(bf16_out) || !is_device_ptr(norm2_out) || !is_device_ptr(err_out))
+        return fail(c, MMALIGN_EINVAL, "mmalign_prep_rows takes device pointers (it feeds an all-gather)");
+    CU(c, cudaSetDevice(c->device));
+    Side s;
+    s.n = n; s.D = D; s.emb = emb; s.emb_bf16 = (__nv_bfloat16 *)bf16_out; s.norm2 = norm2_out; s.err = err_out;
+    CU(c, launch_prep(s, 0, n, c->sm_count, (cudaStream_t)stream));
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_set_chunks_prepared(mmalign_ctx *c, const float *emb, const uint64_t *key, const double *bbox,
+                                           const uint64_t *terms, const void *bf16, const float *norm2, const float *err,
+                                           int64_t m, int32_t D, int32_t term_words, int64_t n_terms, int64_t col_offset,
+                                           void *stream)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_set_chunks_prepared: ctx is NULL");
+    CU(c, cudaSetDevice(c->device));
+    if (m < 0 || m > 0x7FFFFFF0ll) return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks_prepared: row count out of range");
+    if (D <= 0 || D % 4 != 0 || D > 4096) return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks_prepared: D=%d must be a multiple of 4 in 4..4096", D);
+    if (n_terms < 0 || n_terms > (int64_t)term_words * 64 || term_words < 0 || (terms && term_words == 0) || col_offset < 0)
+        return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks_prepared: bad term_words / n_terms / col_offset");
+    if (m > 0) {
+        const void *need[] = {emb, key, bbox, bf16, norm2, err};
+        for (const void *p : need)
+            if (!is_device_ptr(p)) return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks_prepared takes device pointers (emb, page_key, bbox, bf16, norm2, err)");
+        if (terms && !is_device_ptr(terms)) return fail(c, MMALIGN_EINVAL, "mmalign_set_chunks_prepared: terms must be a device pointer");
+    }
+    SideStore &ss = c->chk;
+    int rc;
+    if ((rc = order_after(c, c->s_in, c->s_prep))) return rc;
+    if ((rc = order_after(c, c->s_in, c->s_idx))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ss.ready = false; c->px_ready = false; c->lists_valid = false;
+    ss.s = Side();
+    Side &s = ss.s;
+    s.n = m; s.D = D; s.term_words = term_words;
+    s.emb = emb; s.key = key; s.bbox = bbox; s.terms = terms;
+    s.emb_bf16 = (__nv_bfloat16 *)const_cast<void *>(bf16); s.norm2 = const_cast<float *>(norm2); s.err = const_cast<float *>(err);
+    ss.n_pieces = 0;
+    CU(c, ss.errmax.reserve(sizeof(float))); ss.err_max = (float *)ss.errmax.p;
+    // the caller's stream carries the exchange that filled the prepared operands and the keys
+    CU(c, cudaEventRecord(ss.ev_caller, st));
+    CU(c, cudaEventRecord(ss.ev_small, st));
+    CU(c, cudaStreamWaitEvent(c->s_prep, ss.ev_caller, 0));
+    CU(c, reduce_max_float(s.err, m, ss.err_max, c->s_prep));
+    CU(c, cudaEventRecord(ss.ev_ready, c->s_prep));
+    ss.ev_ready_set = true;
+    ss.prep_lo = 0; ss.prep_hi = m;
+    if (m > 0 && D % 64 == 0) {
+        char msg[256];
+        if (encode_tensor_map(&ss.tmap, s.emb_bf16, m, D, 256, msg, sizeof msg))
+            return fail(c, MMALIGN_ECUDA, "mmalign_set_chunks_prepared: %s", msg);
+    }
+    c->n_terms = n_terms;
+    c->col_offset = col_offset;
+    ss.ready = true;
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_rescore_after(mmalign_ctx *c, void *event)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_rescore_after: ctx is NULL");
+    c->resc_wait = (cudaEvent_t)event;
+    return MMALIGN_OK;
+}
+
+// `st` waits for the side's small arrays, for the caller's producers and for the K0 launches queued so far
+static int wait_side(mmalign_ctx *c, SideStore &ss, cudaStream_t st)
+{
+    CU(c, cudaStreamWaitEvent(st, ss.ev_small, 0));
+    CU(c, cudaStreamWaitEvent(st, ss.ev_caller, 0));
+    if (ss.ev_ready_set) CU(c, cudaStreamWaitEvent(st, ss.ev_ready, 0));
+    return MMALIGN_OK;
+}
+
+// K0 of image rows [lo, hi) on `st` (behind the upload pieces that hold them), unless it is queued already
+static int prepare_images(mmalign_ctx *c, int64_t lo, int64_t hi, cudaStream_t st, long long *launched = nullptr)
+{
+    SideStore &ss = c->img;
+    if (lo >= hi) return MMALIGN_OK;
+    if (lo >= ss.prep_lo && hi <= ss.prep_hi) return MMALIGN_OK;  // (wait_side ordered `st` behind those launches)
+    if (ss.n_pieces > 0) {
+        const int p0 = (int)(lo / ss.piece_rows), p1 = (int)((hi - 1) / ss.piece_rows);
+        for (int p = p0; p <= p1 && p < ss.n_pieces; ++p) CU(c, cudaStreamWaitEvent(st, ss.ev_piece[p], 0));
+    }
+    CU(c, launch_prep(ss.s, lo, hi - lo, c->sm_count, st));
+    if (launched) *launched += 1;
+    CU(c, cudaEventRecord(ss.ev_ready, st));
+    ss.ev_ready_set = true;
+    if (ss.prep_lo == ss.prep_hi) { ss.prep_lo = lo; ss.prep_hi = hi; }
+    else if (lo <= ss.prep_hi && hi >= ss.prep_lo) { ss.prep_lo = lo < ss.prep_lo ? lo : ss.prep_lo; ss.prep_hi = hi > ss.prep_hi ? hi : ss.prep_hi; }
+    else { ss.prep_lo = lo; ss.prep_hi = hi; }
+    return MMALIGN_OK;
+}
+
+// every input of a kernel that reads both tables whole (the sharded passes, debug hooks)
+static int wait_tables(mmalign_ctx *c, cudaStream_t st)
+{
+    int rc;
+    if ((rc = wait_side(c, c->img, st))) return rc;
+    if ((rc = wait_side(c, c->chk, st))) return rc;
+    return prepare_images(c, 0, c->img.s.n, st);
 }
 
 static int ensure_index(mmalign_ctx *c)
@@ -260,7 +474,12 @@ static int ensure_index(mmalign_ctx *c)
     c->px.sp_start = (int64_t *)c->px_start.p;
     const size_t sb = pair_index_scratch_bytes(N, M);
     CU(c, c->px_scratch.reserve(sb));
-    CU(c, build_pair_index(c->img.s, c->chk.s, c->px, c->px_scratch.p, sb, 0));
+    // the index needs the page keys only: it is built on its own stream while the embedding rows still travel
+    for (SideStore *ss : {&c->img, &c->chk}) {
+        CU(c, cudaStreamWaitEvent(c->s_idx, ss->ev_small, 0));
+        CU(c, cudaStreamWaitEvent(c->s_idx, ss->ev_caller, 0));
+    }
+    CU(c, build_pair_index(c->img.s, c->chk.s, c->px, c->px_scratch.p, sb, c->s_idx));
     c->px_ready = true;
     return MMALIGN_OK;
 }
@@ -276,22 +495,28 @@ extern "C" int mmalign_num_pairs(mmalign_ctx *c, int64_t *num_pairs)
 
 // ---- output staging: host pointers get a device twin that is copied back --------------------
 struct Stager {
+    enum Kind { kSmall, kPerRow, kPerPair };  // per-row: [S][rows][w]; per-pair: [S][P] (S = 1: [P])
     mmalign_ctx *c;
     cudaStream_t st;
-    struct Item { void *host; void *dev; size_t bytes; };
+    struct Item { void *host; void *dev; size_t bytes; Kind kind; size_t unit; int S; };
     std::vector<Item> items;
     size_t used = 0;
     std::vector<std::pair<void **, size_t>> pending;  // (slot to patch, offset)
-    template <typename T> int map(T *user, size_t count, T **dev)
+    template <typename T> int map(T *user, size_t count, T **dev, Kind kind = kSmall, size_t unit = 0, int S = 1)
     {
         *dev = nullptr;
         if (!user || count == 0) return 0;
         if (is_device_ptr(user)) { *dev = user; return 0; }
         const size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
-        items.push_back({user, nullptr, count * sizeof(T)});
+        items.push_back({user, nullptr, count * sizeof(T), kind, unit, S});
         pending.push_back({(void **)dev, used});
         used += bytes;
         return 0;
+    }
+    bool any_large() const
+    {
+        for (auto &it : items) if (it.kind != kSmall) return true;
+        return false;
     }
     int commit()
     {
@@ -304,9 +529,26 @@ struct Stager {
         }
         return 0;
     }
-    int copy_back()
+    int copy_back(cudaStream_t s, bool small_only = false)
     {
-        for (auto &it : items) CU(c, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, st));
+        for (auto &it : items)
+            if (!small_only || it.kind == kSmall) CU(c, cudaMemcpyAsync(it.host, it.dev, it.bytes, cudaMemcpyDeviceToHost, s));
+        return 0;
+    }
+    int copy_back() { return copy_back(st); }
+    // rows [r0, r1) of N and pairs [p0, p1) of P (positions within the run's output window)
+    int copy_slab(cudaStream_t s, int64_t r0, int64_t r1, int64_t N, int64_t p0, int64_t p1, int64_t P)
+    {
+        for (auto &it : items) {
+            if (it.kind == kSmall) continue;
+            const int64_t lo = it.kind == kPerRow ? r0 : p0, hi = it.kind == kPerRow ? r1 : p1, tot = it.kind == kPerRow ? N : P;
+            if (hi <= lo) continue;
+            for (int si = 0; si < it.S; ++si) {
+                const size_t off = ((size_t)si * tot + lo) * it.unit;
+                CU(c, cudaMemcpyAsync((char *)it.host + off, (char *)it.dev + off, (size_t)(hi - lo) * it.unit,
+                                      cudaMemcpyDeviceToHost, s));
+            }
+        }
         return 0;
     }
 };
@@ -316,7 +558,7 @@ extern "C" int mmalign_get_pairs(mmalign_ctx *c, int64_t *pair_offsets, int64_t 
     if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_get_pairs: ctx is NULL");
     int rc = ensure_index(c);
     if (rc) return rc;
-    cudaStream_t st = 0;
+    cudaStream_t st = c->s_idx;
     const int64_t N = c->img.s.n;
     if (pair_offsets)
         CU(c, cudaMemcpyAsync(pair_offsets, c->px.offsets, sizeof(int64_t) * (N + 1), cudaMemcpyDefault, st));
@@ -367,6 +609,7 @@ static int parse_params(mmalign_ctx *c, const mmalign_params *prm, RunParams *ou
     if (needs_terms && !chk.terms && chk.n > 0) return fail(c, MMALIGN_EINVAL, "lexical schema requested but the chunks have no term sets");
     if (prm->path < 0 || prm->path > 2) return fail(c, MMALIGN_EINVAL, "path=%d unknown", prm->path);
     if (prm->n_ranks < 0 || prm->n_ranks > 64) return fail(c, MMALIGN_EINVAL, "n_ranks=%d must be in 0..64", prm->n_ranks);
+    if (prm->pipeline_rows < -1) return fail(c, MMALIGN_EINVAL, "pipeline_rows=%d must be >= -1", prm->pipeline_rows);
     *out = rp;
     return MMALIGN_OK;
 }
@@ -380,28 +623,43 @@ static int resolve_range(mmalign_ctx *c, int64_t lo, int64_t cnt, int64_t total,
     return MMALIGN_OK;
 }
 
-// Rows [row0, row0 + n_rows) with their slice of the pair arrays (two 8-byte reads of the pair index).
-static int make_row_range(mmalign_ctx *c, int64_t row0, int64_t n_rows, cudaStream_t st, RowRange *out)
+// Pair offsets at the given image rows (a handful of 8-byte reads of the pair index, one synchronisation)
+static int pair_offsets_at(mmalign_ctx *c, const std::vector<int64_t> &rows, std::vector<int64_t> *out)
+{
+    out->assign(rows.size(), 0);
+    for (size_t q = 0; q < rows.size(); ++q)
+        CU(c, cudaMemcpyAsync(out->data() + q, c->px.offsets + rows[q], sizeof(int64_t), cudaMemcpyDeviceToHost, c->s_idx));
+    CU(c, cudaStreamSynchronize(c->s_idx));
+    return MMALIGN_OK;
+}
+
+// Rows [row0, row0 + n_rows) with their slice of the pair arrays
+static int make_row_range(mmalign_ctx *c, int64_t row0, int64_t n_rows, RowRange *out)
 {
     RowRange r;
     r.row0 = row0; r.n_rows = n_rows;
-    int64_t h[2] = {0, 0};
-    CU(c, cudaMemcpyAsync(&h[0], c->px.offsets + row0, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(c, cudaMemcpyAsync(&h[1], c->px.offsets + row0 + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CU(c, cudaStreamSynchronize(st));
+    std::vector<int64_t> h;
+    int rc = pair_offsets_at(c, {row0, row0 + n_rows}, &h);
+    if (rc) return rc;
     r.pair0 = h[0]; r.P_out = h[1] - h[0];
     *out = r;
     return MMALIGN_OK;
 }
 
-// K1 of image rows [row0, +n_rows) against chunk rows [col0, +n_cols) of the current corpus; the lists (row and
-// column indices relative to the ranges) stay in the context for the rescoring / export pass
-static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, int64_t row0, int64_t n_rows,
-                     int64_t col0, int64_t n_cols, cudaStream_t st, FusedPlan *plan_out)
+// K1 of image rows [row0, +n_rows) against chunk rows [col0, +n_cols) of the current corpus into `lists` (row and
+// column indices relative to the ranges); the list buffers of the context must hold plan.n_lists lists
+static int reserve_lists(mmalign_ctx *c, const FusedPlan &plan)
+{
+    CU(c, c->list_keys.reserve((size_t)plan.n_lists * plan.cap * sizeof(uint64_t)));
+    CU(c, c->list_tau.reserve((size_t)plan.n_lists * sizeof(float)));
+    CU(c, c->list_count.reserve((size_t)plan.n_lists * sizeof(int32_t)));
+    return MMALIGN_OK;
+}
+
+static int launch_fused_range(mmalign_ctx *c, const FusedPlan &plan, int64_t row0, int64_t n_rows, int64_t col0, int64_t n_cols,
+                              cudaStream_t st, CandLists *lists)
 {
     Side img = c->img.s, chk = c->chk.s;
-    if (img.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", img.D);
-    if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
     alignas(64) CUtensorMap tmap_a = c->img.tmap, tmap_b = c->chk.tmap;
     char msg[256];
     if (row0 != 0 || n_rows != img.n) {
@@ -412,24 +670,56 @@ static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_
         if (encode_tensor_map(&tmap_b, chk.emb_bf16 + col0 * chk.D, n_cols, chk.D, 256, msg, sizeof msg)) return fail(c, MMALIGN_ECUDA, "%s", msg);
         chk.n = n_cols;
     }
-    c->lists_col0 = col0;
+    *lists = CandLists();
+    lists->keys = (uint64_t *)c->list_keys.p; lists->tau = (float *)c->list_tau.p; lists->count = (int32_t *)c->list_count.p;
+    CU(c, launch_fused(img, chk, plan, &tmap_a, &tmap_b, *lists, nullptr, st));
+    return MMALIGN_OK;
+}
+
+static int plan_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, int64_t n_rows, int64_t n_cols, FusedPlan *plan)
+{
+    if (c->img.s.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", c->img.s.D);
+    if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
+    const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, c->sm_count, n_ranks, plan);
+    if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)n_rows, (long long)n_cols, c->img.s.D, kprime_req, prc);
+    return MMALIGN_OK;
+}
+
+// the fused pass of the sharded entry points: one launch over [row0, +n_rows) x [col0, +n_cols), lists kept in the context
+static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, int64_t row0, int64_t n_rows,
+                     int64_t col0, int64_t n_cols, cudaStream_t st, FusedPlan *plan_out)
+{
     FusedPlan plan;
-    const int prc = fused_plan(img.n, chk.n, img.D, rp.kneed, kprime_req, c->sm_count, n_ranks, &plan);
-    if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)img.n, (long long)chk.n, img.D, kprime_req, prc);
-    CU(c, c->list_keys.reserve((size_t)plan.n_lists * plan.cap * sizeof(uint64_t)));
-    CU(c, c->list_tau.reserve((size_t)plan.n_lists * sizeof(float)));
-    CU(c, c->list_count.reserve((size_t)plan.n_lists * sizeof(int32_t)));
-    CU(c, c->fail_rows.reserve((size_t)img.n * sizeof(int32_t)));
-    c->lists = CandLists();
-    c->lists.keys = (uint64_t *)c->list_keys.p; c->lists.tau = (float *)c->list_tau.p; c->lists.count = (int32_t *)c->list_count.p;
-    CU(c, launch_fused(img, chk, plan, &tmap_a, &tmap_b, c->lists, nullptr, st));
+    int rc;
+    if ((rc = plan_fused(c, rp, kprime_req, n_ranks, n_rows, n_cols, &plan))) return rc;
+    if ((rc = reserve_lists(c, plan))) return rc;
+    CU(c, c->fail_rows.reserve((size_t)c->img.s.n * sizeof(int32_t)));
+    if ((rc = launch_fused_range(c, plan, row0, n_rows, col0, n_cols, st, &c->lists))) return rc;
+    c->lists_col0 = col0;
+    c->lists_rows = n_rows; c->lists_cols = n_cols;
     c->lists_valid = true;
     *plan_out = plan;
     return MMALIGN_OK;
 }
 
+static int slab_events(mmalign_ctx *c, int n_slabs)
+{
+    while ((int)c->ev_slab.size() < 4 * n_slabs) {
+        cudaEvent_t e = nullptr;
+        CU(c, cudaEventCreate(&e));
+        c->ev_slab.push_back(e);
+    }
+    return MMALIGN_OK;
+}
+
 // mmalign_run and mmalign_rescore_slab: rank image rows [slab_row0, +slab_rows) (0, 0 = all).  `imported` = the
 // candidate lists received from the ranks' fused passes (global chunk indices); without it the fused kernel runs here.
+//
+// The rows are processed in pipeline slabs that share one set of device output arrays: slab s is prepared (K0),
+// contracted (K1), re-scored (K2) and, where its certificate fails, scanned exactly on the run's stream while the
+// copy stream still uploads the embedding rows of later slabs (queued by mmalign_set_images) and the download
+// stream already returns the results of earlier ones.  Every kernel of every slab is queued before the first
+// download is, so a pageable destination (whose copies block the host) stalls nothing on the device.
 static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, void *stream, const CandLists *imported)
 {
     Trace tr("run");
@@ -442,31 +732,45 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     RunParams rp;
     if ((rc = parse_params(c, prm, &rp))) return rc;
     CU(c, cudaSetDevice(c->device));
-    int64_t row0, N;  // the slab; per-row outputs are [S][N][..], per-pair outputs [S][P]
+    int64_t row0, N;  // the rows of this run; per-row outputs are [S][N][..], per-pair outputs [S][P]
     if ((rc = resolve_range(c, prm->slab_row0, prm->slab_rows, img.n, "slab rows", &row0, &N))) return rc;
-    RowRange range;
-    if ((rc = make_row_range(c, row0, N, st, &range))) return rc;
-    const int64_t P = range.P_out;
     // ---- outputs
+    if ((uo->topk_idx == nullptr) != (uo->topk_score == nullptr)) return fail(c, MMALIGN_EINVAL, "topk_idx and topk_score go together");
+    if ((uo->deep_idx == nullptr) != (uo->deep_score == nullptr)) return fail(c, MMALIGN_EINVAL, "deep_idx and deep_score go together");
+    const bool fused_path = rp.candidates == MMALIGN_CAND_ALL && prm->path != MMALIGN_PATH_EXACT && M > 0;
+    // ---- pipeline slabs
+    const void *large_out[] = {uo->topk_idx, uo->pair_rank, uo->pair_sim, uo->pair_score, uo->deep_idx};
+    bool host_out = false;
+    for (const void *p : large_out) host_out = host_out || (p && !is_device_ptr(p));
+    int64_t slab_rows = N > 0 ? N : 1;
+    const int64_t wave_rows = (int64_t)c->sm_count * 128;  // one 128-row block per SM
+    if (imported || prm->pipeline_rows < 0) { /* one slab */ }
+    else if (prm->pipeline_rows > 0) slab_rows = ((int64_t)prm->pipeline_rows + 127) / 128 * 128;
+    else if (c->img.n_pieces > 0 || host_out) {  // auto: whole waves, at least two slabs
+        if (N >= 2 * kSlabWaves * wave_rows) slab_rows = kSlabWaves * wave_rows;
+        else if (N >= 4 * wave_rows) slab_rows = 2 * wave_rows;
+    }
+    if (N > slab_rows * kMaxSlabs) slab_rows = ((N + kMaxSlabs - 1) / kMaxSlabs + 127) / 128 * 128;
+    const int n_slabs = N > 0 ? (int)((N + slab_rows - 1) / slab_rows) : 0;
+    std::vector<int64_t> bounds((size_t)n_slabs + 1), poff;
+    for (int s = 0; s <= n_slabs; ++s) bounds[s] = row0 + ((int64_t)s * slab_rows < N ? (int64_t)s * slab_rows : N);
+    if ((rc = pair_offsets_at(c, bounds, &poff))) return rc;
+    const int64_t pair0 = poff[0], P = poff[n_slabs] - poff[0];
     Stager sg{c, st};
     Outputs out = {};
-    int64_t *d_hits = nullptr, *d_np = nullptr, *d_stats = nullptr;
+    int64_t *d_hits = nullptr;
     double *d_rr = nullptr, *d_sim = nullptr;
     const size_t SNK = (size_t)rp.S * N * rp.kmax, SP = (size_t)rp.S * P;
-    if ((uo->topk_idx == nullptr) != (uo->topk_score == nullptr)) return fail(c, MMALIGN_EINVAL, "topk_idx and topk_score go together");
-    sg.map(uo->topk_idx, SNK, &out.topk_idx);
-    sg.map(uo->topk_score, SNK, &out.topk_score);
-    sg.map(uo->pair_rank, SP, &out.pair_rank);
-    sg.map(uo->pair_sim, (size_t)P, &out.pair_sim);
+    sg.map(uo->topk_idx, SNK, &out.topk_idx, Stager::kPerRow, (size_t)rp.kmax * 8, rp.S);
+    sg.map(uo->topk_score, SNK, &out.topk_score, Stager::kPerRow, (size_t)rp.kmax * 8, rp.S);
+    sg.map(uo->pair_rank, SP, &out.pair_rank, Stager::kPerPair, 4, rp.S);
+    sg.map(uo->pair_sim, (size_t)P, &out.pair_sim, Stager::kPerPair, 8, 1);
     sg.map(uo->hits, (size_t)rp.S * rp.n_k, &d_hits);
     sg.map(uo->rr_sum, (size_t)rp.S, &d_rr);
     sg.map(uo->sim_sum, 1, &d_sim);
-    sg.map(uo->num_pairs, 1, &d_np);
-    sg.map(uo->stats, 8, &d_stats);
-    sg.map(uo->pair_score, SP, &out.pair_score);
-    if ((uo->deep_idx == nullptr) != (uo->deep_score == nullptr)) return fail(c, MMALIGN_EINVAL, "deep_idx and deep_score go together");
-    sg.map(uo->deep_idx, (size_t)rp.S * N * rp.kneed, &out.deep_idx);
-    sg.map(uo->deep_score, (size_t)rp.S * N * rp.kneed, &out.deep_score);
+    sg.map(uo->pair_score, SP, &out.pair_score, Stager::kPerPair, 8, rp.S);
+    sg.map(uo->deep_idx, (size_t)rp.S * N * rp.kneed, &out.deep_idx, Stager::kPerRow, (size_t)rp.kneed * 8, rp.S);
+    sg.map(uo->deep_score, (size_t)rp.S * N * rp.kneed, &out.deep_score, Stager::kPerRow, (size_t)rp.kneed * 8, rp.S);
     // metric sums need the per-pair arrays even if the caller did not ask for them
     const bool want_sums = uo->hits || uo->rr_sum || uo->sim_sum;
     if ((rc = sg.commit())) return rc;
@@ -476,54 +780,86 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         if (!out.pair_rank) out.pair_rank = (int32_t *)extra.p;
         if (!out.pair_sim) out.pair_sim = (double *)((char *)extra.p + ((SP * sizeof(int32_t) + 255) & ~(size_t)255));
     }
+    // ---- plans and scratch of every slab, before anything is queued (a growing buffer would stall the pipeline)
+    std::vector<FusedPlan> plans((size_t)n_slabs);
+    if (fused_path) {
+        CU(c, c->fail_rows.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(int32_t)));
+        CU(c, c->fail_thr.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(unsigned long long)));
+        CU(c, c->scan_buf.reserve(scan_scratch_bytes()));
+        CU(c, c->scan_cnt.reserve(sizeof(int32_t) * kScanSlots));
+        if (!imported) {
+            FusedPlan big = {};
+            for (int s = 0; s < n_slabs; ++s) {
+                if ((rc = plan_fused(c, rp, prm->kprime, 1, bounds[s + 1] - bounds[s], M, &plans[s]))) return rc;
+                if ((size_t)plans[s].n_lists * plans[s].cap >= (size_t)big.n_lists * big.cap) { big.cap = plans[s].cap; big.n_lists = plans[s].n_lists; }
+            }
+            FusedPlan most = big;
+            for (int s = 0; s < n_slabs; ++s) if (plans[s].n_lists > most.n_lists) most.n_lists = plans[s].n_lists;
+            if ((rc = reserve_lists(c, big))) return rc;
+            CU(c, c->list_tau.reserve((size_t)most.n_lists * sizeof(float)));
+            CU(c, c->list_count.reserve((size_t)most.n_lists * sizeof(int32_t)));
+        }
+    }
+    if ((rc = slab_events(c, n_slabs))) return rc;
     tr.mark("params + staging");
     // ---- small device state
-    int32_t *fail_count = (int32_t *)c->small.p;
+    int32_t *slab_fail = (int32_t *)((char *)c->small.p + 1024);  // [n_slabs] rows of the slab that missed the certificate
     unsigned long long *cand_counter = (unsigned long long *)((char *)c->small.p + 8);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
     int32_t *k_list_dev = (int32_t *)((char *)c->small.p + 64);
+    if ((rc = wait_side(c, c->img, st))) return rc;
+    if ((rc = wait_side(c, c->chk, st))) return rc;
     CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
+    CU(c, cudaMemsetAsync(slab_fail, 0, sizeof(int32_t) * kMaxSlabs, st));
     CU(c, cudaMemcpyAsync(k_list_dev, rp.k_list, sizeof(int32_t) * kMaxK, cudaMemcpyHostToDevice, st));
     if (out.pair_rank && SP) CU(c, cudaMemsetAsync(out.pair_rank, 0, SP * sizeof(int32_t), st));
-    long long launches = 2, fused_launches = 0, kprime_used = 0;
-    // ---- scoring
-    CU(c, cudaEventRecord(c->ev[0], st));
-    for (int q = 1; q < 4; ++q) CU(c, cudaEventRecord(c->ev[q], st));  // overwritten by the phases that run
-    if (N > 0) {
+    long long launches = 0, fused_launches = 0, kprime_used = 0;
+    ScanScratch pre;
+    // ---- the slabs
+    for (int s = 0; s < n_slabs; ++s) {
+        const int64_t r0 = bounds[s], rows = bounds[s + 1] - bounds[s];
+        RowRange range;
+        range.row0 = r0; range.n_rows = rows;
+        range.pair0 = pair0; range.P_out = P;
+        range.o_row0 = row0; range.o_rows = N;
+        cudaEvent_t *ev = &c->ev_slab[4 * (size_t)s];
+        if ((rc = prepare_images(c, r0, r0 + rows, st, &launches))) return rc;
+        CU(c, cudaEventRecord(ev[0], st));
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
             CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, nullptr, cand_counter,
                                  error_flag, nullptr, nullptr, range, st));
             launches += 1;
-        } else if (prm->path == MMALIGN_PATH_EXACT || M == 0) {
-            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, N, out, error_flag, range, nullptr, st));
+        } else if (!fused_path) {
+            CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, rows, out, error_flag, range, nullptr, st));
             launches += 1;
         } else {
-            CU(c, c->fail_thr.reserve((size_t)img.n * sizeof(unsigned long long)));
-            CU(c, c->scan_buf.reserve(scan_scratch_bytes()));
-            CU(c, c->scan_cnt.reserve(sizeof(int32_t) * kScanSlots));
-            ScanScratch pre;
-            pre.thr = (unsigned long long *)c->fail_thr.p; pre.buf = c->scan_buf.p; pre.cnt = (int32_t *)c->scan_cnt.p;
+            CandLists L;
             if (imported) {
-                CU(c, c->fail_rows.reserve((size_t)img.n * sizeof(int32_t)));
+                L = *imported;
                 kprime_used = imported->kprime;
             } else {
-                FusedPlan plan;
-                if ((rc = run_fused(c, rp, prm->kprime, 1, row0, N, 0, M, st, &plan))) return rc;
-                fused_launches = 1;
+                if ((rc = launch_fused_range(c, plans[s], r0, rows, 0, M, st, &L))) return rc;
+                fused_launches += 1;
                 launches += 1;
-                kprime_used = plan.kprime;
+                kprime_used = plans[s].kprime;
             }
-            const CandLists &L = imported ? *imported : c->lists;
-            CU(c, cudaEventRecord(c->ev[1], st));
-            CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, (int32_t *)c->fail_rows.p, fail_count,
-                                 pre.thr, cand_counter, error_flag, nullptr, nullptr, range, st));
-            CU(c, cudaEventRecord(c->ev[2], st));
-            CU(c, launch_exact_scan(img, chk, c->px, rp, (int32_t *)c->fail_rows.p, fail_count, 0, out, error_flag, range, &pre, st));
-            CU(c, cudaEventRecord(c->ev[3], st));
+            CU(c, cudaEventRecord(ev[1], st));
+            if (s == 0 && c->resc_wait) {  // the exact rescoring reads the fp32 master rows: mmalign_rescore_after
+                CU(c, cudaStreamWaitEvent(st, c->resc_wait, 0));
+                c->resc_wait = nullptr;
+            }
+            int32_t *fail_rows = (int32_t *)c->fail_rows.p + r0;
+            pre.thr = (unsigned long long *)c->fail_thr.p + r0; pre.buf = c->scan_buf.p; pre.cnt = (int32_t *)c->scan_cnt.p;
+            CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, fail_rows, slab_fail + s, pre.thr,
+                                 cand_counter, error_flag, nullptr, nullptr, range, st));
+            CU(c, cudaEventRecord(ev[2], st));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, fail_rows, slab_fail + s, 0, out, error_flag, range, &pre, st));
             launches += 3;
         }
+        CU(c, cudaEventRecord(ev[3], st));
     }
-    tr.mark("launch scoring");
+    c->lists_valid = false;  // (the context's lists cover the last slab only)
+    tr.mark("queued scoring");
     // ---- metric sums
     if (want_sums) {
         CU(c, c->metrics_scratch.reserve(metrics_scratch_bytes(rp.S, rp.n_k)));
@@ -531,34 +867,48 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
                                     d_rr, d_sim, c->metrics_scratch.p, st));
         launches += 2;
     }
-    CU(c, cudaEventRecord(c->ev[4], st));
-    // ---- status, stats
-    struct { int32_t fail; int32_t pad; unsigned long long cand; int32_t err; } h = {};
-    CU(c, cudaMemcpyAsync(&h, c->small.p, 24, cudaMemcpyDeviceToHost, st));
-    CU(c, cudaStreamSynchronize(st));
-    tr.mark("kernels done");
-    if (h.err) { extra.release(); return fail(c, MMALIGN_ELIMIT, "an image has more than 512 same-page chunks (capacity limit of this build)"); }
-    if (prm->path == MMALIGN_PATH_FUSED && h.fail > 0) {
-        extra.release();
-        return fail(c, MMALIGN_ELIMIT, "%d rows were not certified by the fused path (MMALIGN_PATH_FUSED forbids the exact rescan)", h.fail);
-    }
-    if (d_np) CU(c, cudaMemcpyAsync(d_np, &P, sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    if (d_stats) {
-        float t_fused = 0.f, t_resc = 0.f, t_scan = 0.f;
-        if (fused_launches || imported) {
-            if (fused_launches) cudaEventElapsedTime(&t_fused, c->ev[0], c->ev[1]);
-            cudaEventElapsedTime(&t_resc, c->ev[1], c->ev[2]);
-            cudaEventElapsedTime(&t_scan, c->ev[2], c->ev[3]);
+    // ---- results of the slabs travel while later slabs compute
+    const bool stream_out = sg.any_large();
+    if (stream_out) {
+        for (int s = 0; s < n_slabs; ++s) {
+            CU(c, cudaStreamWaitEvent(c->s_out, c->ev_slab[4 * (size_t)s + 3], 0));
+            if ((rc = sg.copy_slab(c->s_out, bounds[s] - row0, bounds[s + 1] - row0, N, poff[s] - pair0, poff[s + 1] - pair0, P))) return rc;
         }
-        const int64_t stats[8] = {h.fail, (int64_t)h.cand, imported ? 1 : fused_launches, launches + (imported ? 2 : 0), kprime_used,
-                                  imported ? c->last_fused_us : (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f),
-                                  (int64_t)(t_scan * 1000.f)};
-        CU(c, cudaMemcpyAsync(d_stats, stats, sizeof stats, cudaMemcpyHostToDevice, st));
     }
-    if ((rc = sg.copy_back())) { extra.release(); return rc; }
+    // ---- status, stats
+    struct { int32_t fail; int32_t pad; unsigned long long cand; int32_t err; int32_t pad2; unsigned long long viol; } h = {};
+    std::vector<int32_t> h_fail((size_t)(n_slabs > 0 ? n_slabs : 1), 0);
+    CU(c, cudaMemcpyAsync(&h, c->small.p, 32, cudaMemcpyDeviceToHost, st));
+    if (n_slabs > 0) CU(c, cudaMemcpyAsync(h_fail.data(), slab_fail, sizeof(int32_t) * n_slabs, cudaMemcpyDeviceToHost, st));
+    if ((rc = sg.copy_back(st, true))) { extra.release(); return rc; }
     CU(c, cudaStreamSynchronize(st));
+    if (stream_out) CU(c, cudaStreamSynchronize(c->s_out));
+    tr.mark("kernels + copies done");
     extra.release();
-    tr.mark("copy back");
+    int64_t n_fail = 0;
+    for (int s = 0; s < n_slabs; ++s) n_fail += h_fail[s];
+    if (h.err) return fail(c, MMALIGN_ELIMIT, "an image has more than 512 same-page chunks (capacity limit of this build)");
+    if (prm->path == MMALIGN_PATH_FUSED && n_fail > 0)
+        return fail(c, MMALIGN_ELIMIT, "%lld rows were not certified by the fused path (MMALIGN_PATH_FUSED forbids the exact rescan)", (long long)n_fail);
+    if (uo->num_pairs) CU(c, cudaMemcpy(uo->num_pairs, &P, sizeof(int64_t), cudaMemcpyDefault));
+    if (uo->stats) {
+        double t_fused = 0.0, t_resc = 0.0, t_scan = 0.0;
+        if (fused_path) {
+            for (int s = 0; s < n_slabs; ++s) {
+                float a = 0.f, b = 0.f, d = 0.f;
+                const cudaEvent_t *ev = &c->ev_slab[4 * (size_t)s];
+                if (fused_launches) cudaEventElapsedTime(&a, ev[0], ev[1]);
+                cudaEventElapsedTime(&b, ev[1], ev[2]);
+                cudaEventElapsedTime(&d, ev[2], ev[3]);
+                t_fused += a; t_resc += b; t_scan += d;
+            }
+        }
+        const int64_t stats[16] = {n_fail, (int64_t)h.cand, imported ? 1 : fused_launches, launches + (imported ? 2 : 0), kprime_used,
+                                   imported ? c->last_fused_us : (int64_t)(t_fused * 1000.0), (int64_t)(t_resc * 1000.0),
+                                   (int64_t)(t_scan * 1000.0), (int64_t)h.viol, n_slabs};
+        CU(c, cudaMemcpy(uo->stats, stats, sizeof stats, cudaMemcpyDefault));
+    }
+    tr.mark("status");
     return MMALIGN_OK;
 }
 
@@ -603,7 +953,7 @@ extern "C" int mmalign_num_pairs_range(mmalign_ctx *c, int64_t row0, int64_t row
     int64_t r0, n;
     if ((rc = resolve_range(c, row0, rows, c->img.s.n, "rows", &r0, &n))) return rc;
     RowRange range;
-    if ((rc = make_row_range(c, r0, n, 0, &range))) return rc;
+    if ((rc = make_row_range(c, r0, n, &range))) return rc;
     *num_pairs = range.P_out;
     return MMALIGN_OK;
 }
@@ -654,6 +1004,7 @@ extern "C" int mmalign_fused_pass(mmalign_ctx *c, const mmalign_params *prm, flo
     if ((rc = sg.commit())) return rc;
     c->last_fused_us = 0;
     if (N == 0) return MMALIGN_OK;
+    if ((rc = wait_tables(c, st))) return rc;
     if (n_cols == 0) {  // an empty shard holds every one of its (zero) columns
         if (d_tau) {
             std::vector<float> inf((size_t)N, -INFINITY);
@@ -707,8 +1058,14 @@ extern "C" int mmalign_rescore_pass(mmalign_ctx *c, const mmalign_params *prm, c
     if (!is_device_ptr(tau_global) || !is_device_ptr(cert_count)) return fail(c, MMALIGN_EINVAL, "mmalign_rescore_pass: tau_global and cert_count must be device pointers");
     const int64_t N = c->img.s.n, M = c->chk.s.n, P = c->px.P;
     if (M > 0 && !c->lists_valid) return fail(c, MMALIGN_ESTATE, "mmalign_fused_pass must run before mmalign_rescore_pass");
+    // the lists' columns are relative to the range of the fused pass; this pass reads them as table rows
+    if (M > 0 && (c->lists_col0 != 0 || c->lists_cols != M || c->lists_rows != N))
+        return fail(c, MMALIGN_ESTATE, "mmalign_rescore_pass needs lists of a fused pass over the whole tables (the last one covered "
+                    "%lld rows x columns [%lld, +%lld)); lists of a column shard go through mmalign_export_lists",
+                    (long long)c->lists_rows, (long long)c->lists_col0, (long long)c->lists_cols);
     cudaStream_t st = (cudaStream_t)stream;
     CU(c, cudaSetDevice(c->device));
+    if ((rc = wait_tables(c, st))) return rc;
     Outputs out;
     outputs_from(uo, &out);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
@@ -734,7 +1091,7 @@ extern "C" int mmalign_rescore_pass(mmalign_ctx *c, const mmalign_params *prm, c
     if (uo->stats && !is_device_ptr(uo->stats)) {
         float t_fused = 0.f, t_resc = 0.f;
         if (M > 0) { cudaEventElapsedTime(&t_fused, c->ev[0], c->ev[1]); cudaEventElapsedTime(&t_resc, c->ev[1], c->ev[2]); }
-        const int64_t stats[8] = {0, (int64_t)h.cand, M > 0, 4, c->lists.kprime, (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f), 0};
+        const int64_t stats[16] = {0, (int64_t)h.cand, M > 0, 4, c->lists.kprime, (int64_t)(t_fused * 1000.f), (int64_t)(t_resc * 1000.f), 0};
         memcpy(uo->stats, stats, sizeof stats);
     }
     return MMALIGN_OK;
@@ -753,6 +1110,7 @@ extern "C" int mmalign_rescan_rows(mmalign_ctx *c, const mmalign_params *prm, co
     if (!is_device_ptr(rows)) return fail(c, MMALIGN_EINVAL, "mmalign_rescan_rows: rows must be a device pointer");
     cudaStream_t st = (cudaStream_t)stream;
     CU(c, cudaSetDevice(c->device));
+    if ((rc = wait_tables(c, st))) return rc;
     Outputs out;
     outputs_from(uo, &out);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
@@ -770,6 +1128,7 @@ extern "C" int mmalign_chunk_err_max(mmalign_ctx *c, float *err_max)
     if (!c || !err_max) return fail(c, MMALIGN_EINVAL, "mmalign_chunk_err_max: NULL argument");
     if (!c->chk.ready) return fail(c, MMALIGN_ESTATE, "set_chunks must be called first");
     CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->s_prep));
     CU(c, cudaMemcpy(err_max, c->chk.err_max, sizeof(float), cudaMemcpyDeviceToHost));
     return MMALIGN_OK;
 }
@@ -927,6 +1286,7 @@ extern "C" int mmalign_debug_scores(mmalign_ctx *c, float *out, void *stream)
     if ((double)img.n * (double)chk.n > 2.7e8) return fail(c, MMALIGN_ELIMIT, "mmalign_debug_scores is for small problems (N*M <= 2.7e8)");
     cudaStream_t st = (cudaStream_t)stream;
     CU(c, cudaSetDevice(c->device));
+    if ((rc = wait_tables(c, st))) return rc;
     FusedPlan plan;
     if (fused_plan(img.n, chk.n, img.D, 10, 0, c->sm_count, 1, &plan)) return fail(c, MMALIGN_ELIMIT, "no fused plan");
     Stager sg{c, st};
@@ -936,6 +1296,21 @@ extern "C" int mmalign_debug_scores(mmalign_ctx *c, float *out, void *stream)
     CandLists L;
     CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, L, d, st));
     if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+extern "C" int mmalign_debug_operands(mmalign_ctx *c, void *img_bf16, void *chk_bf16, void *stream)
+{
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "mmalign_debug_operands: ctx is NULL");
+    if (!c->img.ready || !c->chk.ready) return fail(c, MMALIGN_ESTATE, "set_images and set_chunks must be called first");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    int rc;
+    if ((rc = wait_tables(c, st))) return rc;
+    const Side &img = c->img.s, &chk = c->chk.s;
+    if (img_bf16 && img.n > 0) CU(c, cudaMemcpyAsync(img_bf16, img.emb_bf16, (size_t)img.n * img.D * 2, cudaMemcpyDefault, st));
+    if (chk_bf16 && chk.n > 0) CU(c, cudaMemcpyAsync(chk_bf16, chk.emb_bf16, (size_t)chk.n * chk.D * 2, cudaMemcpyDefault, st));
     CU(c, cudaStreamSynchronize(st));
     return MMALIGN_OK;
 }

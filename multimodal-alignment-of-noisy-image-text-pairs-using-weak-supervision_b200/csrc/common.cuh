@@ -85,7 +85,8 @@ struct CandLists {
 
 struct RowRange {             // image rows a rescoring launch ranks (0, 0 = all); outputs are indexed relative to it
     int64_t row0 = 0, n_rows = 0;
-    int64_t pair0 = 0, P_out = 0;  // offsets[row0], offsets[row0 + n_rows] - offsets[row0]
+    int64_t pair0 = 0, P_out = 0;  // window of the per-pair outputs: first pair, number of pairs
+    int64_t o_row0 = 0, o_rows = 0; // window of the per-row outputs (0, 0 = the rows themselves)
 };
 
 // ---------------------------------------------------------------------------
@@ -251,7 +252,8 @@ __device__ __forceinline__ long long term_hits(const uint64_t *chunk_terms, cons
 // Launchers (each returns the cudaError_t of its launch)
 // ---------------------------------------------------------------------------
 // prep.cu
-cudaError_t launch_prep(Side &side, cudaStream_t st);
+int sm_count();  // SMs of the current device
+cudaError_t launch_prep(const Side &side, int64_t row0, int64_t rows, int sm_count, cudaStream_t st);
 cudaError_t reduce_max_float(const float *x, int64_t n, float *out, cudaStream_t st);
 size_t pair_index_scratch_bytes(int64_t N, int64_t M);
 cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, void *scratch, size_t scratch_bytes,

@@ -186,7 +186,7 @@ cudaError_t launch_term_bitsets(const uint8_t *text, const int64_t *text_off, in
     cudaError_t e = cudaFuncSetAttribute(term_bitsets_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t grid = (m + kIngestWarps - 1) / kIngestWarps;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     term_bitsets_kernel<<<(unsigned)grid, kIngestThreads, smem, st>>>(text, text_off, m, tt, term_words, always, bits);
     return cudaGetLastError();
 }

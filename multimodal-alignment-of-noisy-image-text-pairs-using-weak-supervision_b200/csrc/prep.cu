@@ -14,6 +14,20 @@
 
 namespace mma {
 
+// SM count of the current device (grids are sized in multiples of it); cached per device
+int sm_count()
+{
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float *__restrict__ emb, int64_t n, int D, __nv_bfloat16 *__restrict__ out,
                  float *__restrict__ norm2, float *__restrict__ err)
@@ -50,12 +64,14 @@ prep_rows_kernel(const float *__restrict__ emb, int64_t n, int D, __nv_bfloat16 
     }
 }
 
-cudaError_t launch_prep(Side &s, cudaStream_t st)
+// K0 of rows [row0, row0 + rows) of a side (a piece of an upload, or a query slab)
+cudaError_t launch_prep(const Side &s, int64_t row0, int64_t rows, int sm_count, cudaStream_t st)
 {
-    if (s.n == 0) return cudaSuccess;
-    int64_t blocks = (s.n + 7) / 8;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(s.emb, s.n, s.D, s.emb_bf16, s.norm2, s.err);
+    if (rows <= 0) return cudaSuccess;
+    int64_t blocks = (rows + 7) / 8;
+    if (blocks > (int64_t)sm_count * 16) blocks = (int64_t)sm_count * 16;
+    prep_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(s.emb + row0 * s.D, rows, s.D, s.emb_bf16 + row0 * s.D,
+                                                       s.norm2 + row0, s.err + row0);
     return cudaGetLastError();
 }
 
@@ -83,7 +99,7 @@ cudaError_t reduce_max_float(const float *x, int64_t n, float *out, cudaStream_t
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float), st);
     if (e != cudaSuccess || n == 0) return e;
     int64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 4) blocks = 148 * 4;
+    if (blocks > (int64_t)sm_count() * 4) blocks = (int64_t)sm_count() * 4;
     max_float_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, n, out);
     return cudaGetLastError();
 }
@@ -152,11 +168,11 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, vo
 #define CK(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
     CK(cudaMemsetAsync(counts + N + 1, 0, sizeof(int64_t), st));
     if (M > 0) {
-        iota_kernel<<<(unsigned)((M + 255) / 256 > 1184 ? 1184 : (M + 255) / 256), 256, 0, st>>>(iota, M);
+        iota_kernel<<<(unsigned)((M + 255) / 256 > sm_count() * 8 ? sm_count() * 8 : (M + 255) / 256), 256, 0, st>>>(iota, M);
         CK(cudaGetLastError());
         CK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, chk.key, sorted_key, iota, px.sorted_chunk, (int)M, 0, 64, st));
     }
-    page_range_kernel<<<(unsigned)((N + 256) / 256 > 1184 ? 1184 : (N + 256) / 256), 256, 0, st>>>(
+    page_range_kernel<<<(unsigned)((N + 256) / 256 > sm_count() * 8 ? sm_count() * 8 : (N + 256) / 256), 256, 0, st>>>(
         img.key, N, sorted_key, M, px.sp_start, counts, reinterpret_cast<unsigned long long *>(counts + N + 1));
     CK(cudaGetLastError());
     CK(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts, px.offsets, (int)(N + 1), st));

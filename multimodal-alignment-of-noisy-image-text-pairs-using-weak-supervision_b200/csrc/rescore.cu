@@ -100,11 +100,15 @@ struct RowArgs {
     RunParams rp;
     Outputs out;
     int32_t *error_flag;  // set to 1 when a capacity limit is hit
+    unsigned long long *viol_counter;  // rows whose re-scored candidates broke |exact - approximate| <= eps (may be null)
     int ent_cap, sp_cap;  // shared-memory capacities of this launch (>= 256 / >= 8)
     bool need_lex, need_pos;  // some requested schema uses the lexical / positional term
     // rows [row0, row0 + n_rows) are ranked; per-row outputs are indexed by (i - row0), per-pair outputs by
     // (pair - offsets[row0]) and sized P_out = offsets[row0 + n_rows] - offsets[row0]
     int64_t row0, n_rows, pair0, P_out;
+    // window of the per-row outputs: indexed by (i - o_row0) with o_rows rows per schema.  Equal to (row0, n_rows)
+    // unless a run is cut into slabs that share one set of output arrays (api.cu: the slab pipeline).
+    int64_t o_row0, o_rows;
 };
 
 __device__ __forceinline__ int next_pow2(int n)
@@ -318,15 +322,18 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
                            const float *approx, int n_approx, int32_t *cert_count = nullptr)
 {
     __shared__ double s_kth;
-    __shared__ int s_cert, s_bad;
+    __shared__ int s_cert, s_bad, s_viol;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_viol = 0;  // (published by the barrier below)
     const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
     const int64_t p0 = A.offsets[i] - A.pair0;  // position of the row's first pair in the per-pair outputs
-    const int64_t io = i - A.row0;               // position of the row in the per-row outputs
+    const int64_t io = i - A.o_row0;             // position of the row in the per-row outputs
     const int n = n_ca + c;
     const int d4 = A.D >> 2;
     const RunParams &rp = A.rp;
     const bool certify = bound > -CUDART_INF;
+    // depth the lists must be final to: the top-K lists, or the full exact depth when the caller takes deep_idx
+    const int kcert = A.out.deep_idx ? rp.kneed : rp.kmax;
     // exact cosine of the candidates
     const float na = A.img_n2[i];
     for (int e = c + warp; e < n; e += 2 * kWarps) {
@@ -344,10 +351,15 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         sm.cosv[e] = x;
         Key k; k.k = ord64(x); k.j = sm.cols[e]; k.e = e;
         sm.buf[e - c] = k;
+        // The certificate rests on |exact - approximate| <= eps.  Every re-scored candidate tests that bound: a
+        // violation (an input the error model does not cover) withdraws the row's certificate, and the row is
+        // ranked by the exact scan instead.
+        if (approx && certify && !(fabs(x - (double)approx[e - c]) <= eps)) s_viol = 1;
     }
     __syncthreads();
     sort_keys(sm.buf, n_ca);
-    bool ok = true;
+    bool ok = !s_viol;
+    if (s_viol && threadIdx.x == 0 && A.viol_counter) atomicAdd(A.viol_counter, 1ull);
     for (int si = 0; si < rp.S; ++si) {
         const int s = rp.schema[si];
         if (threadIdx.x == 0) { s_kth = -CUDART_INF; s_cert = 0; s_bad = 0; }
@@ -359,7 +371,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
             if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P_out + p0 + p] = sc;
         }
         __syncthreads();
-        const int64_t o_top = ((int64_t)si * A.n_rows + io) * rp.kmax, o_deep = ((int64_t)si * A.n_rows + io) * rp.kneed;
+        const int64_t o_top = ((int64_t)si * A.o_rows + io) * rp.kmax, o_deep = ((int64_t)si * A.o_rows + io) * rp.kneed;
         // final position of an element = its position in its own sorted list + elements of the other list before it
         for (int t = threadIdx.x; t < c + min(n_ca, rp.kneed); t += kThreads) {
             unsigned long long k;
@@ -397,7 +409,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
                 A.out.deep_idx[o_deep + pos] = (int64_t)j + rp.col_offset;
                 A.out.deep_score[o_deep + pos] = sc;
             }
-            if (pos == rp.kmax - 1) s_kth = sc;
+            if (pos == kcert - 1) s_kth = sc;
             if (cert_count && sc > bound) atomicAdd(&s_cert, 1);
         }
         for (int r = n + threadIdx.x; r < rp.kneed; r += kThreads) {  // fewer entries than the lists are wide
@@ -408,7 +420,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         if (certify && !cert_count) ok = ok && !s_bad && (s_kth > bound);
         // fully sharded runs certify globally: this rank's entries that are provably above every column it left out
         // (counted among its best kneed + same-page entries, which is all the global test needs)
-        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.n_rows + io] = certify ? s_cert : rp.kneed;
+        if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.o_rows + io] = certify ? s_cert : rp.kneed;
         __syncthreads();
     }
     return ok;
@@ -541,7 +553,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                     __syncthreads();
                     if (n_all >= rp.kneed) thr = ord64((double)sm.approx[rp.kneed - 1] - eps);
                     int n_ca = n_all;
-                    if (!tau_global) {
+                    if (!tau_global && !A.out.deep_idx) {  // (deep lists are final to kneed entries: no pruning)
                         // lowest line that needs exact scores
                         if (threadIdx.x == 0 && n_all >= rp.kmax)
                             atomicMin(&s_theta, ord64((double)sm.approx[rp.kmax - 1] - 2.0 * eps));
@@ -742,11 +754,14 @@ static RowArgs make_args(const Side &img, const Side &chk, const PairIndex &px, 
     A.N = img.n; A.M = chk.n; A.D = img.D; A.term_words = chk.term_words;
     A.offsets = px.offsets; A.sorted_chunk = px.sorted_chunk; A.sp_start = px.sp_start; A.P = px.P;
     A.rp = rp; A.out = out; A.error_flag = error_flag;
+    A.viol_counter = error_flag ? reinterpret_cast<unsigned long long *>(error_flag + 2) : nullptr;  // api.cu: `small` layout
     A.ent_cap = kEntCapMax; A.sp_cap = kSpCapMax;
     A.row0 = 0; A.n_rows = img.n; A.pair0 = 0; A.P_out = px.P;
     if (range && range->n_rows >= 0 && !(range->row0 == 0 && range->n_rows == 0)) {
         A.row0 = range->row0; A.n_rows = range->n_rows; A.pair0 = range->pair0; A.P_out = range->P_out;
     }
+    A.o_row0 = A.row0; A.o_rows = A.n_rows;
+    if (range && range->o_rows > 0) { A.o_row0 = range->o_row0; A.o_rows = range->o_rows; }
     A.need_lex = A.need_pos = false;
     for (int q = 0; q < rp.S; ++q) {
         A.need_lex = A.need_lex || rp.schema[q] == 1 || rp.schema[q] == 3;
@@ -771,7 +786,7 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     const size_t smem = row_smem_bytes(img.D, A.ent_cap, A.sp_cap);
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int64_t grid = A.n_rows < 148 * 16 ? A.n_rows : 148 * 16;
+    int64_t grid = A.n_rows < (int64_t)sm_count() * 16 ? A.n_rows : (int64_t)sm_count() * 16;
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
                                                            fail_count, fail_thr, cand_counter, tau_global, cert_count);
     return cudaGetLastError();
@@ -792,12 +807,12 @@ cudaError_t launch_exact_scan(const Side &img, const Side &chk, const PairIndex 
     if (two_stage) {
         e = cudaMemsetAsync(pre->cnt, 0, sizeof(int32_t) * kScanSlots, st);
         if (e != cudaSuccess) return e;
-        exact_prefilter_kernel<<<148 * 4, kPreThreads, (size_t)img.D * sizeof(float), st>>>(
+        exact_prefilter_kernel<<<(unsigned)(sm_count() * 4), kPreThreads, (size_t)img.D * sizeof(float), st>>>(
             A, rows, n_rows_dev, pre->thr, reinterpret_cast<Key *>(pre->buf), pre->cnt, kScanCap, kScanSlots);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    int64_t grid = 148 * 4;
+    int64_t grid = (int64_t)sm_count() * 4;
     if (!n_rows_dev && n_rows_host < grid) grid = n_rows_host;
     exact_scan_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, rows, n_rows_dev, n_rows_host,
                                                               two_stage ? reinterpret_cast<const Key *>(pre->buf) : nullptr,
@@ -840,7 +855,7 @@ cudaError_t launch_alignments(const Side &img, const Side &chk, const PairIndex 
     Outputs out = {};
     const RowArgs A = make_args(img, chk, px, rp, out, nullptr);
     int64_t grid = (px.P + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     alignments_kernel<<<(unsigned)grid, 256, 0, st>>>(A, schema, n_terms, raw, rec);
     return cudaGetLastError();
 }
@@ -910,7 +925,7 @@ cudaError_t launch_export_lists(const CandLists &L, int64_t N, int n_dest, int64
 {
     const int64_t total = (int64_t)n_dest * slab_rows;
     int64_t grid = (total * 32 + 255) / 256;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
     export_lists_kernel<<<(unsigned)grid, 256, 0, st>>>(L, N, total, stride, col_offset, keys, count, tau);
     return cudaGetLastError();
 }
@@ -919,7 +934,7 @@ cudaError_t launch_row_tau(const CandLists &L, int64_t N, float *tau_row, cudaSt
 {
     if (N == 0) return cudaSuccess;
     int64_t grid = (N + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     row_tau_kernel<<<(unsigned)grid, 256, 0, st>>>(L, N, tau_row);
     return cudaGetLastError();
 }
@@ -929,7 +944,7 @@ cudaError_t launch_pair_chunk(const PairIndex &px, int64_t N, int64_t col_offset
 {
     if (N == 0 || px.P == 0) return cudaSuccess;
     int64_t grid = (N * 32 + 255) / 256;
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     pair_chunk_kernel<<<(unsigned)grid, 256, 0, st>>>(px.offsets, px.sorted_chunk, px.sp_start, N, col_offset,
                                                       pair_chunk);
     return cudaGetLastError();
@@ -1077,7 +1092,7 @@ cudaError_t launch_merge_topk(const int64_t *in_idx, const double *in_score, int
 {
     if (n_lists == 0) return cudaSuccess;
     int64_t grid = (n_lists + 127) / 128;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
     merge_topk_kernel<<<(unsigned)grid, 128, 0, st>>>(in_idx, in_score, G, n_lists, K, out_idx, out_score);
     return cudaGetLastError();
 }
@@ -1114,7 +1129,7 @@ cudaError_t launch_count_beating(const int64_t *deep_idx, const double *deep_sco
 {
     if (n_q == 0) return cudaSuccess;
     int64_t grid = (n_q * S + 255) / 256;
-    if (grid > 148 * 16) grid = 148 * 16;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
     count_beating_kernel<<<(unsigned)grid, 256, 0, st>>>(deep_idx, deep_score, N, S, K, n_q, q_image, q_chunk,
                                                          q_score, counts);
     return cudaGetLastError();

@@ -26,6 +26,12 @@ too large to replicate).  Images replicated, three exchanges:
         -> all-reduce(sum) of the counts            (global rank of every true pair)
   3. all-reduce(sum) of the metric sums from mmalign_reduce_metrics.
 
+ShardedScorer with contraction="rows" (what "auto" picks when every rank's query slab fills its GPU): rank g
+contracts and re-scores its own query slab against the whole chunk table, so no candidate list travels.  Each
+rank prepares (K0) the 1/G of the chunk table it ingests; the prepared bf16 operands, norms and page keys are
+all-gathered first and the contraction starts, while the fp32 master rows follow on a side stream for the
+exact rescoring (mmalign_prep_rows / mmalign_set_chunks_prepared / mmalign_rescore_after).
+
 With world size 1 no collective runs.
 """
 from __future__ import annotations
@@ -63,7 +69,7 @@ def slab_range(N: int, world: int, rank: int):
 
 
 class ShardedScorer:
-    """Contraction sharded by chunk columns, rescoring by query rows (module docstring)."""
+    """Contraction sharded by chunk columns or by query rows, rescoring by query rows (module docstring)."""
     FIELDS = ("emb", "key", "bbox", "terms")
 
     def __init__(self, engine, world: int = 1, rank: int = 0, device=None, dist=None, contraction: str = "auto"):
@@ -71,8 +77,8 @@ class ShardedScorer:
         candidate lists are exchanged (all-to-all).  contraction="rows": rank g contracts its own query slab against
         the whole chunk table -- no list exchange, and the lists of a row warm up 2*splits times instead of
         2*splits*G times (the fused kernel's per-list warm-up is the one cost that grows with G in the column
-        layout: measured 139 -> 126.5 ms per step at G=8, config 5).  "auto" (default): rows when every slab fills
-        the GPU on its own (>= 148 row blocks of 128 queries), columns for query-poor shapes."""
+        layout).  "auto" (default): rows when every slab fills the GPU on its own (>= 148 row blocks of 128
+        queries), columns for query-poor shapes."""
         self.eng, self.world, self.rank, self.device = engine, world, rank, device
         if contraction not in ("auto", "columns", "rows"):
             raise ValueError("contraction must be 'auto', 'columns' or 'rows'")
@@ -81,45 +87,123 @@ class ShardedScorer:
             import torch.distributed as dist
         self.dist = dist
         self._full = {}
+        self._side = None
         self.N = self.M = 0
+        self.mode = "rows"
         self.MAX = getattr(getattr(dist, "ReduceOp", None), "MAX", "max") if dist is not None else "max"
 
+    def _mode(self, N):
+        if self.contraction != "auto":
+            return self.contraction
+        return "rows" if slab_size(N, self.world) >= 148 * 128 else "columns"
+
     # -- ingest ---------------------------------------------------------------------------------------
+    @staticmethod
+    def _as_tensor(x):
+        import torch
+        if x is None:
+            return None
+        if not type(x).__module__.startswith("torch"):
+            x = torch.from_numpy(x.view("int64") if x.dtype.kind == "u" else x)
+        return x.view(torch.int64) if x.dtype == torch.uint64 else x
+
+    def _buffer(self, name, shape, dtype, like):
+        import torch
+        buf = self._full.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype, device=self.device if self.device is not None else like.device)
+            self._full[name] = buf
+        return buf
+
+    def _gather(self, buf, slot):
+        import torch
+        if buf.dtype == torch.int16:  # bf16 bit patterns travel as bytes (gloo has no 16-bit integer type)
+            buf, slot = buf.view(torch.uint8), slot.view(torch.uint8)
+        if hasattr(self.dist, "all_gather_into_tensor"):
+            self.dist.all_gather_into_tensor(buf, slot)
+        else:
+            parts = [torch.empty_like(slot) for _ in range(self.world)]
+            self.dist.all_gather(parts, slot.contiguous())
+            per = slot.shape[0]
+            for g, p_ in enumerate(parts):
+                buf[g * per:(g + 1) * per].copy_(p_)
+
     def _replicate(self, side, shard, total, per):
         """All-gather of one table: every rank contributes `per` rows (the last ranks fewer; their slots are
         padded) into persistent [G * per, ...] buffers.  Returns the dict of full tables cut to `total` rows."""
-        import torch
         G, out = self.world, {}
         for f in self.FIELDS:
-            x = shard.get(f)
+            x = self._as_tensor(shard.get(f))
             if x is None:
                 out[f] = None
                 continue
-            if not type(x).__module__.startswith("torch"):
-                x = torch.from_numpy(x.view("int64") if x.dtype.kind == "u" else x)
-            if x.dtype == torch.uint64:
-                x = x.view(torch.int64)
-            shape = (G * per,) + tuple(x.shape[1:])
-            buf = self._full.get((side, f))
-            if buf is None or buf.shape != shape or buf.dtype != x.dtype:
-                buf = torch.empty(shape, dtype=x.dtype, device=self.device if self.device is not None else x.device)
-                self._full[(side, f)] = buf
+            buf = self._buffer((side, f), (G * per,) + tuple(x.shape[1:]), x.dtype, x)
             slot = buf[self.rank * per:(self.rank + 1) * per]
             slot[:x.shape[0]].copy_(x, non_blocking=True)  # host->device for pinned host shards
-            if hasattr(self.dist, "all_gather_into_tensor"):
-                self.dist.all_gather_into_tensor(buf, slot)
-            else:
-                parts = [torch.empty_like(slot) for _ in range(G)]
-                self.dist.all_gather(parts, slot.contiguous())
-                for g, p_ in enumerate(parts):
-                    buf[g * per:(g + 1) * per].copy_(p_)
+            self._gather(buf, slot)
             out[f] = buf[:total]
         return out
+
+    def _load_rows(self, img, chk, N, M, n_terms):
+        """Query-row layout: the rank keeps its own image slab; the chunk table is prepared where it is ingested
+        (K0 of 1/G of the rows on every rank) and the PREPARED operands travel first -- bf16 rows, norms, rounding
+        errors and page keys are all the contraction and the pair index need -- while the fp32 master rows, boxes
+        and term sets, which only the exact rescoring reads, follow on a side stream beside the contraction."""
+        import torch
+        G, eng = self.world, self.eng
+        per = -(-M // G) if M else 1
+        x = {f: self._as_tensor(chk.get(f)) for f in self.FIELDS}
+        m, D = int(x["emb"].shape[0]), int(x["emb"].shape[1])
+        cuda = self.device is not None and torch.device(self.device).type == "cuda"
+        full, slot = {}, {}
+        for f in self.FIELDS:
+            if x[f] is None:
+                full[f] = None
+                continue
+            full[f] = self._buffer(("chk", f), (G * per,) + tuple(x[f].shape[1:]), x[f].dtype, x[f])
+            slot[f] = full[f][self.rank * per:(self.rank + 1) * per]
+            slot[f][:m].copy_(x[f], non_blocking=True)
+        like = x["emb"]
+        full["bf16"] = self._buffer(("chk", "bf16"), (G * per, D), torch.int16, like)
+        full["norm2"] = self._buffer(("chk", "norm2"), (G * per,), torch.float32, like)
+        full["err"] = self._buffer(("chk", "err"), (G * per,), torch.float32, like)
+        for f in ("bf16", "norm2", "err"):
+            slot[f] = full[f][self.rank * per:(self.rank + 1) * per]
+        st = torch.cuda.current_stream().cuda_stream if cuda else None
+        if m:
+            eng.prep_rows(slot["emb"][:m], slot["bf16"][:m], slot["norm2"][:m], slot["err"][:m], stream=st)
+        for f in ("bf16", "norm2", "err", "key"):     # what the contraction and the pair index read
+            self._gather(full[f], slot[f])
+        event = None
+        if cuda:                                      # what only the exact rescoring reads: beside the contraction
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                for f in ("emb", "bbox", "terms"):
+                    if full[f] is not None:
+                        self._gather(full[f], slot[f])
+                event = torch.cuda.Event()
+                event.record(self._side)
+        else:
+            for f in ("emb", "bbox", "terms"):
+                if full[f] is not None:
+                    self._gather(full[f], slot[f])
+        cutm = lambda t: None if t is None else t[:M]
+        eng.set_chunks_prepared(cutm(full["emb"]), cutm(full["key"]), cutm(full["bbox"]), cutm(full["terms"]),
+                                cutm(full["bf16"]), cutm(full["norm2"]), cutm(full["err"]), n_terms=n_terms, stream=st)
+        if event is not None:
+            eng.rescore_after(event)
+        eng.set_images(img["emb"], img["key"], img.get("bbox"), img.get("terms"))
 
     def load(self, img, chk, *, N: int, M: int, n_terms: int = 0):
         """img: image rows slab_range(N, world, rank); chk: chunk rows shard_range(M, world, rank) -- dicts of
         emb / key / bbox / terms (CUDA or pinned host torch tensors, or numpy arrays)."""
         self.N, self.M = int(N), int(M)
+        self.mode = self._mode(N) if self.world > 1 else "rows"
+        if self.world > 1 and self.mode == "rows":
+            self._load_rows(img, chk, N, M, n_terms)
+            return
         if self.world > 1:
             img = self._replicate("img", img, N, slab_size(N, self.world))
             chk = self._replicate("chk", chk, M, -(-M // self.world) if M else 1)
@@ -128,13 +212,13 @@ class ShardedScorer:
 
     # -- one step --------------------------------------------------------------------------------------
     def run(self, *, schemas, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), kprime=0, host_outputs=False,
-            candidates="all", path="auto", eps_scale=0.0):
+            candidates="all", path="auto", eps_scale=0.0, pipeline_rows=0):
         eng = self.eng
         kw = dict(candidates=candidates, k_values=k_values, mrr_cutoff=mrr_cutoff, weak_weight=weak_weight,
                   kprime=kprime, path=path, eps_scale=eps_scale)
         out_kw = dict(want=("topk", "pairs", "sums"), device_outputs=not host_outputs, pinned_outputs=host_outputs)
         if self.world == 1:
-            r = eng.run(schemas, **out_kw, **kw)
+            r = eng.run(schemas, pipeline_rows=pipeline_rows, **out_kw, **kw)
             r["topk_row0"] = 0
         else:
             import time
@@ -143,13 +227,11 @@ class ShardedScorer:
             marks = [("start", time.perf_counter())]
 
             def mark(name):
-                if torch.cuda.is_available():
-                    torch.cuda.synchronize()
                 marks.append((name, time.perf_counter()))
             row0, row1 = slab_range(N, G, self.rank)
-            mode = self.contraction if self.contraction != "auto" else ("rows" if slab_size(N, G) >= 148 * 128 else "columns")
-            if mode == "rows":
-                r = eng.run(schemas, slab=(row0, row1 - row0), **out_kw, **kw)
+            mode = self.mode
+            if mode == "rows":  # the engine holds this rank's slab only
+                r = eng.run(schemas, pipeline_rows=pipeline_rows, **out_kw, **kw)
                 mark("fused + rescore slab")
             else:
                 lo, hi = shard_range(M, G, self.rank)

@@ -119,6 +119,34 @@ class AlignmentEngine:
     def set_chunks(self, emb, page_key, bbox=None, terms=None, n_terms: int = 0, col_offset: int = 0):
         self._set("chunks", emb, page_key, bbox, terms, n_terms, col_offset)
 
+    def sync(self):
+        """Waits for the uploads and preparation queued by set_images / set_chunks (mmalign_sync)."""
+        self._check(self._L.mmalign_sync(self._ctx))
+
+    def prep_rows(self, emb, bf16_out, norm2_out, err_out, stream=None):
+        """K0 of device rows into caller-owned device buffers (mmalign_prep_rows); torch CUDA tensors."""
+        n, D = int(emb.shape[0]), int(emb.shape[1])
+        st = None if stream is None else C.c_void_p(int(stream))
+        self._check(self._L.mmalign_prep_rows(self._ctx, emb.data_ptr(), n, D, bf16_out.data_ptr(), norm2_out.data_ptr(),
+                                              err_out.data_ptr(), st))
+
+    def set_chunks_prepared(self, emb, page_key, bbox, terms, bf16, norm2, err, n_terms: int = 0, col_offset: int = 0,
+                            stream=None):
+        """The gathered chunk table with its prepared operands, all CUDA tensors (mmalign_set_chunks_prepared)."""
+        m, D = int(emb.shape[0]), int(emb.shape[1])
+        W = 0 if terms is None else int(terms.shape[1])
+        st = None if stream is None else C.c_void_p(int(stream))
+        self._keep["chunks"] = (emb, page_key, bbox, terms, bf16, norm2, err)
+        self._check(self._L.mmalign_set_chunks_prepared(
+            self._ctx, emb.data_ptr(), page_key.data_ptr(), bbox.data_ptr(), None if terms is None else terms.data_ptr(),
+            bf16.data_ptr(), norm2.data_ptr(), err.data_ptr(), m, D, W, int(n_terms), int(col_offset), st))
+        self.M, self.col_offset = m, int(col_offset)
+
+    def rescore_after(self, event):
+        """The next run's exact rescoring waits for `event` (a torch.cuda.Event): mmalign_rescore_after."""
+        self._keep["resc_event"] = event
+        self._check(self._L.mmalign_rescore_after(self._ctx, C.c_void_p(int(event.cuda_event))))
+
     def num_pairs(self) -> int:
         p = C.c_int64()
         self._check(self._L.mmalign_num_pairs(self._ctx, C.byref(p)))
@@ -150,7 +178,7 @@ class AlignmentEngine:
     # -- scoring ----------------------------------------------------------------
     @staticmethod
     def _params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime, n_ranks=0,
-                shard=None, slab=None, eps_scale=0.0):
+                shard=None, slab=None, eps_scale=0.0, pipeline_rows=0):
         mask = schema_mask(schemas)
         ks = [int(k) for k in k_values]
         prm = _native.Params()
@@ -166,6 +194,7 @@ class AlignmentEngine:
         prm.kprime = int(kprime)
         prm.n_ranks = int(n_ranks)
         prm.eps_scale = float(eps_scale)
+        prm.pipeline_rows = int(pipeline_rows)
         if shard is not None:  # (first chunk row, rows) the fused pass contracts against
             prm.shard_col0, prm.shard_cols = int(shard[0]), int(shard[1])
         if slab is not None:   # (first image row, rows) that are ranked
@@ -175,12 +204,14 @@ class AlignmentEngine:
     def run(self, schemas="vanilla_clip", *, candidates="same_page", k_values: Sequence[int] = (1, 5, 10),
             mrr_cutoff: int = 100, weak_weight=(0.0, 0.0), lam_comb: Optional[float] = None,
             path="auto", kprime: int = 0, want=("topk", "pairs", "sums"), device_outputs=False,
-            pinned_outputs=False, deep=False, stream=None, slab=None, imported=None, eps_scale=0.0):
+            pinned_outputs=False, deep=False, stream=None, slab=None, imported=None, eps_scale=0.0,
+            pipeline_rows=0):
         """slab=(row0, rows): rank only those image rows (outputs are sized by the slab).
         imported=(keys, count, tau): candidate lists received from the ranks' fused passes
-        (mmalign_rescore_slab) instead of running the fused kernel here."""
+        (mmalign_rescore_slab) instead of running the fused kernel here.
+        pipeline_rows: query rows per pipeline slab of mmalign_run (0 = auto, -1 = one slab)."""
         prm, mask, S, ks = self._params(schemas, candidates, k_values, mrr_cutoff, weak_weight, lam_comb, path, kprime,
-                                        slab=slab, eps_scale=eps_scale)
+                                        slab=slab, eps_scale=eps_scale, pipeline_rows=pipeline_rows)
         kmax = max(ks) if ks else 0
         kneed = max(kmax, int(mrr_cutoff))
         if slab is None or tuple(slab) == (0, 0):
@@ -229,7 +260,7 @@ class AlignmentEngine:
         rr = np.zeros(S, np.float64)
         sim = np.zeros(1, np.float64)
         npairs = np.zeros(1, np.int64)
-        stats = np.zeros(8, np.int64)
+        stats = np.zeros(16, np.int64)
         if "sums" in want:
             out.hits, out.rr_sum, out.sim_sum = hits.ctypes.data, rr.ctypes.data, sim.ctypes.data
         out.num_pairs, out.stats = npairs.ctypes.data, stats.ctypes.data
@@ -246,7 +277,7 @@ class AlignmentEngine:
                    stats=dict(rows_rescanned=int(stats[0]), candidates_rescored=int(stats[1]),
                               fused_launches=int(stats[2]), kernel_launches=int(stats[3]),
                               kprime=int(stats[4]), fused_us=int(stats[5]), rescore_us=int(stats[6]),
-                              exact_scan_us=int(stats[7])),
+                              exact_scan_us=int(stats[7]), eps_violations=int(stats[8]), slabs=int(stats[9])),
                    schemas=[s for s in SCHEMAS if SCHEMA_BITS[s] & mask], k_values=ks)
         return res
 
@@ -298,6 +329,14 @@ class AlignmentEngine:
         out = np.zeros((self.N, self.M), np.float32)
         self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))
         return out
+
+    def debug_operands(self):
+        """The bf16 operands of the fused kernel as float32 arrays (validation hook)."""
+        a = np.zeros((self.N, self.D), np.uint16)
+        b = np.zeros((self.M, self.D), np.uint16)
+        self._check(self._L.mmalign_debug_operands(self._ctx, a.ctypes.data, b.ctypes.data, None))
+        widen = lambda x: (x.astype(np.uint32) << 16).view(np.float32)
+        return widen(a), widen(b)
 
     # -- sharded run, default exchange: contraction sharded by chunk columns, rescoring by query rows -----
     def fused_pass(self, schemas, *, shard, k_values, mrr_cutoff=100, weak_weight=(0.0, 0.0), lam_comb=None,
@@ -405,7 +444,7 @@ class _ShardedSession:
     def rescore_pass(self, tau_global, eps_chunk_global: float):
         """Exact scores of this rank's entries above the global tau.  Returns (results, cert_count [S,N])."""
         res, out = self._outputs()
-        stats = np.zeros(8, np.int64)
+        stats = np.zeros(16, np.int64)
         out.stats = stats.ctypes.data
         cert = self.torch.empty((self.S, self.eng.N), dtype=self.torch.int32, device=self.dev)
         self.eng._check(self.eng._L.mmalign_rescore_pass(self.eng._ctx, C.byref(self.prm), tau_global.data_ptr(),

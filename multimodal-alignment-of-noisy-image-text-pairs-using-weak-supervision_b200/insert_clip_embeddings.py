@@ -56,13 +56,14 @@ def compute_alignment_records(corpus, use_lexical: bool, use_positional: bool,
     """The `alignment_records` list of src/insert_clip_embeddings.py:369-414 for a Corpus, in
     the reference's loop order (image-major, chunk order; lexical before positional).
 
-    Note: that loop compares pages with `!=`, so page None matches page None, while the SQL
-    join of the evaluation never joins NULLs; records here follow the SQL join."""
+    That loop compares manuals and pages with `!=` (:377-380), so page None matches page None -- unlike
+    the SQL join of the evaluation, which never joins NULLs.  The records follow the loop: the tables go to
+    the library with the keys of the Python-side join (corpus.page_keys(python_join=True))."""
     if not (use_lexical or use_positional):
         return []
     eng = engine or _engine()
-    eng.set_images(corpus.img["emb"], corpus.img["key"], corpus.img["bbox"], None)
-    eng.set_chunks(corpus.chk["emb"], corpus.chk["key"], corpus.chk["bbox"], corpus.chk["terms"],
+    eng.set_images(corpus.img["emb"], corpus.img.get("key_py", corpus.img["key"]), corpus.img["bbox"], None)
+    eng.set_chunks(corpus.chk["emb"], corpus.chk.get("key_py", corpus.chk["key"]), corpus.chk["bbox"], corpus.chk["terms"],
                    n_terms=corpus.n_terms)
     off, pc = eng.pairs()
     rec = eng.alignments(SCHEMA_FLAGS[(bool(use_lexical), bool(use_positional))])

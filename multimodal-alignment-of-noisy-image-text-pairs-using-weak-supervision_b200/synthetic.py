@@ -6,7 +6,9 @@ is pulled towards one of that page's chunks (`signal`) so that Top-K / MRR are
 not trivial; bboxes are boxes on a 612 x 792 pt page with 2 % all-zero
 (invalid) entries; term sets are T Bernoulli(p) bits per chunk and, as in the
 reference (src/insert_clip_embeddings.py:144-156 takes no image argument),
-all-ones for images (terms=None).
+all-ones for images (terms=None) -- unless `img_p_term` > 0, which gives every
+image its own Bernoulli(img_p_term) term set, the AND-popcount form of the lexical
+term that BASELINE.json's north_star words (hits = popcount(chunk & image)).
 """
 from __future__ import annotations
 
@@ -31,7 +33,15 @@ def _bboxes(rng, n):
     return b
 
 
-def make_numpy(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000):
+def _pack_bits(bits, T):
+    M, W64 = bits.shape
+    W = W64 // 64
+    bits[:, T:] = False
+    terms = np.packbits(bits.reshape(M, W, 8, 8)[:, :, ::-1, :], axis=-1, bitorder="little")
+    return np.ascontiguousarray(terms[:, :, ::-1, 0]).view(np.uint64).reshape(M, W)
+
+
+def make_numpy(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, img_p_term=0.0):
     """Small/medium corpora on the host (tests, golden vectors, CPU baseline)."""
     rng = np.random.default_rng(seed)
     ce = rng.standard_normal((M, D), dtype=np.float32)
@@ -45,17 +55,16 @@ def make_numpy(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000):
     ie = ce[pick] + np.float32(signal) * u
     ie /= np.linalg.norm(ie, axis=1, keepdims=True)
     W = (T + 63) // 64
-    bits = rng.random((M, W * 64)) < p_term
-    bits[:, T:] = False
-    terms = np.packbits(bits.reshape(M, W, 8, 8)[:, :, ::-1, :], axis=-1, bitorder="little")
-    terms = np.ascontiguousarray(terms[:, :, ::-1, 0]).view(np.uint64).reshape(M, W)
+    terms = _pack_bits(rng.random((M, W * 64)) < p_term, T)
     img = dict(emb=ie.astype(np.float32), key=page_keys(ipage), bbox=_bboxes(rng, N), terms=None)
     chk = dict(emb=ce, key=page_keys(cpage), bbox=_bboxes(rng, M), terms=terms)
+    if img_p_term > 0:  # drawn last, so the rest of the corpus is the same with and without image term sets
+        img["terms"] = _pack_bits(rng.random((N, W * 64)) < img_p_term, T)
     return img, chk, dict(T=T, planted=pick)
 
 
 def make_torch(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, device="cuda",
-               row0=0, rows=None, img_row0=0, img_rows=None):
+               row0=0, rows=None, img_row0=0, img_rows=None, img_p_term=0.0):
     """Full-size corpora generated on the device, by GLOBAL row index in blocks of 65536 rows,
     so that any chunk shard [row0, row0+rows) and any image slab [img_row0, img_row0+img_rows) is
     identical whatever the world size."""
@@ -108,12 +117,16 @@ def make_torch(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, devi
     ce = unit(normal_rows(1, row0, row0 + rows, D))
     cpage = torch.arange(row0, row0 + rows, device=device, dtype=torch.int64) // CHUNKS_PER_PAGE
     W = (T + 63) // 64
-    tb = uniform_rows(3, row0, row0 + rows, W * 64) < p_term
-    tb[:, T:] = False
     weights = (1 << torch.arange(63, device=device, dtype=torch.int64))
-    tb = tb.view(rows, W, 64)
-    terms = (tb[:, :, :63].long() * weights).sum(-1)
-    terms = torch.where(tb[:, :, 63], terms | torch.iinfo(torch.int64).min, terms).contiguous()
+
+    def term_rows(tag, lo, hi, p):
+        tb = uniform_rows(tag, lo, hi, W * 64) < p
+        tb[:, T:] = False
+        tb = tb.view(hi - lo, W, 64)
+        t = (tb[:, :, :63].long() * weights).sum(-1)
+        return torch.where(tb[:, :, 63], t | torch.iinfo(torch.int64).min, t).contiguous()
+
+    terms = term_rows(3, row0, row0 + rows, p_term)
     chk = dict(emb=ce, key=keys(cpage), bbox=bboxes(4, row0, row0 + rows), terms=terms)
     # images
     i0 = img_row0
@@ -136,5 +149,6 @@ def make_torch(N, M, D, *, T=512, p_term=0.01, signal=4.5, seed=0x5EED0000, devi
             sel = (pk // BLK) == b
             src[sel] = rowsb[pk[sel] - b * BLK]
         ie[s:s + SL] = unit(src + signal * u[s:s + SL])
-    img = dict(emb=ie, key=keys(ipage), bbox=bboxes(6, i0, i1), terms=None)
+    img = dict(emb=ie, key=keys(ipage), bbox=bboxes(6, i0, i1),
+               terms=term_rows(7, i0, i1, img_p_term) if img_p_term > 0 else None)
     return img, chk, dict(T=T, planted=pick)

@@ -3,14 +3,45 @@
 TEST / MEASUREMENT INFRASTRUCTURE ONLY (see oracle/mmalign_oracle.c).  Follows the same
 reference sites as the C oracle but uses what a CPU implementation would really use for
 speed: float32 `A @ B.T` through the BLAS numpy links against (all host cores), in column
-slabs, `np.argpartition` + `np.lexsort` for the ordered top-K (lower index wins ties), and
-vectorised weak-supervision terms (src/insert_clip_embeddings.py:144-210, :369-414).
+slabs; selection of each slab's best candidates in float32 with `np.argpartition`, row blocks
+spread over a thread pool (numpy releases the GIL there); float64 cosine, clamp and ordering
+(`np.lexsort`, lower index wins ties) only for the kept candidates; the chunk table's norms and
+sorted page keys computed once per table; vectorised weak-supervision terms
+(src/insert_clip_embeddings.py:144-210, :369-414).
 BLAS sums in its own order, so scores agree with the C oracle to ~1e-7, not bit for bit;
 tests/test_numpy_port.py pins it against the oracle.
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
+
 import numpy as np
+
+_CHUNK_CACHE = {}
+_POOL = None
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=os.cpu_count() or 1)
+    return _POOL
+
+
+def _chunk_side(chk):
+    """Per chunk table, once: squared norms and the page keys in sorted order (the join of evaluate_alignments.py:57-63)."""
+    B = chk["emb"]
+    tag = (id(B), B.shape, id(chk["key"]))
+    hit = _CHUNK_CACHE.get(tag)
+    if hit is None:
+        Bc = np.ascontiguousarray(B, np.float32)
+        nb = np.einsum("ij,ij->i", Bc, Bc).astype(np.float64)
+        ck = np.asarray(chk["key"], np.uint64)
+        order = np.argsort(ck, kind="stable")
+        _CHUNK_CACHE.clear()
+        hit = _CHUNK_CACHE[tag] = (Bc, nb, order, ck[order])
+    return hit
 
 _LEX = (False, True, False, True)
 _POS = (False, False, True, True)
@@ -51,17 +82,13 @@ def evaluate(img, chk, *, T=0, schemas=(0,), lam=(0.0, 0.0, 0.0), kmax=10, cutof
     Returns dict(topk_idx [S,R,kmax], topk_score, pair_rows [P] (index into rows), pair_chunk [P],
     pair_rank [S,P], pair_sim [P])."""
     A = np.ascontiguousarray(img["emb"], np.float32)
-    B = np.ascontiguousarray(chk["emb"], np.float32)
+    B, nb, order, sk = _chunk_side(chk)
     rows = np.arange(A.shape[0]) if rows is None else np.asarray(rows)
     A = A[rows]
     R, M = A.shape[0], B.shape[0]
     kneed = max(kmax, cutoff)
     na = np.einsum("ij,ij->i", A, A).astype(np.float64)
-    nb = np.einsum("ij,ij->i", B, B).astype(np.float64)
-    # ---- same-page pairs (evaluate_alignments.py:57-63) via a sort of the chunk keys
-    ck = np.asarray(chk["key"], np.uint64)
-    order = np.argsort(ck, kind="stable")
-    sk = ck[order]
+    # ---- same-page pairs (evaluate_alignments.py:57-63) via the sorted chunk keys
     ik = np.asarray(img["key"], np.uint64)[rows]
     lo, hi = np.searchsorted(sk, ik, "left"), np.searchsorted(sk, ik, "right")
     hi = np.where(ik == np.uint64(0xFFFFFFFFFFFFFFFF), lo, hi)
@@ -71,22 +98,40 @@ def evaluate(img, chk, *, T=0, schemas=(0,), lam=(0.0, 0.0, 0.0), kmax=10, cutof
     pair_rows = np.repeat(np.arange(R), cnt)
     pair_chunk = order[np.concatenate([np.arange(l, h) for l, h in zip(lo, hi)])] if P else np.zeros(0, np.int64)
     # ---- cosine of every (row, chunk) in slabs; running top-(kneed + max page size)
-    keep = min(M, kneed + int(cnt.max(initial=0)))
-    best_s = np.full((R, 0), -np.inf)
+    # selection in float32 (16 entries of margin for its rounding); the kept candidates get the float64 cosine below
+    keep = min(M, kneed + int(cnt.max(initial=0)) + 16)
+    best_a = np.full((R, 0), -np.inf, np.float32)   # approximate cosine (selection only)
+    best_d = np.zeros((R, 0), np.float32)           # the raw float32 dot product
     best_j = np.zeros((R, 0), np.int64)
+    ra = (1.0 / np.sqrt(na)).astype(np.float32)
+    rb = (1.0 / np.sqrt(nb)).astype(np.float32)
+    blocks = [(r0, min(R, r0 + max(1, -(-R // (os.cpu_count() or 1))))) for r0 in
+              range(0, R, max(1, -(-R // (os.cpu_count() or 1))))]
+
+    def top_of(x, k):  # indices of the k largest per row, row blocks on the thread pool
+        w = x.shape[1]
+        if k >= w:
+            return np.tile(np.arange(w), (x.shape[0], 1))
+        out = np.empty((x.shape[0], k), np.int64)
+
+        def one(b):
+            out[b[0]:b[1]] = np.argpartition(x[b[0]:b[1]], w - k, axis=1)[:, w - k:]
+        list(_pool().map(one, blocks))
+        return out
     for c0 in range(0, M, slab):
         c1 = min(M, c0 + slab)
-        S = (A @ B[c0:c1].T).astype(np.float64)
-        S /= np.sqrt(na[:, None] * nb[None, c0:c1])
-        np.clip(S, -1.0, 1.0, out=S)
-        S = 1.0 - (1.0 - S)
-        k = min(keep, c1 - c0)
-        part = np.argpartition(-S, k - 1, axis=1)[:, :k] if k < c1 - c0 else np.tile(np.arange(c1 - c0), (R, 1))
-        best_s = np.concatenate([best_s, np.take_along_axis(S, part, 1)], 1)
+        dots = A @ B[c0:c1].T                              # float32 sgemm, all host cores
+        approx = dots * ra[:, None] * rb[None, c0:c1]
+        part = top_of(approx, min(keep, c1 - c0))
+        best_a = np.concatenate([best_a, np.take_along_axis(approx, part, 1)], 1)
+        best_d = np.concatenate([best_d, np.take_along_axis(dots, part, 1)], 1)
         best_j = np.concatenate([best_j, part + c0], 1)
-        if best_s.shape[1] > keep:
-            sel = np.argpartition(-best_s, keep - 1, axis=1)[:, :keep]
-            best_s, best_j = np.take_along_axis(best_s, sel, 1), np.take_along_axis(best_j, sel, 1)
+        if best_a.shape[1] > keep:
+            sel = top_of(best_a, keep)
+            best_a, best_d, best_j = (np.take_along_axis(v, sel, 1) for v in (best_a, best_d, best_j))
+    best_s = best_d.astype(np.float64) / np.sqrt(na[:, None] * nb[best_j])
+    np.clip(best_s, -1.0, 1.0, out=best_s)
+    best_s = 1.0 - (1.0 - best_s)
     # ---- exact pair similarities and weak terms
     if P:
         d = np.einsum("ij,ij->i", A[pair_rows], B[pair_chunk]).astype(np.float64)

@@ -17,19 +17,19 @@ def test_header_symbols_are_exported(pkg):
     assert declared == set(pkg._native.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.mmalign_abi_version() == 2
+    assert L.mmalign_abi_version() == 3
 
 
 def test_struct_layout_matches_header(pkg, tmp_path):
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "mmalign.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
                    'sizeof(mmalign_params),sizeof(mmalign_out),offsetof(mmalign_params,lam_lex),offsetof(mmalign_params,path),'
-                   'offsetof(mmalign_params,slab_rows));return 0;}')
+                   'offsetof(mmalign_params,pipeline_rows));return 0;}')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
     a, b, c, d, e = map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split())
     P, O = pkg._native.Params, pkg._native.Out
-    assert (a, b, c, d, e) == (C.sizeof(P), C.sizeof(O), P.lam_lex.offset, P.path.offset, P.slab_rows.offset)
+    assert (a, b, c, d, e) == (C.sizeof(P), C.sizeof(O), P.lam_lex.offset, P.path.offset, P.pipeline_rows.offset)
 
 
 def test_no_cpu_fallback(pkg):

@@ -183,6 +183,20 @@ class OracleSlabEngine:
                         terms=self._np(terms, np.uint64))
         self.M = len(self.chk["key"])
 
+    # query-row layout: the prepared chunk table arrives whole, the engine holds this rank's image slab only
+    def prep_rows(self, emb, bf16, norm2, err, stream=None):
+        bf16.copy_(emb.to(torch.bfloat16).view(torch.int16))   # (stand-in: only the plumbing is under test)
+        norm2.copy_((emb * emb).sum(1))
+        err.zero_()
+
+    def set_chunks_prepared(self, emb, key, bbox, terms, bf16, norm2, err, n_terms=0, col_offset=0, stream=None):
+        assert torch.equal(bf16, emb.to(torch.bfloat16).view(torch.int16))   # every rank's K0 output arrived in place
+        assert torch.allclose(norm2, (emb * emb).sum(1))
+        self.set_chunks(emb, key, bbox, terms, n_terms, col_offset)
+
+    def rescore_after(self, event):
+        raise AssertionError("no side stream on the CPU")
+
     def fused_pass(self, schemas, *, shard, **_):
         self.shard = shard
 
@@ -198,8 +212,8 @@ class OracleSlabEngine:
         tau = torch.full((n_dest, slab_rows), float("-inf"))
         return keys, count, tau
 
-    def run(self, schemas, *, slab, k_values, mrr_cutoff, weak_weight, imported=None, **_):
-        row0, rows = slab
+    def run(self, schemas, *, k_values, mrr_cutoff, weak_weight, slab=None, imported=None, **_):
+        row0, rows = slab if slab is not None else (0, self.N)
         if imported is not None:  # column layout: every global column exactly once, from the rank that owns it
             keys, count, tau = imported
             for r in range(rows):

@@ -39,5 +39,14 @@ mrr = ev.compute_mrr(s)
 avg = ev.compute_average_similarity(s)
 dt = time.perf_counter() - t0
 P = len(ev.get_image_text_pairs(s))
+import json  # noqa: E402
+rec = {"value": N / dt, "unit": "queries/s", "seconds": dt, "images": N, "pairs": P, "cores": 1, "host_vcpus": os.cpu_count(),
+       "fake_db_connections": db.n_connect, "kind": "reference",
+       "what": "UNMODIFIED compute_top_k_accuracy + compute_mrr + compute_average_similarity of src/evaluate_alignments.py:169-231 "
+               "at BASELINE config 1 (1k x 5k x 512, vanilla_clip) over the in-process fake pgvector of oracle/reference_harness.py "
+               "(single Python thread; against a real PostgreSQL every one of the connections is a TCP round trip)",
+       "where": "build container (the reference tree does not travel to the GPU box)",
+       "metrics": {"top_k": {str(k): v for k, v in acc.items()}, "mrr": float(mrr), "avg_similarity": float(avg)}}
+(ROOT / "profiles" / "bench" / "r2_reference_as_written_config1.json").write_text(json.dumps(rec, indent=1) + "\n")
 print(f"reference metric functions, config 1: {dt:.2f} s for {N} images / {P} pairs on {os.cpu_count()} vCPU "
       f"(single Python thread) = {N / dt:.1f} images/s, {db.n_connect} fake-DB connections; top_k={acc} mrr={mrr:.6f} avg={avg:.6f}")
