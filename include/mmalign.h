@@ -147,6 +147,11 @@ int mmalign_set_chunks(mmalign_ctx *ctx, const float *emb, const uint64_t *page_
                        const double *bbox, const uint64_t *terms, int64_t m_local, int32_t D,
                        int32_t term_words, int64_t n_terms, int64_t col_offset);
 
+/* tunables of a context.  "piece_bytes": host embedding rows are uploaded in pieces of about this many bytes
+ * (default 64 MiB; each piece announces itself, so preparation and the first contraction start behind the
+ * first pieces instead of behind the whole table). */
+int mmalign_set_option(mmalign_ctx *ctx, const char *name, int64_t value);
+
 /* waits for every upload and preparation queued by set_images / set_chunks (after it, page-locked host
  * inputs may be reused or freed) */
 int mmalign_sync(mmalign_ctx *ctx);

@@ -41,7 +41,7 @@ EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_
            "mmalign_reduce_metrics", "mmalign_debug_scores", "mmalign_fused_pass", "mmalign_chunk_err_max",
            "mmalign_rescore_pass", "mmalign_rescan_rows", "mmalign_list_stride", "mmalign_export_lists",
            "mmalign_rescore_slab", "mmalign_num_pairs_range", "mmalign_term_bitsets", "mmalign_sync",
-           "mmalign_prep_rows", "mmalign_set_chunks_prepared", "mmalign_rescore_after", "mmalign_debug_operands"]
+           "mmalign_prep_rows", "mmalign_set_chunks_prepared", "mmalign_rescore_after", "mmalign_debug_operands", "mmalign_set_option"]
 ABI_VERSION = 3
 
 _lib = None
@@ -102,6 +102,7 @@ def load():
     L.mmalign_set_chunks_prepared.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i64, i64, vp]
     L.mmalign_rescore_after.argtypes = [vp, vp]
     L.mmalign_debug_operands.argtypes = [vp, vp, vp, vp]
+    L.mmalign_set_option.argtypes = [vp, C.c_char_p, i64]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):

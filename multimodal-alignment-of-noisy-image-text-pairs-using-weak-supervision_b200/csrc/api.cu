@@ -20,7 +20,8 @@ struct Trace {
     bool on;
     std::chrono::steady_clock::time_point t0;
     const char *what;
-    explicit Trace(const char *w) : on(getenv("MMALIGN_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), what(w) {}
+    explicit Trace(const char *w) : on(enabled()), t0(std::chrono::steady_clock::now()), what(w) {}
+    static bool enabled() { static const bool e = getenv("MMALIGN_TRACE") != nullptr; return e; }
     void mark(const char *phase)
     {
         if (!on) return;
@@ -50,6 +51,8 @@ struct DevBuf {  // growable device scratch; frees itself (locals on error paths
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+constexpr int kMaxGroups = 4;
+
 struct SideStore {
     Side s;
     DevBuf up[4];               // uploads of host inputs: emb, key, bbox, terms (reused across set_* calls)
@@ -61,6 +64,13 @@ struct SideStore {
     int64_t piece_rows = 0;
     int n_pieces = 0;                    // 0 = the rows were on the device already
     std::vector<cudaEvent_t> ev_piece;   // [>= n_pieces] piece p is on the device (recorded on the copy stream)
+    const float *pending_emb = nullptr;  // page-locked host rows whose pieces [pieces_queued, n_pieces) are not queued yet
+    int pieces_queued = 0;
+    // chunks: the table in column groups (whole pieces), each announcing its K0 -- the first slab of a run is
+    // contracted group by group while the later groups still travel
+    int n_groups = 1;
+    int64_t group_row[kMaxGroups + 1] = {};
+    cudaEvent_t ev_group[kMaxGroups] = {};
     cudaEvent_t ev_small = nullptr;      // keys / boxes / term sets are on the device (copy stream)
     cudaEvent_t ev_caller = nullptr;     // whatever the caller had queued on the legacy default stream at set_* time
     cudaEvent_t ev_ready = nullptr;      // the K0 launches queued so far have run (chunks: all rows, at set_* time)
@@ -74,12 +84,16 @@ struct SideStore {
         err_max = nullptr;
         ready = false;
         n_pieces = 0; prep_lo = prep_hi = 0; ev_ready_set = false;
+        pending_emb = nullptr; pieces_queued = 0; n_groups = 1;
     }
     void destroy_events()
     {
         for (cudaEvent_t e : ev_piece) if (e) cudaEventDestroy(e);
         ev_piece.clear();
-        for (cudaEvent_t *e : {&ev_small, &ev_caller, &ev_ready}) { if (*e) cudaEventDestroy(*e); *e = nullptr; }
+        for (cudaEvent_t *e : {&ev_small, &ev_caller, &ev_ready, &ev_group[0], &ev_group[1], &ev_group[2], &ev_group[3]}) {
+            if (*e) cudaEventDestroy(*e);
+            *e = nullptr;
+        }
     }
 };
 
@@ -95,6 +109,8 @@ struct mmalign_ctx {
     int64_t n_terms = 0, col_offset = 0;
     PairIndex px;
     bool px_ready = false;
+    bool chk_consumed = true;      // a run has read the chunk table since the last set_chunks
+    size_t piece_bytes = (size_t)64 << 20;  // host embedding rows travel in pieces of about this size (mmalign_set_option)
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
     DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;
@@ -177,7 +193,8 @@ extern "C" int mmalign_create(mmalign_ctx **out, int device)
         ok = ok && cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming) == cudaSuccess;
     for (SideStore *ss : {&c->img, &c->chk})
-        for (cudaEvent_t *ev : {&ss->ev_small, &ss->ev_caller, &ss->ev_ready})
+        for (cudaEvent_t *ev : {&ss->ev_small, &ss->ev_caller, &ss->ev_ready, &ss->ev_group[0], &ss->ev_group[1],
+                                &ss->ev_group[2], &ss->ev_group[3]})
             ok = ok && cudaEventCreateWithFlags(ev, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { mmalign_destroy(c); return fail(nullptr, MMALIGN_ECUDA, "creating the context's streams / events / scratch failed"); }
     *out = c;
@@ -202,6 +219,17 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
     for (cudaStream_t s : {c->s_in, c->s_prep, c->s_idx, c->s_out}) if (s) cudaStreamDestroy(s);
     delete c;
+}
+
+extern "C" int mmalign_set_option(mmalign_ctx *c, const char *name, int64_t value)
+{
+    if (!c || !name) return fail(c, MMALIGN_EINVAL, "mmalign_set_option: NULL argument");
+    if (!strcmp(name, "piece_bytes")) {
+        if (value < 1024 || value > ((int64_t)1 << 34)) return fail(c, MMALIGN_EINVAL, "piece_bytes=%lld must be in 1 KiB..16 GiB", (long long)value);
+        c->piece_bytes = (size_t)value;
+        return MMALIGN_OK;
+    }
+    return fail(c, MMALIGN_EINVAL, "mmalign_set_option: unknown option '%s'", name);
 }
 
 extern "C" int mmalign_sync(mmalign_ctx *c)
@@ -233,7 +261,23 @@ static int order_after(mmalign_ctx *c, cudaStream_t b, cudaStream_t a)
     return MMALIGN_OK;
 }
 
-constexpr size_t kPieceBytes = (size_t)64 << 20;  // embedding rows travel in pieces of about this size
+
+// queues the uploads of pieces [pieces_queued, upto) of a side's host embedding rows on the copy stream
+static int queue_pieces(mmalign_ctx *c, SideStore &ss, int upto)
+{
+    if (!ss.pending_emb) return MMALIGN_OK;
+    if (upto > ss.n_pieces) upto = ss.n_pieces;
+    const int64_t n = ss.s.n, D = ss.s.D, pr = ss.piece_rows;
+    for (int p = ss.pieces_queued; p < upto; ++p) {
+        const int64_t r0 = (int64_t)p * pr, r1 = r0 + pr < n ? r0 + pr : n;
+        CU(c, cudaMemcpyAsync((float *)ss.up[0].p + r0 * D, ss.pending_emb + r0 * D, (size_t)(r1 - r0) * D * sizeof(float),
+                              cudaMemcpyHostToDevice, c->s_in));
+        CU(c, cudaEventRecord(ss.ev_piece[p], c->s_in));
+    }
+    if (upto > ss.pieces_queued) ss.pieces_queued = upto;
+    if (ss.pieces_queued >= ss.n_pieces) ss.pending_emb = nullptr;
+    return MMALIGN_OK;
+}
 
 static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint64_t *key, const double *bbox,
                     const uint64_t *terms, int64_t n, int D, int term_words, int box_rows, const char *what, bool is_chunks)
@@ -272,17 +316,23 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
     CU(c, ss.norm2.reserve(nn * sizeof(float))); s.norm2 = (float *)ss.norm2.p;
     CU(c, ss.err.reserve(nn * sizeof(float))); s.err = (float *)ss.err.p;
     CU(c, ss.errmax.reserve(sizeof(float))); ss.err_max = (float *)ss.errmax.p;
-    // embedding rows: borrowed on the device, or uploaded piece by piece (each piece announces itself with an event)
+    // embedding rows: borrowed on the device, or uploaded piece by piece (each piece announces itself with an event).
+    // Order on the copy stream: the chunk table goes first (the contraction of any query slab needs all of it),
+    // preceded only by the image pieces of the first query slab; a page-locked image table set BEFORE the chunks
+    // therefore waits for set_chunks (or for its first consumer) to queue its pieces.  Pageable rows cannot wait.
     ss.n_pieces = 0;
+    ss.pending_emb = nullptr;
+    ss.pieces_queued = 0;
     ss.prep_lo = ss.prep_hi = 0;
     ss.ev_ready_set = false;
+    ss.n_groups = 1;
     if (n > 0 && is_device_ptr(emb)) {
         s.emb = emb;
     } else if (n > 0) {
         CU(c, ss.up[0].reserve((size_t)n * D * sizeof(float)));
         s.emb = static_cast<const float *>(ss.up[0].p);
-        int64_t pr = (int64_t)(kPieceBytes / ((size_t)D * sizeof(float)));
-        pr = pr < 128 ? 128 : pr / 128 * 128;
+        int64_t pr = (int64_t)(c->piece_bytes / ((size_t)D * sizeof(float)));
+        pr = pr < 256 ? 256 : pr / 256 * 256;  // whole column tiles of the fused kernel
         ss.piece_rows = pr;
         ss.n_pieces = (int)((n + pr - 1) / pr);
         while ((int)ss.ev_piece.size() < ss.n_pieces) {
@@ -290,13 +340,22 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
             CU(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             ss.ev_piece.push_back(e);
         }
-        for (int p = 0; p < ss.n_pieces; ++p) {
-            const int64_t r0 = (int64_t)p * pr, r1 = r0 + pr < n ? r0 + pr : n;
-            CU(c, cudaMemcpyAsync((float *)ss.up[0].p + r0 * D, emb + r0 * D, (size_t)(r1 - r0) * D * sizeof(float),
-                                  cudaMemcpyHostToDevice, sin));
-            CU(c, cudaEventRecord(ss.ev_piece[p], sin));
+        ss.pending_emb = emb;
+        const bool pinned = ptr_kind(emb) == kPtrPinned;
+        if (!is_chunks) {
+            if (!pinned || (c->chk.ready && !c->chk_consumed)) { if ((rc = queue_pieces(c, ss, ss.n_pieces))) return rc; }
+        } else {
+            SideStore &im = c->img;
+            if (im.pending_emb) {  // the first query slab's rows, then the chunks, then the other image rows
+                const int64_t first = (int64_t)kSlabWaves * c->sm_count * 128;
+                if ((rc = queue_pieces(c, im, (int)((first + im.piece_rows - 1) / im.piece_rows)))) return rc;
+            }
+            if ((rc = queue_pieces(c, ss, ss.n_pieces))) return rc;
+            if ((rc = queue_pieces(c, im, im.n_pieces))) return rc;
         }
     }
+    if (is_chunks && c->img.pending_emb && ss.n_pieces == 0)
+        if ((rc = queue_pieces(c, c->img, c->img.n_pieces))) return rc;
     if (n > 0 && D % 64 == 0) {
         char msg[256];
         if (encode_tensor_map(&ss.tmap, s.emb_bf16, n, D, box_rows, msg, sizeof msg))
@@ -307,19 +366,27 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
     if (is_chunks) {
         cudaStream_t sp = c->s_prep;
         CU(c, cudaStreamWaitEvent(sp, ss.ev_caller, 0));
+        ss.group_row[0] = 0; ss.group_row[1] = n;
         if (ss.n_pieces == 0) {
             CU(c, launch_prep(s, 0, n, c->sm_count, sp));
         } else {
+            ss.n_groups = ss.n_pieces >= 2 * kMaxGroups ? kMaxGroups : 1;
+            int g = 0;
             for (int p = 0; p < ss.n_pieces; ++p) {
                 const int64_t r0 = (int64_t)p * ss.piece_rows, r1 = r0 + ss.piece_rows < n ? r0 + ss.piece_rows : n;
                 CU(c, cudaStreamWaitEvent(sp, ss.ev_piece[p], 0));
                 CU(c, launch_prep(s, r0, r1 - r0, c->sm_count, sp));
+                if (p + 1 == (g + 1) * ss.n_pieces / ss.n_groups) {  // last piece of group g
+                    CU(c, cudaEventRecord(ss.ev_group[g], sp));
+                    ss.group_row[++g] = r1;
+                }
             }
         }
         CU(c, reduce_max_float(s.err, n, ss.err_max, sp));
         CU(c, cudaEventRecord(ss.ev_ready, sp));
         ss.ev_ready_set = true;
         ss.prep_lo = 0; ss.prep_hi = n;
+        c->chk_consumed = false;
     }
     tr.mark("queued upload + prep");
     ss.ready = true;
@@ -391,7 +458,10 @@ extern "C" int mmalign_set_chunks_prepared(mmalign_ctx *c, const float *emb, con
     s.n = m; s.D = D; s.term_words = term_words;
     s.emb = emb; s.key = key; s.bbox = bbox; s.terms = terms;
     s.emb_bf16 = (__nv_bfloat16 *)const_cast<void *>(bf16); s.norm2 = const_cast<float *>(norm2); s.err = const_cast<float *>(err);
-    ss.n_pieces = 0;
+    ss.n_pieces = 0; ss.n_groups = 1; ss.pending_emb = nullptr; ss.pieces_queued = 0;
+    ss.group_row[0] = 0; ss.group_row[1] = m;
+    c->chk_consumed = false;
+    if ((rc = queue_pieces(c, c->img, c->img.n_pieces))) return rc;
     CU(c, ss.errmax.reserve(sizeof(float))); ss.err_max = (float *)ss.errmax.p;
     // the caller's stream carries the exchange that filled the prepared operands and the keys
     CU(c, cudaEventRecord(ss.ev_caller, st));
@@ -452,6 +522,8 @@ static int prepare_images(mmalign_ctx *c, int64_t lo, int64_t hi, cudaStream_t s
 static int wait_tables(mmalign_ctx *c, cudaStream_t st)
 {
     int rc;
+    if ((rc = queue_pieces(c, c->img, c->img.n_pieces))) return rc;
+    c->chk_consumed = true;
     if ((rc = wait_side(c, c->img, st))) return rc;
     if ((rc = wait_side(c, c->chk, st))) return rc;
     return prepare_images(c, 0, c->img.s.n, st);
@@ -657,7 +729,7 @@ static int reserve_lists(mmalign_ctx *c, const FusedPlan &plan)
 }
 
 static int launch_fused_range(mmalign_ctx *c, const FusedPlan &plan, int64_t row0, int64_t n_rows, int64_t col0, int64_t n_cols,
-                              cudaStream_t st, CandLists *lists)
+                              cudaStream_t st, CandLists *lists, int64_t list_base = 0, int64_t col_base = 0)
 {
     Side img = c->img.s, chk = c->chk.s;
     alignas(64) CUtensorMap tmap_a = c->img.tmap, tmap_b = c->chk.tmap;
@@ -671,8 +743,10 @@ static int launch_fused_range(mmalign_ctx *c, const FusedPlan &plan, int64_t row
         chk.n = n_cols;
     }
     *lists = CandLists();
-    lists->keys = (uint64_t *)c->list_keys.p; lists->tau = (float *)c->list_tau.p; lists->count = (int32_t *)c->list_count.p;
-    CU(c, launch_fused(img, chk, plan, &tmap_a, &tmap_b, *lists, nullptr, st));
+    lists->keys = (uint64_t *)c->list_keys.p + list_base * plan.cap;
+    lists->tau = (float *)c->list_tau.p + list_base;
+    lists->count = (int32_t *)c->list_count.p + list_base;
+    CU(c, launch_fused(img, chk, plan, &tmap_a, &tmap_b, *lists, nullptr, st, col_base));
     return MMALIGN_OK;
 }
 
@@ -781,7 +855,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         if (!out.pair_sim) out.pair_sim = (double *)((char *)extra.p + ((SP * sizeof(int32_t) + 255) & ~(size_t)255));
     }
     // ---- plans and scratch of every slab, before anything is queued (a growing buffer would stall the pipeline)
-    std::vector<FusedPlan> plans((size_t)n_slabs);
+    std::vector<FusedPlan> plans((size_t)n_slabs), gplans;
     if (fused_path) {
         CU(c, c->fail_rows.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(int32_t)));
         CU(c, c->fail_thr.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(unsigned long long)));
@@ -789,8 +863,22 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         CU(c, c->scan_cnt.reserve(sizeof(int32_t) * kScanSlots));
         if (!imported) {
             FusedPlan big = {};
+            // The first slab of a pipelined run over a chunk table that is still travelling is contracted column
+            // group by column group (set_side): its rows get n_groups times the lists, each over one group.
+            if (n_slabs > 1 && c->chk.n_groups > 1 && !c->chk_consumed) {
+                const SideStore &ck = c->chk;
+                gplans.resize((size_t)ck.n_groups);
+                bool same = true;
+                for (int g = 0; g < ck.n_groups && same; ++g) {
+                    if ((rc = plan_fused(c, rp, prm->kprime, ck.n_groups, bounds[1] - bounds[0], ck.group_row[g + 1] - ck.group_row[g], &gplans[g]))) return rc;
+                    same = gplans[g].cap == gplans[0].cap && gplans[g].kprime_list == gplans[0].kprime_list &&
+                           gplans[g].n_splits == gplans[0].n_splits && gplans[g].n_lists == gplans[0].n_lists;
+                }
+                if (!same) gplans.clear();
+            }
             for (int s = 0; s < n_slabs; ++s) {
                 if ((rc = plan_fused(c, rp, prm->kprime, 1, bounds[s + 1] - bounds[s], M, &plans[s]))) return rc;
+                if (s == 0 && !gplans.empty()) { plans[0] = gplans[0]; plans[0].n_lists = gplans[0].n_lists * (int64_t)gplans.size(); }
                 if ((size_t)plans[s].n_lists * plans[s].cap >= (size_t)big.n_lists * big.cap) { big.cap = plans[s].cap; big.n_lists = plans[s].n_lists; }
             }
             FusedPlan most = big;
@@ -807,8 +895,17 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     unsigned long long *cand_counter = (unsigned long long *)((char *)c->small.p + 8);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
     int32_t *k_list_dev = (int32_t *)((char *)c->small.p + 64);
+    if ((rc = queue_pieces(c, c->img, c->img.n_pieces))) return rc;
     if ((rc = wait_side(c, c->img, st))) return rc;
-    if ((rc = wait_side(c, c->chk, st))) return rc;
+    CU(c, cudaStreamWaitEvent(st, c->chk.ev_small, 0));
+    CU(c, cudaStreamWaitEvent(st, c->chk.ev_caller, 0));
+    bool chunks_waited = false;  // the whole chunk table prepared (its K0 runs behind the uploads on its own stream)
+    auto need_chunks = [&]() -> int {
+        if (!chunks_waited && c->chk.ev_ready_set) CU(c, cudaStreamWaitEvent(st, c->chk.ev_ready, 0));
+        chunks_waited = true;
+        return MMALIGN_OK;
+    };
+    c->chk_consumed = true;
     CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
     CU(c, cudaMemsetAsync(slab_fail, 0, sizeof(int32_t) * kMaxSlabs, st));
     CU(c, cudaMemcpyAsync(k_list_dev, rp.k_list, sizeof(int32_t) * kMaxK, cudaMemcpyHostToDevice, st));
@@ -826,18 +923,36 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         if ((rc = prepare_images(c, r0, r0 + rows, st, &launches))) return rc;
         CU(c, cudaEventRecord(ev[0], st));
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
+            if ((rc = need_chunks())) return rc;
             CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, nullptr, cand_counter,
                                  error_flag, nullptr, nullptr, range, st));
             launches += 1;
         } else if (!fused_path) {
+            if ((rc = need_chunks())) return rc;
             CU(c, launch_exact_scan(img, chk, c->px, rp, nullptr, nullptr, rows, out, error_flag, range, nullptr, st));
             launches += 1;
         } else {
             CandLists L;
             if (imported) {
+                if ((rc = need_chunks())) return rc;
                 L = *imported;
                 kprime_used = imported->kprime;
+            } else if (s == 0 && !gplans.empty()) {
+                const SideStore &ck = c->chk;
+                for (int g = 0; g < ck.n_groups; ++g) {
+                    CU(c, cudaStreamWaitEvent(st, ck.ev_group[g], 0));
+                    CandLists Lg;
+                    if ((rc = launch_fused_range(c, gplans[g], r0, rows, ck.group_row[g], ck.group_row[g + 1] - ck.group_row[g], st, &Lg,
+                                                 (int64_t)g * gplans[0].n_lists, ck.group_row[g]))) return rc;
+                    if (g == 0) L = Lg;
+                }
+                L.n_splits = gplans[0].n_splits * ck.n_groups;  // one row's lists: n_groups x (splits x 2 halves)
+                fused_launches += ck.n_groups;
+                launches += ck.n_groups;
+                kprime_used = gplans[0].kprime;
+                if ((rc = need_chunks())) return rc;
             } else {
+                if ((rc = need_chunks())) return rc;
                 if ((rc = launch_fused_range(c, plans[s], r0, rows, 0, M, st, &L))) return rc;
                 fused_launches += 1;
                 launches += 1;
@@ -893,7 +1008,13 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     if (uo->num_pairs) CU(c, cudaMemcpy(uo->num_pairs, &P, sizeof(int64_t), cudaMemcpyDefault));
     if (uo->stats) {
         double t_fused = 0.0, t_resc = 0.0, t_scan = 0.0;
-        if (fused_path) {
+        if (!fused_path) {  // same-page candidates: the rescoring kernel alone; exact path: the scan alone
+            for (int s = 0; s < n_slabs; ++s) {
+                float a = 0.f;
+                cudaEventElapsedTime(&a, c->ev_slab[4 * (size_t)s], c->ev_slab[4 * (size_t)s + 3]);
+                (rp.candidates == MMALIGN_CAND_SAME_PAGE ? t_resc : t_scan) += a;
+            }
+        } else {
             for (int s = 0; s < n_slabs; ++s) {
                 float a = 0.f, b = 0.f, d = 0.f;
                 const cudaEvent_t *ev = &c->ev_slab[4 * (size_t)s];

@@ -144,8 +144,9 @@ struct FusedArgs {
     int32_t *count;
     int kprime;
     float *dump;           // debug: write raw scores [N][M] instead of lists
-    float tau_init;        // -inf; tuning experiments start the lists at a threshold (MMALIGN_TAU_INIT)
-    int skip_final;        // tuning experiments: no end-of-unit compaction (MMALIGN_SKIP_FINAL)
+    float tau_init;        // -inf; tuning builds (-DMMALIGN_TUNING) can start the lists at a threshold
+    int skip_final;        // tuning builds: no end-of-unit compaction
+    uint32_t col_base;     // added to the column index of every entry (a launch over a column group of the table)
 };
 
 // ---------------------------------------------------------------------------
@@ -223,7 +224,7 @@ __device__ __forceinline__ float max8(const uint32_t *v)
 // One 32-column chunk of one accumulator row: append every score above tau to the row's list.
 template <int KPL>
 __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t M, const char *ubase,
-                                              uint32_t off0, int &n, float &tau, int kprime)
+                                              uint32_t off0, int &n, float &tau, int kprime, uint32_t col_base)
 {
     constexpr int CAP = 32 * KPL;
     if (col0 + 32 > M) {  // ragged last tile: TMA zero-filled these columns
@@ -238,7 +239,7 @@ __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t
     const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
     if (__any_sync(0xFFFFFFFFu, m > tau)) {
         uint32_t woff = off0 + 8u * (uint32_t)n;
-        const uint32_t c0 = (uint32_t)col0;
+        const uint32_t c0 = (uint32_t)col0 + col_base;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (__any_sync(0xFFFFFFFFu, g[q] > tau)) {
@@ -409,20 +410,20 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     tmem_ld32(taddr, va);
                     tmem_ld_wait(va);
                     tmem_ld32(taddr + 32, vb);
-                    process_chunk<KPL>(va, col0, P.M, ubase, off0, n, tau, P.kprime);
+                    process_chunk<KPL>(va, col0, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
                     __syncwarp();
                     tmem_ld_wait(vb);
                     tmem_ld32(taddr + 64, va);
-                    process_chunk<KPL>(vb, col0 + 32, P.M, ubase, off0, n, tau, P.kprime);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
                     __syncwarp();
                     tmem_ld_wait(va);
                     tmem_ld32(taddr + 96, vb);
-                    process_chunk<KPL>(va, col0 + 64, P.M, ubase, off0, n, tau, P.kprime);
+                    process_chunk<KPL>(va, col0 + 64, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
                     __syncwarp();
                     tmem_ld_wait(vb);
                     tc_fence_before();  // last read of this accumulator: hand it back to the MMA warp
                     mbar_arrive(bar_tempty + 8u * acc);
-                    process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime);
+                    process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
                     // Routine compaction happens HERE, after the accumulator went back to the MMA warp, so that its
                     // global-memory latency is off the MMA critical path (the check inside process_chunk only fires
                     // when a single tile overflows the remaining room, i.e. in the first tiles of a sweep).
@@ -481,7 +482,9 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     if (p.kprime < kneed) p.kprime = kneed;
     // A row has 2 * n_splits lists over disjoint columns on each of the n_ranks GPUs; the union of their best
     // k entries is complete to a depth of about n_lists * k, so each list keeps its share plus 15 % for imbalance.
-    if (const char *e = getenv("MMALIGN_PLAN_RANKS")) n_ranks = atoi(e);  // tuning experiments: size the lists as for a sharded run
+#ifdef MMALIGN_TUNING  // tuning builds only: size the lists as for a sharded run
+    if (const char *e = getenv("MMALIGN_PLAN_RANKS")) n_ranks = atoi(e);
+#endif
     const int lists_per_row = 2 * p.n_splits * (n_ranks > 1 ? n_ranks : 1);
     // The union is complete above the LARGEST of the lists' thresholds.  A list's k-th best score sits at
     // global rank ~ L*k with relative spread 1/sqrt(k), and the largest of L of them about z_L = sqrt(2 ln L)
@@ -498,7 +501,9 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     // tile; the room between those two marks is how many insertions one compaction buys.  Measured (K1 alone): 6 slots
     // of room (the 4-GPU share in 128-entry lists) cost 6.5 % against 64; 300 slots in 512-entry lists gain nothing.
     int room = 64;
-    if (const char *e = getenv("MMALIGN_CAP_ROOM")) room = atoi(e);  // tuning experiments
+#ifdef MMALIGN_TUNING
+    if (const char *e = getenv("MMALIGN_CAP_ROOM")) room = atoi(e);
+#endif
     int need = p.kprime_list + kSlack + kCompactMargin + room;
     if (need > 512) need = p.kprime_list + kSlack + kCompactMargin + 32;
     if (need <= 128) p.cap = 128;
@@ -507,7 +512,9 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     else return -2;
     p.n_lists = p.n_row_blocks * p.n_splits * 256;
     p.a_resident = D <= 512;
-    if (const char *e = getenv("MMALIGN_A_RESIDENT")) p.a_resident = p.a_resident && atoi(e) != 0;  // tuning experiments
+#ifdef MMALIGN_TUNING
+    if (const char *e = getenv("MMALIGN_A_RESIDENT")) p.a_resident = p.a_resident && atoi(e) != 0;
+#endif
     const size_t a_bytes = p.a_resident ? (size_t)(D / BK) * kABlockBytes : 0;
     const size_t stage_bytes = kBStageBytes + (p.a_resident ? 0 : kABlockBytes);
     const size_t fixed = 1024 /*alignment slack*/ + a_bytes + 256 /*barriers*/;
@@ -567,8 +574,10 @@ static cudaError_t launch_variant(const CUtensorMap &ta, const CUtensorMap &tb, 
     return cudaGetLastError();
 }
 
+// `lists` are the buffers of this launch (a launch over a column group of the table passes its slice of a row's
+// lists and the group's first column as col_base; fused_tc.cu numbers columns from the start of tensor map B)
 cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan, const void *tmap_a,
-                         const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st)
+                         const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st, int64_t col_base)
 {
     FusedArgs a = {};
     a.N = img.n; a.M = chk.n; a.num_kb = img.D / BK;
@@ -581,8 +590,12 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     a.kprime = plan.kprime_list;
     a.dump = dump;
     a.tau_init = -INFINITY;
+    a.skip_final = 0;
+#ifdef MMALIGN_TUNING
     if (const char *e = getenv("MMALIGN_TAU_INIT")) a.tau_init = (float)atof(e);
     a.skip_final = getenv("MMALIGN_SKIP_FINAL") != nullptr;
+#endif
+    a.col_base = (uint32_t)col_base;
     const CUtensorMap &ta = *reinterpret_cast<const CUtensorMap *>(tmap_a);
     const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;

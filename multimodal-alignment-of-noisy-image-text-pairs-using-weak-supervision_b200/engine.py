@@ -119,6 +119,10 @@ class AlignmentEngine:
     def set_chunks(self, emb, page_key, bbox=None, terms=None, n_terms: int = 0, col_offset: int = 0):
         self._set("chunks", emb, page_key, bbox, terms, n_terms, col_offset)
 
+    def set_option(self, name: str, value: int):
+        """mmalign_set_option (e.g. "piece_bytes")."""
+        self._check(self._L.mmalign_set_option(self._ctx, name.encode(), int(value)))
+
     def sync(self):
         """Waits for the uploads and preparation queued by set_images / set_chunks (mmalign_sync)."""
         self._check(self._L.mmalign_sync(self._ctx))
