@@ -59,6 +59,7 @@ struct SideStore {
     DevBuf bf16, norm2, err, errmax;
     float *err_max = nullptr;   // [1] max rounding-error norm over the rows (chunks)
     alignas(64) CUtensorMap tmap;
+    alignas(64) CUtensorMap tmap_half;  // chunks: 128-row boxes (the B halves of the CTA-pair kernel)
     bool ready = false;
     // asynchronous ingest: host embedding rows arrive in pieces on the context's copy stream
     int64_t piece_rows = 0;
@@ -110,6 +111,7 @@ struct mmalign_ctx {
     PairIndex px;
     bool px_ready = false;
     bool chk_consumed = true;      // a run has read the chunk table since the last set_chunks
+    bool cta_pairs = false;        // the fused kernel on CTA pairs (tcgen05.mma.cta_group::2): mmalign_set_option
     size_t piece_bytes = (size_t)64 << 20;  // host embedding rows travel in pieces of about this size (mmalign_set_option)
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
@@ -227,6 +229,11 @@ extern "C" int mmalign_set_option(mmalign_ctx *c, const char *name, int64_t valu
     if (!strcmp(name, "piece_bytes")) {
         if (value < 1024 || value > ((int64_t)1 << 34)) return fail(c, MMALIGN_EINVAL, "piece_bytes=%lld must be in 1 KiB..16 GiB", (long long)value);
         c->piece_bytes = (size_t)value;
+        return MMALIGN_OK;
+    }
+    if (!strcmp(name, "cta_pairs")) {
+        if (value != 0 && value != 1) return fail(c, MMALIGN_EINVAL, "cta_pairs=%lld must be 0 or 1", (long long)value);
+        c->cta_pairs = value != 0;
         return MMALIGN_OK;
     }
     return fail(c, MMALIGN_EINVAL, "mmalign_set_option: unknown option '%s'", name);
@@ -358,7 +365,8 @@ static int set_side(mmalign_ctx *c, SideStore &ss, const float *emb, const uint6
         if ((rc = queue_pieces(c, c->img, c->img.n_pieces))) return rc;
     if (n > 0 && D % 64 == 0) {
         char msg[256];
-        if (encode_tensor_map(&ss.tmap, s.emb_bf16, n, D, box_rows, msg, sizeof msg))
+        if (encode_tensor_map(&ss.tmap, s.emb_bf16, n, D, box_rows, msg, sizeof msg) ||
+            (is_chunks && encode_tensor_map(&ss.tmap_half, s.emb_bf16, n, D, 128, msg, sizeof msg)))
             return fail(c, MMALIGN_ECUDA, "%s: %s", what, msg);
     }
     // chunks: K0 runs now, piece by piece behind the uploads.  Images: K0 runs in the consumer (mmalign_run prepares
@@ -473,7 +481,8 @@ extern "C" int mmalign_set_chunks_prepared(mmalign_ctx *c, const float *emb, con
     ss.prep_lo = 0; ss.prep_hi = m;
     if (m > 0 && D % 64 == 0) {
         char msg[256];
-        if (encode_tensor_map(&ss.tmap, s.emb_bf16, m, D, 256, msg, sizeof msg))
+        if (encode_tensor_map(&ss.tmap, s.emb_bf16, m, D, 256, msg, sizeof msg) ||
+            encode_tensor_map(&ss.tmap_half, s.emb_bf16, m, D, 128, msg, sizeof msg))
             return fail(c, MMALIGN_ECUDA, "mmalign_set_chunks_prepared: %s", msg);
     }
     c->n_terms = n_terms;
@@ -732,14 +741,14 @@ static int launch_fused_range(mmalign_ctx *c, const FusedPlan &plan, int64_t row
                               cudaStream_t st, CandLists *lists, int64_t list_base = 0, int64_t col_base = 0)
 {
     Side img = c->img.s, chk = c->chk.s;
-    alignas(64) CUtensorMap tmap_a = c->img.tmap, tmap_b = c->chk.tmap;
+    alignas(64) CUtensorMap tmap_a = c->img.tmap, tmap_b = plan.pairs ? c->chk.tmap_half : c->chk.tmap;
     char msg[256];
     if (row0 != 0 || n_rows != img.n) {
         if (encode_tensor_map(&tmap_a, img.emb_bf16 + row0 * img.D, n_rows, img.D, 128, msg, sizeof msg)) return fail(c, MMALIGN_ECUDA, "%s", msg);
         img.n = n_rows;
     }
     if (col0 != 0 || n_cols != chk.n) {
-        if (encode_tensor_map(&tmap_b, chk.emb_bf16 + col0 * chk.D, n_cols, chk.D, 256, msg, sizeof msg)) return fail(c, MMALIGN_ECUDA, "%s", msg);
+        if (encode_tensor_map(&tmap_b, chk.emb_bf16 + col0 * chk.D, n_cols, chk.D, plan.pairs ? 128 : 256, msg, sizeof msg)) return fail(c, MMALIGN_ECUDA, "%s", msg);
         chk.n = n_cols;
     }
     *lists = CandLists();
@@ -754,7 +763,7 @@ static int plan_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n
 {
     if (c->img.s.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", c->img.s.D);
     if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
-    const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, c->sm_count, n_ranks, plan);
+    const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, c->sm_count, n_ranks, plan, c->cta_pairs);
     if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)n_rows, (long long)n_cols, c->img.s.D, kprime_req, prc);
     return MMALIGN_OK;
 }
@@ -1409,13 +1418,13 @@ extern "C" int mmalign_debug_scores(mmalign_ctx *c, float *out, void *stream)
     CU(c, cudaSetDevice(c->device));
     if ((rc = wait_tables(c, st))) return rc;
     FusedPlan plan;
-    if (fused_plan(img.n, chk.n, img.D, 10, 0, c->sm_count, 1, &plan)) return fail(c, MMALIGN_ELIMIT, "no fused plan");
+    if (fused_plan(img.n, chk.n, img.D, 10, 0, c->sm_count, 1, &plan, c->cta_pairs)) return fail(c, MMALIGN_ELIMIT, "no fused plan");
     Stager sg{c, st};
     float *d = nullptr;
     sg.map(out, (size_t)img.n * chk.n, &d);
     if ((rc = sg.commit())) return rc;
     CandLists L;
-    CU(c, launch_fused(img, chk, plan, &c->img.tmap, &c->chk.tmap, L, d, st));
+    CU(c, launch_fused(img, chk, plan, &c->img.tmap, plan.pairs ? &c->chk.tmap_half : &c->chk.tmap, L, d, st));
     if ((rc = sg.copy_back())) return rc;
     CU(c, cudaStreamSynchronize(st));
     return MMALIGN_OK;

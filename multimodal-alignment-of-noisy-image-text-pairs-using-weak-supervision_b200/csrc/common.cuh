@@ -317,8 +317,10 @@ struct FusedPlan {
     size_t smem_bytes;
     int stages;
     bool a_resident;
+    bool pairs;            // CTA pairs (tcgen05.mma.cta_group::2): tensor map B carries 128-row boxes
 };
-int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan);
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan,
+               bool pairs = false);
 cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan, const void *tmap_a,
                          const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st, int64_t col_base = 0);
 int encode_tensor_map(void *tmap_out, const void *base, int64_t rows, int D, int box_rows,

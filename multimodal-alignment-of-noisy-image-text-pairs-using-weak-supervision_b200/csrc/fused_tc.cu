@@ -31,6 +31,7 @@ constexpr int kFusedThreads = 384;
 constexpr uint32_t kABlockBytes = BM * BK * 2;   // 16 KiB: one 64-wide k block of the A tile
 constexpr uint32_t kBStageBytes = BN * BK * 2;   // 32 KiB
 constexpr int kMaxStages = 8;
+constexpr int kMaxPairStages = 12;      // the pair kernel's ring (16 / 32 KiB stages)
 constexpr size_t kSmemLimit = 232448;            // 227 KiB opt-in maximum per CTA
 
 // ---------------------------------------------------------------------------
@@ -64,15 +65,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
 }
+// A wait that lasts seconds is a protocol deadlock, not a long wait (every legitimate wait of this kernel is a
+// few microseconds): trap, so that the launch fails with an error instead of hanging the GPU.
+__device__ __noinline__ void mbar_watchdog(uint64_t &t0)
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > 8000000000ull) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    while (!mbar_try_wait(bar, parity)) { }
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity))
+        if ((++polls & 0xFFFu) == 0) mbar_watchdog(t0);
 }
 // For the single-thread roles: their spin loops would otherwise steal issue slots from the
 // epilogue warps that share their scheduler.
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
 {
-    while (!mbar_try_wait(bar, parity)) __nanosleep(40);
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);
+        if ((++polls & 0xFFFu) == 0) mbar_watchdog(t0);
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1)
 {
@@ -452,14 +472,269 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// The same kernel on CTA pairs: tcgen05.mma.cta_group::2, M = 256 (two 128-image row blocks, one per CTA of a
+// 2-CTA cluster = the two SMs of a TPC), N = 256.  Each CTA holds its own A rows and HALF of every B k-slice
+// (128 chunks x 64): 16 KiB of B per stage and CTA instead of 32, so the ring is twice as deep in k and every B
+// byte is read from L2 by one SM of the pair instead of both.
+//   * both CTAs run a TMA producer (warp 0); every load signals the LEADER's (cluster rank 0) full barrier
+//     (.cta_group::2 load, barrier address with the peer bit cleared); the leader expects the bytes of both
+//   * only the leader issues MMAs (warp 1); its tcgen05.commit is multicast to the barriers of both CTAs
+//     (stage free, accumulator ready, A rows free)
+//   * both CTAs run the epilogue on their own TMEM (their 128 rows of the 256 x 256 accumulator); the 2 x 256
+//     epilogue threads hand an accumulator back by arriving on the leader's tmem_empty barrier
+// Row blocks are handed out in pairs (2p, 2p + 1); an odd count is padded with a phantom block whose rows TMA fills
+// with zeros and whose lists nobody reads.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;       // shared::cluster address of the same offset in cluster rank 0
+constexpr uint32_t kBHalfBytes = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half of a B k-slice
+constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void *tmap, uint32_t leader_bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tmap), "r"(leader_bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar)  // arrives on `bar` in both CTAs when the MMAs retire
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar)  // on the barrier at this offset in cluster rank 0
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(bar), "r"(0u) : "memory");
+}
+
+template <int KPL, bool A_RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
+fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                             const FusedArgs P)
+{
+    constexpr int CAP = 32 * KPL;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_kb = P.num_kb;
+    const uint32_t a_bytes = A_RES ? (uint32_t)num_kb * kABlockBytes : 0u;
+    const uint32_t stage_bytes = kBHalfBytes + (A_RES ? 0u : kABlockBytes);
+    const uint32_t sA = smem_base;
+    const uint32_t sStage = smem_base + a_bytes;
+    const uint32_t sBar = sStage + (uint32_t)P.stages * stage_bytes;
+    const uint32_t bar_full = sBar, bar_empty = sBar + 8u * kMaxPairStages;
+    const uint32_t bar_tfull = sBar + 16u * kMaxPairStages, bar_tempty = bar_tfull + 16u;
+    const uint32_t bar_afull = bar_tempty + 16u, bar_aempty = bar_afull + 8u;
+    const uint32_t tmem_slot = bar_aempty + 8u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 512); }
+        mbar_init(bar_afull, 1);
+        mbar_init(bar_aempty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers exist before anything signals them
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int64_t n_pairs = P.n_row_blocks / 2;  // the plan pads n_row_blocks to an even count
+    const int64_t n_units = n_pairs * P.n_splits;
+    const int64_t cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+            int stage = 0;
+            uint32_t phase = 0, uphase = 0;
+            for (int64_t u = cluster_id; u < n_units; u += n_clusters) {
+                const int64_t rb = 2 * (u % n_pairs) + rank;
+                const int sp = (int)(u / n_pairs);
+                const int64_t t0 = (int64_t)sp * P.tiles_per_split;
+                const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
+                if (A_RES) {
+                    mbar_wait_relaxed(bar_aempty, uphase ^ 1u);  // (own copy; the leader's commit reaches both)
+                    if (leader) mbar_expect_tx(bar_afull, 2u * a_bytes);
+                    for (int kb = 0; kb < num_kb; ++kb)
+                        tma_load_2d_pair(sA + kb * kABlockBytes, &tmap_a, bar_afull, kb * BK, (int)(rb * BM));
+                    uphase ^= 1u;
+                }
+                for (int64_t t = t0; t < t1; ++t) {
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1u);
+                        const uint32_t dst = sStage + stage * stage_bytes;
+                        if (leader) mbar_expect_tx(bar_full + 8u * stage, 2u * stage_bytes);
+                        tma_load_2d_pair(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN + rank * (BN / 2)));
+                        if (!A_RES)
+                            tma_load_2d_pair(dst + kBHalfBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
+                        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader only) =====================
+        if (leader && lane == 0) {
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, uphase = 0;
+            for (int64_t u = cluster_id; u < n_units; u += n_clusters) {
+                const int sp = (int)(u / n_pairs);
+                const int64_t t0 = (int64_t)sp * P.tiles_per_split;
+                const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
+                if (A_RES) { mbar_wait(bar_afull, uphase); uphase ^= 1u; }
+                for (int64_t t = t0; t < t1; ++t) {
+                    mbar_wait_relaxed(bar_tempty + 8u * acc, acc_phase ^ 1u);  // both epilogues have drained it
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        mbar_wait(bar_full + 8u * stage, phase);
+                        tc_fence_after();
+                        const uint32_t b_addr = sStage + stage * stage_bytes;
+                        const uint32_t a_addr = A_RES ? sA + kb * kABlockBytes : b_addr + kBHalfBytes;
+                        const uint64_t adesc = umma_desc_sw128(a_addr);
+                        const uint64_t bdesc = umma_desc_sw128(b_addr);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdescPair,
+                                             (uint32_t)((kb | k) != 0));
+                        tc_commit_pair(bar_empty + 8u * stage);
+                        if (++stage == P.stages) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit_pair(bar_tfull + 8u * acc);
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                }
+                if (A_RES) tc_commit_pair(bar_aempty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int quad = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int r = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t u = cluster_id; u < n_units; u += n_clusters) {
+            const int64_t rb = 2 * (u % n_pairs) + rank;
+            const int sp = (int)(u / n_pairs);
+            const int64_t t0 = (int64_t)sp * P.tiles_per_split;
+            const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
+            const int64_t list_id = (((int64_t)sp * P.n_row_blocks + rb) * 2 + half) * 128 + r;
+            const char *ubase = reinterpret_cast<const char *>(P.keys + (list_id - (half * 128 + r)) * CAP);
+            const uint32_t off0 = (uint32_t)(half * 128 + r) * (uint32_t)(CAP * 8);
+            float tau = P.tau_init;
+            int n = 0;
+            const int64_t row = rb * BM + r;
+            for (int64_t t = t0; t < t1; ++t) {
+                mbar_wait(bar_tfull + 8u * acc, acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+                const int64_t col0 = t * BN + half * 128;
+                if (P.dump) {
+#pragma unroll 1
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t v[32];
+                        __syncwarp();
+                        tmem_ld32(taddr + ch * 32, v);
+                        tmem_ld_wait(v);
+                        if (row < P.N)
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (col0 + ch * 32 + k < P.M) P.dump[row * P.M + col0 + ch * 32 + k] = __uint_as_float(v[k]);
+                    }
+                    tc_fence_before();
+                    mbar_arrive_rank0(bar_tempty + 8u * acc);
+                } else {
+                    uint32_t va[32], vb[32];
+                    __syncwarp();
+                    tmem_ld32(taddr, va);
+                    tmem_ld_wait(va);
+                    tmem_ld32(taddr + 32, vb);
+                    process_chunk<KPL>(va, col0, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    __syncwarp();
+                    tmem_ld_wait(vb);
+                    tmem_ld32(taddr + 64, va);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    __syncwarp();
+                    tmem_ld_wait(va);
+                    tmem_ld32(taddr + 96, vb);
+                    process_chunk<KPL>(va, col0 + 64, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    __syncwarp();
+                    tmem_ld_wait(vb);
+                    tc_fence_before();
+                    mbar_arrive_rank0(bar_tempty + 8u * acc);  // 2 x 256 arrivals free the accumulator for the pair
+                    process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    __syncwarp();
+                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
+                        compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > CAP - kCompactMargin);
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+            if (!P.dump && !P.skip_final) {
+                __syncwarp();
+                if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
+                    compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > P.kprime + kSlack);
+            }
+            if (!P.dump) {
+                P.tau[list_id] = tau;
+                P.count[list_id] = n;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // neither CTA leaves (or frees its TMEM) while the other may still signal its barriers
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan)
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan, bool pairs)
 {
     if (D % BK != 0 || D < BK || N <= 0 || M <= 0) return -1;
     FusedPlan p = {};
     p.n_row_blocks = (N + BM - 1) / BM;
+    p.pairs = pairs && sm_count % 2 == 0;
+    if (p.pairs) p.n_row_blocks = (p.n_row_blocks + 1) & ~(int64_t)1;  // whole pairs; a phantom block's lists are never read
     const int64_t n_tiles = (M + BN - 1) / BN;
     // column splits: the fewest that keep the last wave of persistent CTAs >= 95 % full
     int best = 1;
@@ -516,15 +791,16 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     if (const char *e = getenv("MMALIGN_A_RESIDENT")) p.a_resident = p.a_resident && atoi(e) != 0;
 #endif
     const size_t a_bytes = p.a_resident ? (size_t)(D / BK) * kABlockBytes : 0;
-    const size_t stage_bytes = kBStageBytes + (p.a_resident ? 0 : kABlockBytes);
+    const size_t stage_bytes = (p.pairs ? kBHalfBytes : kBStageBytes) + (p.a_resident ? 0 : kABlockBytes);
     const size_t fixed = 1024 /*alignment slack*/ + a_bytes + 256 /*barriers*/;
     int stages = (int)((kSmemLimit - fixed) / stage_bytes);
-    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages > (p.pairs ? kMaxPairStages : kMaxStages)) stages = p.pairs ? kMaxPairStages : kMaxStages;
     if (stages < 2) return -3;
     p.stages = stages;
     p.smem_bytes = fixed + (size_t)stages * stage_bytes;
     const int64_t units = p.n_row_blocks * p.n_splits;
     p.grid = (int)(units < sm_count ? units : sm_count);
+    if (p.pairs) p.grid &= ~1;  // whole clusters
     *plan = p;
     return 0;
 }
@@ -561,6 +837,17 @@ int encode_tensor_map(void *tmap_out, const void *base, int64_t rows, int D, int
         return -1;
     }
     return 0;
+}
+
+template <int KPL, bool A_RES>
+static cudaError_t launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, const FusedArgs &args,
+                                       const FusedPlan &plan, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(fused_score_topk_pair_kernel<KPL, A_RES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    fused_score_topk_pair_kernel<KPL, A_RES><<<plan.grid, kFusedThreads, plan.smem_bytes, st>>>(ta, tb, args);  // __cluster_dims__(2)
+    return cudaGetLastError();
 }
 
 template <int KPL, bool A_RES>
@@ -601,8 +888,10 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;
     lists.kprime = plan.kprime;
     lists.kprime_list = plan.kprime_list;
-#define VARIANT(KPL) (plan.a_resident ? launch_variant<KPL, true>(ta, tb, a, plan, st) \
-                                      : launch_variant<KPL, false>(ta, tb, a, plan, st))
+#define VARIANT(KPL) (plan.pairs ? (plan.a_resident ? launch_pair_variant<KPL, true>(ta, tb, a, plan, st)      \
+                                                    : launch_pair_variant<KPL, false>(ta, tb, a, plan, st)) \
+                                  : (plan.a_resident ? launch_variant<KPL, true>(ta, tb, a, plan, st)           \
+                                                    : launch_variant<KPL, false>(ta, tb, a, plan, st)))
     switch (plan.cap) {
     case 128: return VARIANT(4);
     case 256: return VARIANT(8);
