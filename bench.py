@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--kprime", type=int, default=0)
     ap.add_argument("--pipeline-rows", type=int, default=0, help="query rows per pipeline slab of mmalign_run (0 = auto)")
+    ap.add_argument("--cta-pairs", type=int, default=-1, help="fused kernel on CTA pairs (cta_group::2): 1 / 0, -1 = library default")
     ap.add_argument("--exchange", default="auto", choices=["auto", "alltoall", "allgather", "none"],
                     help="multi-GPU: none = contraction and rescoring both sharded by query rows (no list exchange); "
                          "alltoall = contraction sharded by chunk columns, rescoring by query rows; auto (default) = none "
@@ -393,6 +394,8 @@ def run_ours(args):
     args.gpus = world
     r0, r1 = distributed.shard_range(M, world, rank)
     eng = pkg.AlignmentEngine(local)
+    if args.cta_pairs >= 0:
+        eng.set_option("cta_pairs", args.cta_pairs)
     run_kw = dict(schemas=args.schema_list, k_values=args.k_values, mrr_cutoff=MRR_CUTOFF, weak_weight=args.weak,
                   kprime=args.kprime, candidates=args.candidates)
     phase_ms, step_ms = {}, {}

@@ -22,6 +22,15 @@ def eng(pkg):
     e.close()
 
 
+@pytest.fixture(scope="module")
+def eng_pairs(pkg):
+    """An engine whose fused kernel runs on CTA pairs (tcgen05.mma.cta_group::2)."""
+    e = pkg.AlignmentEngine(0)
+    e.set_option("cta_pairs", 1)
+    yield e
+    e.close()
+
+
 def load(eng, img, chk, T=0):
     eng.set_images(img["emb"], img["key"], img.get("bbox"), img.get("terms"))
     eng.set_chunks(chk["emb"], chk["key"], chk.get("bbox"), chk.get("terms"), n_terms=T)
@@ -202,6 +211,52 @@ def test_fused_raw_scores_match_bf16_matmul(eng, synthetic):
         # tolerance: the tensor cores accumulate in fp32 with truncation; measured 2.9e-5 at D=512.
         # The row certificate (rescore.cu) budgets D * 2.4e-7 = 1.2e-4 for it.
         assert np.abs(got - want).max() < D * 1.2e-7, (N, M, D, np.abs(got - want).max())
+
+
+def test_cta_pair_raw_scores(eng_pairs, synthetic):
+    """The CTA-pair kernel's tile scores against an fp64 product of the very bf16 operands: row blocks in pairs
+    (odd counts padded by a phantom block), B halves of 128 columns per CTA, ragged last tiles, D from 64 to 1024
+    (A rows resident in shared memory up to D = 512, streamed with B beyond)."""
+    import torch
+    for N, M, D in [(128, 256, 64), (256, 512, 64), (200, 700, 128), (300, 1000, 512), (130, 300, 768), (700, 1500, 1024),
+                    (1000, 40000, 256)]:
+        img, chk, _ = synthetic.make_numpy(N, M, D, seed=5)
+        load(eng_pairs, img, chk)
+        got = eng_pairs.debug_scores()
+        a, b = eng_pairs.debug_operands()
+        want = (torch.from_numpy(a).cuda().double() @ torch.from_numpy(b).cuda().double().T).cpu().numpy()
+        assert np.abs(got - want).max() < D * 1.2e-7, (N, M, D, np.abs(got - want).max())
+
+
+@pytest.mark.parametrize("N,M,D,ks,cutoff", [
+    (300, 1000, 128, (1, 5, 10), 20), (1000, 5000, 512, (1, 5, 10, 20), 100), (130, 2000, 64, (1, 5, 10, 20), 100),
+    (513, 3000, 256, (10,), 10), (256, 4096, 768, (1, 5, 10, 20), 30), (200, 3000, 1024, (1, 5, 10, 20), 100),
+    (20000, 30000, 128, (1, 5, 10, 20), 100),
+])
+def test_cta_pair_path_matches_oracle(oracle, eng_pairs, synthetic, N, M, D, ks, cutoff):
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=512, seed=3)
+    if N > 5000:      # many units per CTA pair: the oracle checks a sample of rows, pipelined in small slabs
+        load(eng_pairs, img, chk, 512)
+        r = eng_pairs.run(ALL4, candidates="all", k_values=ks, mrr_cutoff=cutoff, weak_weight=(0.3, 0.2), pipeline_rows=8192)
+        rows = np.arange(0, N, 97)
+        sub = {k: (v[rows] if v is not None else None) for k, v in img.items()}
+        o = oracle.evaluate(sub, chk, T=512, schema_mask=15, candidates="all", lam=(0.3, 0.2, 0.5), kmax=max(ks), cutoff=cutoff)
+        assert np.array_equal(r["topk_idx"][:, rows], o["topk_idx"]) and np.array_equal(r["topk_score"][:, rows], o["topk_score"])
+        assert r["stats"]["slabs"] == 3 and r["stats"]["eps_violations"] == 0
+        return
+    r = check_against_oracle(oracle, eng_pairs, img, chk, 512, candidates="all", lam=(0.3, 0.2), ks=ks, cutoff=cutoff)
+    assert r["stats"]["fused_launches"] == 1
+
+
+def test_cta_pair_ties_and_groups(oracle, eng_pairs, synthetic):
+    img, chk, _ = synthetic.make_numpy(256, 3000, 128, T=64, seed=9)
+    chk["emb"][100:400] = chk["emb"][100]          # 300 identical chunks: a wall of equal scores
+    img["emb"][7] = chk["emb"][100]
+    r = check_against_oracle(oracle, eng_pairs, img, chk, 64, candidates="all", lam=(0.1, 0.1), ks=(1, 5, 10), cutoff=20,
+                             kprime=20)
+    assert r["stats"]["rows_rescanned"] > 0
+    check_against_oracle(oracle, eng_pairs, img, chk, 64, candidates="all", lam=(0.1, 0.1), ks=(1, 5, 10), cutoff=20,
+                         pipeline_rows=128, inputs="pinned", pinned_outputs=True)
 
 
 @pytest.mark.parametrize("N,M,D,ks,cutoff", [
