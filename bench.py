@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--kprime", type=int, default=0)
     ap.add_argument("--pipeline-rows", type=int, default=0, help="query rows per pipeline slab of mmalign_run (0 = auto)")
+    ap.add_argument("--option", action="append", help="name=value for mmalign_set_option (repeatable)")
     ap.add_argument("--cta-pairs", type=int, default=-1, help="fused kernel on CTA pairs (cta_group::2): 1 / 0, -1 = library default")
     ap.add_argument("--exchange", default="auto", choices=["auto", "alltoall", "allgather", "none"],
                     help="multi-GPU: none = contraction and rescoring both sharded by query rows (no list exchange); "
@@ -396,6 +397,9 @@ def run_ours(args):
     eng = pkg.AlignmentEngine(local)
     if args.cta_pairs >= 0:
         eng.set_option("cta_pairs", args.cta_pairs)
+    for kv in args.option or []:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     run_kw = dict(schemas=args.schema_list, k_values=args.k_values, mrr_cutoff=MRR_CUTOFF, weak_weight=args.weak,
                   kprime=args.kprime, candidates=args.candidates)
     phase_ms, step_ms = {}, {}

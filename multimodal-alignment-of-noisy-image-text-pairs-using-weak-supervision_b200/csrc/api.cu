@@ -111,6 +111,7 @@ struct mmalign_ctx {
     PairIndex px;
     bool px_ready = false;
     bool chk_consumed = true;      // a run has read the chunk table since the last set_chunks
+    int epi_sleep_ns = 0;          // mmalign_set_option: pause between polls of the epilogue's accumulator barrier
     bool cta_pairs = false;        // the fused kernel on CTA pairs (tcgen05.mma.cta_group::2): mmalign_set_option
     size_t piece_bytes = (size_t)64 << 20;  // host embedding rows travel in pieces of about this size (mmalign_set_option)
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
@@ -229,6 +230,11 @@ extern "C" int mmalign_set_option(mmalign_ctx *c, const char *name, int64_t valu
     if (!strcmp(name, "piece_bytes")) {
         if (value < 1024 || value > ((int64_t)1 << 34)) return fail(c, MMALIGN_EINVAL, "piece_bytes=%lld must be in 1 KiB..16 GiB", (long long)value);
         c->piece_bytes = (size_t)value;
+        return MMALIGN_OK;
+    }
+    if (!strcmp(name, "epi_sleep_ns")) {
+        if (value < 0 || value > 100000) return fail(c, MMALIGN_EINVAL, "epi_sleep_ns=%lld must be in 0..100000", (long long)value);
+        c->epi_sleep_ns = (int)value;
         return MMALIGN_OK;
     }
     if (!strcmp(name, "cta_pairs")) {
@@ -765,6 +771,7 @@ static int plan_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n
     if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
     const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, c->sm_count, n_ranks, plan, c->cta_pairs);
     if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)n_rows, (long long)n_cols, c->img.s.D, kprime_req, prc);
+    plan->epi_sleep_ns = c->epi_sleep_ns;
     return MMALIGN_OK;
 }
 

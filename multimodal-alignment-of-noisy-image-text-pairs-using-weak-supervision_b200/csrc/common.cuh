@@ -317,6 +317,7 @@ struct FusedPlan {
     size_t smem_bytes;
     int stages;
     bool a_resident;
+    int epi_sleep_ns;      // pause between the epilogue warps' polls of their accumulator barrier
     bool pairs;            // CTA pairs (tcgen05.mma.cta_group::2): tensor map B carries 128-row boxes
 };
 int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan,

@@ -35,6 +35,27 @@ constexpr int kMaxPairStages = 12;      // the pair kernel's ring (16 / 32 KiB s
 constexpr size_t kSmemLimit = 232448;            // 227 KiB opt-in maximum per CTA
 
 // ---------------------------------------------------------------------------
+// Profiling build (-DMMALIGN_PROFILE_EPI, tools/k1_epilogue_profile.py): where the epilogue warps spend their cycles.
+// ---------------------------------------------------------------------------
+#ifdef MMALIGN_PROFILE_EPI
+__device__ unsigned long long g_epi_prof[16];
+#define EPI_T(var) const long long var = clock64()
+#define EPI_ADD(slot, expr) prof[slot] += (expr)
+extern "C" int mmalign_profile_counters(unsigned long long *out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_epi_prof, sizeof(g_epi_prof));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[16] = {};
+        e = cudaMemcpyToSymbol(g_epi_prof, z, sizeof z);
+    }
+    return (int)e;
+}
+#else
+#define EPI_T(var)
+#define EPI_ADD(slot, expr)
+#endif
+
+// ---------------------------------------------------------------------------
 // PTX wrappers
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +102,18 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
     uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity))
         if ((++polls & 0xFFFu) == 0) mbar_watchdog(t0);
+}
+// Polling with a pause: the eight epilogue warps wait for an accumulator most of the time (they are ahead of the
+// tensor pipe); a spinning wait is executed instructions, i.e. power, on a kernel that runs against the power cap.
+__device__ __forceinline__ void mbar_wait_paused(uint32_t bar, uint32_t parity, uint32_t ns)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t polls = 0;
+    uint64_t t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (ns) __nanosleep(ns);
+        if ((++polls & 0xFFFu) == 0) mbar_watchdog(t0);
+    }
 }
 // For the single-thread roles: their spin loops would otherwise steal issue slots from the
 // epilogue warps that share their scheduler.
@@ -167,11 +200,12 @@ struct FusedArgs {
     float tau_init;        // -inf; tuning builds (-DMMALIGN_TUNING) can start the lists at a threshold
     int skip_final;        // tuning builds: no end-of-unit compaction
     uint32_t col_base;     // added to the column index of every entry (a launch over a column group of the table)
+    uint32_t epi_sleep_ns; // the epilogue warps poll their accumulator barrier this many ns apart (0 = spin)
 };
 
 // ---------------------------------------------------------------------------
 // Candidate lists.  An entry is 8 bytes: lo = chunk column, hi = fp32 score bits.
-// Thread (row, half) owns list `ubase + off0`; `n` entries are live.
+// Thread (row, half) owns one list of CAP slots; `n` entries are live.
 // ---------------------------------------------------------------------------
 constexpr int kSlack = kListSlack;  // a compaction may keep up to K' + kSlack entries (saves bisection steps)
 constexpr int kCompactMargin = 72;  // routine compaction when fewer than this many slots are free (one tile adds <= 128 - ...)
@@ -179,8 +213,7 @@ constexpr int kCompactMargin = 72;  // routine compaction when fewer than this m
 // Warp-cooperative compaction of the lists of the lanes that ask for it: keeps the best ~K'
 // entries and raises the lane's threshold tau to the smallest kept score.
 template <int KPL>
-__device__ __noinline__ void compact_lists(const char *ubase, uint32_t my_off0, int &n, float &tau, int kprime,
-                                           bool need)
+__device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, int kprime, bool need)
 {
     constexpr int CAP = 32 * KPL;
     const int lane = threadIdx.x & 31;
@@ -189,9 +222,8 @@ __device__ __noinline__ void compact_lists(const char *ubase, uint32_t my_off0, 
     while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
-        const uint32_t off0 = __shfl_sync(0xFFFFFFFFu, my_off0, src);
         const int cnt = __shfl_sync(0xFFFFFFFFu, n, src);
-        uint2 *L = reinterpret_cast<uint2 *>(const_cast<char *>(ubase) + off0);
+        uint2 *L = reinterpret_cast<uint2 *>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_list), src));
         __syncwarp();
         uint32_t h[KPL], c[KPL];  // ordered score key, column
         uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
@@ -242,37 +274,65 @@ __device__ __forceinline__ float max8(const uint32_t *v)
 }
 
 // One 32-column chunk of one accumulator row: append every score above tau to the row's list.
+// Appends the columns of one 8-column group whose score exceeds tau to the thread's list; returns the new write pointer.
+__device__ __noinline__ uint2 *append_group(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4, uint32_t a5,
+                                            uint32_t a6, uint32_t a7, uint32_t c0, float tau, uint2 *wp)
+{
+    if (__uint_as_float(a0) > tau) { *wp = make_uint2(c0, a0); ++wp; }
+    if (__uint_as_float(a1) > tau) { *wp = make_uint2(c0 + 1, a1); ++wp; }
+    if (__uint_as_float(a2) > tau) { *wp = make_uint2(c0 + 2, a2); ++wp; }
+    if (__uint_as_float(a3) > tau) { *wp = make_uint2(c0 + 3, a3); ++wp; }
+    if (__uint_as_float(a4) > tau) { *wp = make_uint2(c0 + 4, a4); ++wp; }
+    if (__uint_as_float(a5) > tau) { *wp = make_uint2(c0 + 5, a5); ++wp; }
+    if (__uint_as_float(a6) > tau) { *wp = make_uint2(c0 + 6, a6); ++wp; }
+    if (__uint_as_float(a7) > tau) { *wp = make_uint2(c0 + 7, a7); ++wp; }
+    return wp;
+}
+
+#ifdef MMALIGN_PROFILE_EPI
+#define PC_PROF , long long *prof
+#define PC_PROF_ARG , prof
+#else
+#define PC_PROF
+#define PC_PROF_ARG
+#endif
 template <int KPL>
-__device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t M, const char *ubase,
-                                              uint32_t off0, int &n, float &tau, int kprime, uint32_t col_base)
+__device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t M, uint2 *list, int &n, float &tau,
+                                              int kprime, uint32_t col_base PC_PROF)
 {
     constexpr int CAP = 32 * KPL;
+    EPI_T(p0_);
     if (col0 + 32 > M) {  // ragged last tile: TMA zero-filled these columns
 #pragma unroll
         for (int k = 0; k < 32; ++k)
             if (col0 + k >= M) v[k] = 0xFF800000u;  // -inf
     }
-    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) compact_lists<KPL>(ubase, off0, n, tau, kprime, n > CAP - 32);
+    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) compact_lists<KPL>(list, n, tau, kprime, n > CAP - 32);
     float g[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) g[q] = max8(v + 8 * q);
     const float m = fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3]));
+    EPI_T(p1_);
+    EPI_ADD(8, p1_ - p0_);  // maxima + vote
     if (__any_sync(0xFFFFFFFFu, m > tau)) {
-        uint32_t woff = off0 + 8u * (uint32_t)n;
+        EPI_ADD(9, 1);      // chunks with a hit
+        // Appends are rare once tau has risen, and the sixteen call sites of a tile (4 chunks x 4 groups) would each
+        // carry their own copy of the append code: kept out of line, ONE copy serves them all and stays in the
+        // instruction cache (the inlined copies were measured at ~430 cycles per 8-column group with a hit, most
+        // of it instruction fetch).
+        uint2 *wp = list + n;
         const uint32_t c0 = (uint32_t)col0 + col_base;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (__any_sync(0xFFFFFFFFu, g[q] > tau)) {
-#pragma unroll
-                for (int k = 8 * q; k < 8 * q + 8; ++k) {
-                    if (__uint_as_float(v[k]) > tau) {
-                        *reinterpret_cast<uint2 *>(const_cast<char *>(ubase) + woff) = make_uint2(c0 + k, v[k]);
-                        woff += 8u;
-                    }
-                }
+                EPI_ADD(10, 1);  // 8-column groups with a hit
+                wp = append_group(v[8 * q], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], v[8 * q + 4], v[8 * q + 5],
+                                  v[8 * q + 6], v[8 * q + 7], c0 + 8 * q, tau, wp);
             }
         }
-        n = (int)((woff - off0) >> 3);
+        n = (int)(wp - list);
+        EPI_T(p2_);
+        EPI_ADD(11, p2_ - p1_);  // the hit path
     }
 }
 
@@ -302,7 +362,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 256); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 8); }  // one arrival per epilogue warp
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -392,20 +452,25 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         const int r = quad * 32 + lane;     // image row within the block
         int acc = 0;
         uint32_t acc_phase = 0;
+#ifdef MMALIGN_PROFILE_EPI
+        long long prof[12] = {};
+        const long long prof_t0 = clock64();
+#endif
         for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int64_t rb = u % P.n_row_blocks;
             const int sp = (int)(u / P.n_row_blocks);
             const int64_t t0 = (int64_t)sp * P.tiles_per_split;
             const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
             const int64_t list_id = (((int64_t)sp * P.n_row_blocks + rb) * 2 + half) * 128 + r;
-            // uniform base of this unit's 256 lists + a 32-bit per-thread offset
-            const char *ubase = reinterpret_cast<const char *>(P.keys + (list_id - (half * 128 + r)) * CAP);
-            const uint32_t off0 = (uint32_t)(half * 128 + r) * (uint32_t)(CAP * 8);
+            uint2 *const list = reinterpret_cast<uint2 *>(P.keys + list_id * CAP);  // this thread's candidate list
             float tau = P.tau_init;
             int n = 0;
             const int64_t row = rb * BM + r;
             for (int64_t t = t0; t < t1; ++t) {
-                mbar_wait(bar_tfull + 8u * acc, acc_phase);
+                EPI_T(w0_);
+                mbar_wait_paused(bar_tfull + 8u * acc, acc_phase, P.epi_sleep_ns);
+                EPI_T(w1_);
+                EPI_ADD(0, w1_ - w0_);  // waiting for the tensor pipe
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
@@ -422,47 +487,72 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                 if (col0 + ch * 32 + k < P.M) P.dump[row * P.M + col0 + ch * 32 + k] = __uint_as_float(v[k]);
                     }
                     tc_fence_before();
-                    mbar_arrive(bar_tempty + 8u * acc);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
                 } else {
                     // ping-pong: the load of chunk c+1 is in flight while chunk c is filtered
                     uint32_t va[32], vb[32];
                     __syncwarp();
+                    EPI_T(c0_);
                     tmem_ld32(taddr, va);
                     tmem_ld_wait(va);
+                    EPI_T(c1_);
                     tmem_ld32(taddr + 32, vb);
-                    process_chunk<KPL>(va, col0, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
+                    EPI_T(c2_);
                     tmem_ld_wait(vb);
+                    EPI_T(c3_);
                     tmem_ld32(taddr + 64, va);
-                    process_chunk<KPL>(vb, col0 + 32, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
+                    EPI_T(c4_);
                     tmem_ld_wait(va);
+                    EPI_T(c5_);
                     tmem_ld32(taddr + 96, vb);
-                    process_chunk<KPL>(va, col0 + 64, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
+                    EPI_T(c6_);
                     tmem_ld_wait(vb);
-                    tc_fence_before();  // last read of this accumulator: hand it back to the MMA warp
-                    mbar_arrive(bar_tempty + 8u * acc);
-                    process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    EPI_T(c7_);
+                    tc_fence_before();  // last read of this accumulator: hand it back to the MMA warp (every lane's loads
+                    __syncwarp();       // have completed; one arrival per warp)
+                    if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     // Routine compaction happens HERE, after the accumulator went back to the MMA warp, so that its
                     // global-memory latency is off the MMA critical path (the check inside process_chunk only fires
                     // when a single tile overflows the remaining room, i.e. in the first tiles of a sweep).
                     __syncwarp();
-                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
-                        compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > CAP - kCompactMargin);
+                    EPI_T(c8_);
+                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin)) {
+                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin);
+                        EPI_ADD(5, 1);
+                    }
+                    EPI_T(c9_);
+                    EPI_ADD(1, (c1_ - c0_) + (c3_ - c2_) + (c5_ - c4_) + (c7_ - c6_));  // waiting for TMEM loads
+                    EPI_ADD(2, (c2_ - c1_) + (c4_ - c3_) + (c6_ - c5_) + (c8_ - c7_));  // filtering (incl. appends)
+                    EPI_ADD(3, c9_ - c8_);                                              // routine compaction
+                    EPI_ADD(4, 1);                                                      // tiles
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
             if (!P.dump && !P.skip_final) {  // leave at most K' + slack entries per list for the rescoring kernel
                 __syncwarp();
                 if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
-                    compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > P.kprime + kSlack);
+                    compact_lists<KPL>(list, n, tau, P.kprime, n > P.kprime + kSlack);
             }
             if (!P.dump) {
                 P.tau[list_id] = tau;
                 P.count[list_id] = n;
             }
         }
+#ifdef MMALIGN_PROFILE_EPI
+        if (lane == 0) {
+            prof[6] = clock64() - prof_t0;
+            for (int q = 0; q < 12; ++q) if (q != 7) atomicAdd(&g_epi_prof[q], (unsigned long long)prof[q]);
+            atomicAdd(&g_epi_prof[7], 1ull);
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -483,7 +573,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 //   * only the leader issues MMAs (warp 1); its tcgen05.commit is multicast to the barriers of both CTAs
 //     (stage free, accumulator ready, A rows free)
 //   * both CTAs run the epilogue on their own TMEM (their 128 rows of the 256 x 256 accumulator); the 2 x 256
-//     epilogue threads hand an accumulator back by arriving on the leader's tmem_empty barrier
+//     epilogue threads hand an accumulator back by arriving (one lane per warp) on the leader's tmem_empty barrier
 // Row blocks are handed out in pairs (2p, 2p + 1); an odd count is padded with a phantom block whose rows TMA fills
 // with zeros and whose lists nobody reads.
 // ---------------------------------------------------------------------------
@@ -528,7 +618,7 @@ __device__ __forceinline__ void mbar_arrive_rank0(uint32_t bar)  // on the barri
     asm volatile(
         "{\n\t.reg .b32 ra;\n\t"
         "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
         ::"r"(bar), "r"(0u) : "memory");
 }
 
@@ -556,7 +646,7 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 512); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 16); }  // one arrival per epilogue warp of the pair
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -655,13 +745,15 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
             const int64_t t0 = (int64_t)sp * P.tiles_per_split;
             const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
             const int64_t list_id = (((int64_t)sp * P.n_row_blocks + rb) * 2 + half) * 128 + r;
-            const char *ubase = reinterpret_cast<const char *>(P.keys + (list_id - (half * 128 + r)) * CAP);
-            const uint32_t off0 = (uint32_t)(half * 128 + r) * (uint32_t)(CAP * 8);
+            uint2 *const list = reinterpret_cast<uint2 *>(P.keys + list_id * CAP);
             float tau = P.tau_init;
             int n = 0;
             const int64_t row = rb * BM + r;
+#ifdef MMALIGN_PROFILE_EPI
+            long long prof[12] = {};
+#endif
             for (int64_t t = t0; t < t1; ++t) {
-                mbar_wait(bar_tfull + 8u * acc, acc_phase);
+                mbar_wait_paused(bar_tfull + 8u * acc, acc_phase, P.epi_sleep_ns);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
@@ -678,37 +770,39 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                                 if (col0 + ch * 32 + k < P.M) P.dump[row * P.M + col0 + ch * 32 + k] = __uint_as_float(v[k]);
                     }
                     tc_fence_before();
-                    mbar_arrive_rank0(bar_tempty + 8u * acc);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);
                 } else {
                     uint32_t va[32], vb[32];
                     __syncwarp();
                     tmem_ld32(taddr, va);
                     tmem_ld_wait(va);
                     tmem_ld32(taddr + 32, vb);
-                    process_chunk<KPL>(va, col0, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
                     tmem_ld_wait(vb);
                     tmem_ld32(taddr + 64, va);
-                    process_chunk<KPL>(vb, col0 + 32, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
                     tmem_ld_wait(va);
                     tmem_ld32(taddr + 96, vb);
-                    process_chunk<KPL>(va, col0 + 64, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
                     tmem_ld_wait(vb);
                     tc_fence_before();
-                    mbar_arrive_rank0(bar_tempty + 8u * acc);  // 2 x 256 arrivals free the accumulator for the pair
-                    process_chunk<KPL>(vb, col0 + 96, P.M, ubase, off0, n, tau, P.kprime, P.col_base);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);  // 2 x 8 arrivals free the accumulator for the pair
+                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
                     __syncwarp();
                     if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
-                        compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > CAP - kCompactMargin);
+                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin);
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
             if (!P.dump && !P.skip_final) {
                 __syncwarp();
                 if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
-                    compact_lists<KPL>(ubase, off0, n, tau, P.kprime, n > P.kprime + kSlack);
+                    compact_lists<KPL>(list, n, tau, P.kprime, n > P.kprime + kSlack);
             }
             if (!P.dump) {
                 P.tau[list_id] = tau;
@@ -883,6 +977,7 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     a.skip_final = getenv("MMALIGN_SKIP_FINAL") != nullptr;
 #endif
     a.col_base = (uint32_t)col_base;
+    a.epi_sleep_ns = (uint32_t)plan.epi_sleep_ns;
     const CUtensorMap &ta = *reinterpret_cast<const CUtensorMap *>(tmap_a);
     const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;
