@@ -334,7 +334,9 @@ def verify_rows(args, eng, sharded, img, chk, res, world, rank, dev):
     if n_local == 0:
         return {"rows": 0, "ok": True}
     rng = np.random.default_rng(12345)
-    rows = np.sort(rng.choice(n_local, size=min(VERIFY_ROWS, n_local), replace=False))
+    # 64 rows at config 5's 1M x 512 per row; fewer where a row costs more (the oracle scans every column of every sampled row)
+    n_rows = int(max(8, min(VERIFY_ROWS, VERIFY_ROWS * (1e6 * 512) / max(1.0, float(args.M) * args.D))))
+    rows = np.sort(rng.choice(n_local, size=min(n_rows, n_local), replace=False))
     if world > 1 and getattr(sharded, "mode", "") == "rows":     # the engine holds the slab; the chunk table is gathered
         full = {f: sharded._full.get(("chk", f)) for f in ("emb", "key", "bbox", "terms")}
         chk_h = {f: (to_np(v[:args.M]) if v is not None else None) for f, v in full.items()}
