@@ -120,7 +120,8 @@ typedef struct {
                              4: K' used, 5/6/7: microseconds (CUDA events) of the fused
                              kernel / the rescoring kernel / the exact rescan, 8: rows whose
                              re-scored candidates broke the certificate's error bound (they were
-                             rescanned exactly), 9: pipeline slabs of the run, 10..15: 0 */
+                             rescanned exactly), 9: pipeline slabs of the run, 10: SMs the rescoring of a slab
+                             had beside the contraction of the next one (0 = no overlap), 11..15: 0 */
 } mmalign_out;
 
 int mmalign_abi_version(void);

@@ -111,11 +111,13 @@ struct mmalign_ctx {
     PairIndex px;
     bool px_ready = false;
     bool chk_consumed = true;      // a run has read the chunk table since the last set_chunks
+    int k2_sms = 0;                // SMs left to the exact rescoring of slab s while slab s+1 is contracted (0 = no overlap)
     int epi_sleep_ns = 0;          // mmalign_set_option: pause between polls of the epilogue's accumulator barrier
     bool cta_pairs = false;        // the fused kernel on CTA pairs (tcgen05.mma.cta_group::2): mmalign_set_option
     size_t piece_bytes = (size_t)64 << 20;  // host embedding rows travel in pieces of about this size (mmalign_set_option)
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
+    DevBuf list_keys2, list_tau2, list_count2;  // second set: slab s+1 is contracted while slab s is re-scored
     DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     DevBuf term_table, text_off, text_bytes;  // mmalign_term_bitsets: term table, uploads of host texts
@@ -127,8 +129,9 @@ struct mmalign_ctx {
     cudaEvent_t ev[5] = {};        // fused pass / rescore pass timing
     // streams of the context (non-blocking): uploads, chunk preparation, pair index, downloads
     cudaStream_t s_in = nullptr, s_prep = nullptr, s_idx = nullptr, s_out = nullptr;
+    cudaStream_t s_k1 = nullptr, s_k2 = nullptr;  // contraction (high priority) and rescoring when the two overlap
     cudaEvent_t ev_tmp = nullptr;
-    std::vector<cudaEvent_t> ev_slab;  // 4 per slab: start, after fused, after rescore, after exact scan (= slab done)
+    std::vector<cudaEvent_t> ev_slab;  // 5 per slab: start, after fused, after rescore, after exact scan (= slab done), rescore start
     cudaEvent_t resc_wait = nullptr;   // mmalign_rescore_after: one-shot
 };
 
@@ -192,8 +195,13 @@ extern "C" int mmalign_create(mmalign_ctx **out, int device)
     c->sm_count = prop.multiProcessorCount;
     bool ok = c->small.reserve(kSmallBytes) == cudaSuccess;
     for (cudaEvent_t &ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
-    for (cudaStream_t *s : {&c->s_in, &c->s_prep, &c->s_idx, &c->s_out})
+    for (cudaStream_t *s : {&c->s_in, &c->s_prep, &c->s_idx, &c->s_out, &c->s_k2})
         ok = ok && cudaStreamCreateWithFlags(s, cudaStreamNonBlocking) == cudaSuccess;
+    {   // the contraction's CTAs are dispatched before the rescoring's when both kernels are ready
+        int least = 0, greatest = 0;
+        ok = ok && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&c->s_k1, cudaStreamNonBlocking, greatest) == cudaSuccess;
+    }
     ok = ok && cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming) == cudaSuccess;
     for (SideStore *ss : {&c->img, &c->chk})
         for (cudaEvent_t *ev : {&ss->ev_small, &ss->ev_caller, &ss->ev_ready, &ss->ev_group[0], &ss->ev_group[1],
@@ -214,13 +222,13 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     c->img.destroy_events();
     c->chk.destroy_events();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
-                      &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
+                      &c->list_keys2, &c->list_tau2, &c->list_count2, &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
                       &c->term_table, &c->text_off, &c->text_bytes};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_slab) if (e) cudaEventDestroy(e);
     if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
-    for (cudaStream_t s : {c->s_in, c->s_prep, c->s_idx, c->s_out}) if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : {c->s_in, c->s_prep, c->s_idx, c->s_out, c->s_k1, c->s_k2}) if (s) cudaStreamDestroy(s);
     delete c;
 }
 
@@ -230,6 +238,11 @@ extern "C" int mmalign_set_option(mmalign_ctx *c, const char *name, int64_t valu
     if (!strcmp(name, "piece_bytes")) {
         if (value < 1024 || value > ((int64_t)1 << 34)) return fail(c, MMALIGN_EINVAL, "piece_bytes=%lld must be in 1 KiB..16 GiB", (long long)value);
         c->piece_bytes = (size_t)value;
+        return MMALIGN_OK;
+    }
+    if (!strcmp(name, "k2_sms")) {
+        if (value < 0 || value > c->sm_count / 2) return fail(c, MMALIGN_EINVAL, "k2_sms=%lld must be in 0..%d", (long long)value, c->sm_count / 2);
+        c->k2_sms = (int)value;
         return MMALIGN_OK;
     }
     if (!strcmp(name, "epi_sleep_ns")) {
@@ -744,7 +757,7 @@ static int reserve_lists(mmalign_ctx *c, const FusedPlan &plan)
 }
 
 static int launch_fused_range(mmalign_ctx *c, const FusedPlan &plan, int64_t row0, int64_t n_rows, int64_t col0, int64_t n_cols,
-                              cudaStream_t st, CandLists *lists, int64_t list_base = 0, int64_t col_base = 0)
+                              cudaStream_t st, CandLists *lists, int64_t list_base = 0, int64_t col_base = 0, int set = 0)
 {
     Side img = c->img.s, chk = c->chk.s;
     alignas(64) CUtensorMap tmap_a = c->img.tmap, tmap_b = plan.pairs ? c->chk.tmap_half : c->chk.tmap;
@@ -758,18 +771,19 @@ static int launch_fused_range(mmalign_ctx *c, const FusedPlan &plan, int64_t row
         chk.n = n_cols;
     }
     *lists = CandLists();
-    lists->keys = (uint64_t *)c->list_keys.p + list_base * plan.cap;
-    lists->tau = (float *)c->list_tau.p + list_base;
-    lists->count = (int32_t *)c->list_count.p + list_base;
+    lists->keys = (uint64_t *)(set ? c->list_keys2.p : c->list_keys.p) + list_base * plan.cap;
+    lists->tau = (float *)(set ? c->list_tau2.p : c->list_tau.p) + list_base;
+    lists->count = (int32_t *)(set ? c->list_count2.p : c->list_count.p) + list_base;
     CU(c, launch_fused(img, chk, plan, &tmap_a, &tmap_b, *lists, nullptr, st, col_base));
     return MMALIGN_OK;
 }
 
-static int plan_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, int64_t n_rows, int64_t n_cols, FusedPlan *plan)
+static int plan_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_ranks, int64_t n_rows, int64_t n_cols, FusedPlan *plan,
+                      int sms = 0)
 {
     if (c->img.s.D % 64 != 0) return fail(c, MMALIGN_EINVAL, "the fused path needs D %% 64 == 0 (D=%d); use MMALIGN_PATH_EXACT", c->img.s.D);
     if (rp.kneed > 256) return fail(c, MMALIGN_ELIMIT, "kneed=%d exceeds 256", rp.kneed);
-    const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, c->sm_count, n_ranks, plan, c->cta_pairs);
+    const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, sms > 0 ? sms : c->sm_count, n_ranks, plan, c->cta_pairs);
     if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)n_rows, (long long)n_cols, c->img.s.D, kprime_req, prc);
     plan->epi_sleep_ns = c->epi_sleep_ns;
     return MMALIGN_OK;
@@ -794,7 +808,7 @@ static int run_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n_
 
 static int slab_events(mmalign_ctx *c, int n_slabs)
 {
-    while ((int)c->ev_slab.size() < 4 * n_slabs) {
+    while ((int)c->ev_slab.size() < 5 * n_slabs) {
         cudaEvent_t e = nullptr;
         CU(c, cudaEventCreate(&e));
         c->ev_slab.push_back(e);
@@ -834,16 +848,40 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     for (const void *p : large_out) host_out = host_out || (p && !is_device_ptr(p));
     int64_t slab_rows = N > 0 ? N : 1;
     const int64_t wave_rows = (int64_t)c->sm_count * 128;  // one 128-row block per SM
+    bool whole_waves_first = false;
+    // k2_sms > 0: the exact rescoring of slab s runs on a few SMs left free by the contraction of slab s+1
+    int k1_sms = c->sm_count;
+    if (fused_path && !imported && c->k2_sms > 0 && prm->pipeline_rows >= 0) {
+        k1_sms = (c->sm_count - c->k2_sms) & ~1;
+        const int64_t w = (int64_t)k1_sms * 128;
+        if (prm->pipeline_rows > 0 ? N > (int64_t)prm->pipeline_rows : N >= 4 * w) {
+            if (prm->pipeline_rows == 0) slab_rows = N >= 2 * kSlabWaves * w ? kSlabWaves * w : 2 * w;
+        } else k1_sms = c->sm_count;  // a single slab: nothing to overlap
+    }
+    const bool overlap = k1_sms != c->sm_count;
     if (imported || prm->pipeline_rows < 0) { /* one slab */ }
     else if (prm->pipeline_rows > 0) slab_rows = ((int64_t)prm->pipeline_rows + 127) / 128 * 128;
-    else if (c->img.n_pieces > 0 || host_out) {  // auto: whole waves, at least two slabs
-        if (N >= 2 * kSlabWaves * wave_rows) slab_rows = kSlabWaves * wave_rows;
-        else if (N >= 4 * wave_rows) slab_rows = 2 * wave_rows;
+    else if (overlap) { /* chosen above */ }
+    else if ((c->img.n_pieces > 0 || host_out) && N >= 4 * wave_rows) {  // auto: whole waves, at least two slabs
+        slab_rows = N >= 2 * kSlabWaves * wave_rows ? kSlabWaves * wave_rows : 2 * wave_rows;
+    } else if (fused_path && N > wave_rows && N % wave_rows != 0) {
+        // Nothing to overlap, but the row blocks do not fill whole waves of the persistent kernel: one slab of whole
+        // waves (one unit = one row block against every column: two lists per row), and the remainder on its own,
+        // cut by columns to fill the GPU.  Cutting ALL rows by columns instead would give every row several times the
+        // lists and their warm-up (measured at 8 GPUs, 977 row blocks per rank: 108.6 -> ms per rank).
+        whole_waves_first = true;
     }
     if (N > slab_rows * kMaxSlabs) slab_rows = ((N + kMaxSlabs - 1) / kMaxSlabs + 127) / 128 * 128;
-    const int n_slabs = N > 0 ? (int)((N + slab_rows - 1) / slab_rows) : 0;
-    std::vector<int64_t> bounds((size_t)n_slabs + 1), poff;
-    for (int s = 0; s <= n_slabs; ++s) bounds[s] = row0 + ((int64_t)s * slab_rows < N ? (int64_t)s * slab_rows : N);
+    std::vector<int64_t> bounds, poff;
+    if (N > 0 && whole_waves_first) {
+        bounds = {row0, row0 + N / wave_rows * wave_rows, row0 + N};
+    } else if (N > 0) {
+        for (int64_t r = 0; r < N; r += slab_rows) bounds.push_back(row0 + r);
+        bounds.push_back(row0 + N);
+    } else {
+        bounds.push_back(row0);
+    }
+    const int n_slabs = (int)bounds.size() - 1;
     if ((rc = pair_offsets_at(c, bounds, &poff))) return rc;
     const int64_t pair0 = poff[0], P = poff[n_slabs] - poff[0];
     Stager sg{c, st};
@@ -886,14 +924,14 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
                 gplans.resize((size_t)ck.n_groups);
                 bool same = true;
                 for (int g = 0; g < ck.n_groups && same; ++g) {
-                    if ((rc = plan_fused(c, rp, prm->kprime, ck.n_groups, bounds[1] - bounds[0], ck.group_row[g + 1] - ck.group_row[g], &gplans[g]))) return rc;
+                    if ((rc = plan_fused(c, rp, prm->kprime, ck.n_groups, bounds[1] - bounds[0], ck.group_row[g + 1] - ck.group_row[g], &gplans[g], k1_sms))) return rc;
                     same = gplans[g].cap == gplans[0].cap && gplans[g].kprime_list == gplans[0].kprime_list &&
                            gplans[g].n_splits == gplans[0].n_splits && gplans[g].n_lists == gplans[0].n_lists;
                 }
                 if (!same) gplans.clear();
             }
             for (int s = 0; s < n_slabs; ++s) {
-                if ((rc = plan_fused(c, rp, prm->kprime, 1, bounds[s + 1] - bounds[s], M, &plans[s]))) return rc;
+                if ((rc = plan_fused(c, rp, prm->kprime, 1, bounds[s + 1] - bounds[s], M, &plans[s], k1_sms))) return rc;
                 if (s == 0 && !gplans.empty()) { plans[0] = gplans[0]; plans[0].n_lists = gplans[0].n_lists * (int64_t)gplans.size(); }
                 if ((size_t)plans[s].n_lists * plans[s].cap >= (size_t)big.n_lists * big.cap) { big.cap = plans[s].cap; big.n_lists = plans[s].n_lists; }
             }
@@ -902,6 +940,11 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             if ((rc = reserve_lists(c, big))) return rc;
             CU(c, c->list_tau.reserve((size_t)most.n_lists * sizeof(float)));
             CU(c, c->list_count.reserve((size_t)most.n_lists * sizeof(int32_t)));
+            if (overlap) {
+                CU(c, c->list_keys2.reserve((size_t)big.n_lists * big.cap * sizeof(uint64_t)));
+                CU(c, c->list_tau2.reserve((size_t)most.n_lists * sizeof(float)));
+                CU(c, c->list_count2.reserve((size_t)most.n_lists * sizeof(int32_t)));
+            }
         }
     }
     if ((rc = slab_events(c, n_slabs))) return rc;
@@ -928,16 +971,30 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     if (out.pair_rank && SP) CU(c, cudaMemsetAsync(out.pair_rank, 0, SP * sizeof(int32_t), st));
     long long launches = 0, fused_launches = 0, kprime_used = 0;
     ScanScratch pre;
-    // ---- the slabs
+    // ---- the slabs.  Without overlap everything runs on the caller's stream.  With it (k2_sms > 0) the contraction
+    // runs on a high-priority stream with a grid that leaves k2_sms SMs free, and the exact rescoring of slab s
+    // (HBM-bound row gathers) runs on those SMs from a second stream while slab s+1 is contracted; two sets of list
+    // buffers alternate.  The rescoring of the last slab has the GPU to itself.
+    cudaStream_t sk1 = overlap ? c->s_k1 : st, sk2 = overlap ? c->s_k2 : st;
+    if (overlap) {
+        if ((rc = order_after(c, sk1, st))) return rc;
+        if ((rc = order_after(c, sk2, st))) return rc;
+    }
     for (int s = 0; s < n_slabs; ++s) {
         const int64_t r0 = bounds[s], rows = bounds[s + 1] - bounds[s];
         RowRange range;
         range.row0 = r0; range.n_rows = rows;
         range.pair0 = pair0; range.P_out = P;
         range.o_row0 = row0; range.o_rows = N;
-        cudaEvent_t *ev = &c->ev_slab[4 * (size_t)s];
-        if ((rc = prepare_images(c, r0, r0 + rows, st, &launches))) return rc;
-        CU(c, cudaEventRecord(ev[0], st));
+        cudaEvent_t *ev = &c->ev_slab[5 * (size_t)s];
+        if (overlap) {  // (prepare_images orders sk1 behind the uploads it needs)
+            CU(c, cudaStreamWaitEvent(sk1, c->img.ev_small, 0));
+            CU(c, cudaStreamWaitEvent(sk1, c->img.ev_caller, 0));
+            if (c->img.ev_ready_set) CU(c, cudaStreamWaitEvent(sk1, c->img.ev_ready, 0));
+        }
+        if ((rc = prepare_images(c, r0, r0 + rows, sk1, &launches))) return rc;
+        if (overlap && s >= 2) CU(c, cudaStreamWaitEvent(sk1, c->ev_slab[5 * (size_t)(s - 2) + 3], 0));  // its list buffers are free again
+        CU(c, cudaEventRecord(ev[0], sk1));
         if (rp.candidates == MMALIGN_CAND_SAME_PAGE) {
             if ((rc = need_chunks())) return rc;
             CU(c, launch_rescore(img, chk, c->px, rp, nullptr, nullptr, out, nullptr, nullptr, nullptr, cand_counter,
@@ -949,6 +1006,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             launches += 1;
         } else {
             CandLists L;
+            const int set = overlap ? (s & 1) : 0;
             if (imported) {
                 if ((rc = need_chunks())) return rc;
                 L = *imported;
@@ -956,10 +1014,10 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             } else if (s == 0 && !gplans.empty()) {
                 const SideStore &ck = c->chk;
                 for (int g = 0; g < ck.n_groups; ++g) {
-                    CU(c, cudaStreamWaitEvent(st, ck.ev_group[g], 0));
+                    CU(c, cudaStreamWaitEvent(sk1, ck.ev_group[g], 0));
                     CandLists Lg;
-                    if ((rc = launch_fused_range(c, gplans[g], r0, rows, ck.group_row[g], ck.group_row[g + 1] - ck.group_row[g], st, &Lg,
-                                                 (int64_t)g * gplans[0].n_lists, ck.group_row[g]))) return rc;
+                    if ((rc = launch_fused_range(c, gplans[g], r0, rows, ck.group_row[g], ck.group_row[g + 1] - ck.group_row[g], sk1, &Lg,
+                                                 (int64_t)g * gplans[0].n_lists, ck.group_row[g], set))) return rc;
                     if (g == 0) L = Lg;
                 }
                 L.n_splits = gplans[0].n_splits * ck.n_groups;  // one row's lists: n_groups x (splits x 2 halves)
@@ -969,25 +1027,37 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
                 if ((rc = need_chunks())) return rc;
             } else {
                 if ((rc = need_chunks())) return rc;
-                if ((rc = launch_fused_range(c, plans[s], r0, rows, 0, M, st, &L))) return rc;
+                if (overlap) CU(c, cudaStreamWaitEvent(sk1, c->chk.ev_ready, 0));
+                if ((rc = launch_fused_range(c, plans[s], r0, rows, 0, M, sk1, &L, 0, 0, set))) return rc;
                 fused_launches += 1;
                 launches += 1;
                 kprime_used = plans[s].kprime;
             }
-            CU(c, cudaEventRecord(ev[1], st));
+            CU(c, cudaEventRecord(ev[1], sk1));
+            if (overlap) {
+                CU(c, cudaStreamWaitEvent(sk2, ev[1], 0));
+                if (c->chk.ev_ready_set) CU(c, cudaStreamWaitEvent(sk2, c->chk.ev_ready, 0));
+            }
             if (s == 0 && c->resc_wait) {  // the exact rescoring reads the fp32 master rows: mmalign_rescore_after
-                CU(c, cudaStreamWaitEvent(st, c->resc_wait, 0));
+                CU(c, cudaStreamWaitEvent(sk2, c->resc_wait, 0));
                 c->resc_wait = nullptr;
             }
+            CU(c, cudaEventRecord(ev[4], sk2));
             int32_t *fail_rows = (int32_t *)c->fail_rows.p + r0;
             pre.thr = (unsigned long long *)c->fail_thr.p + r0; pre.buf = c->scan_buf.p; pre.cnt = (int32_t *)c->scan_cnt.p;
+            // beside the next slab's contraction the rescoring gets the SMs that were left free: 8 CTAs on each
+            const int64_t k2_grid = overlap && s + 1 < n_slabs ? (int64_t)(c->sm_count - k1_sms) * 8 : 0;
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, fail_rows, slab_fail + s, pre.thr,
-                                 cand_counter, error_flag, nullptr, nullptr, range, st));
-            CU(c, cudaEventRecord(ev[2], st));
-            CU(c, launch_exact_scan(img, chk, c->px, rp, fail_rows, slab_fail + s, 0, out, error_flag, range, &pre, st));
+                                 cand_counter, error_flag, nullptr, nullptr, range, sk2, k2_grid));
+            CU(c, cudaEventRecord(ev[2], sk2));
+            CU(c, launch_exact_scan(img, chk, c->px, rp, fail_rows, slab_fail + s, 0, out, error_flag, range, &pre, sk2));
             launches += 3;
         }
-        CU(c, cudaEventRecord(ev[3], st));
+        CU(c, cudaEventRecord(ev[3], fused_path ? sk2 : st));
+    }
+    if (overlap && n_slabs > 0) {  // the caller's stream continues behind both
+        if ((rc = order_after(c, st, sk1))) return rc;
+        if ((rc = order_after(c, st, sk2))) return rc;
     }
     c->lists_valid = false;  // (the context's lists cover the last slab only)
     tr.mark("queued scoring");
@@ -1002,7 +1072,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     const bool stream_out = sg.any_large();
     if (stream_out) {
         for (int s = 0; s < n_slabs; ++s) {
-            CU(c, cudaStreamWaitEvent(c->s_out, c->ev_slab[4 * (size_t)s + 3], 0));
+            CU(c, cudaStreamWaitEvent(c->s_out, c->ev_slab[5 * (size_t)s + 3], 0));
             if ((rc = sg.copy_slab(c->s_out, bounds[s] - row0, bounds[s + 1] - row0, N, poff[s] - pair0, poff[s + 1] - pair0, P))) return rc;
         }
     }
@@ -1027,22 +1097,22 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         if (!fused_path) {  // same-page candidates: the rescoring kernel alone; exact path: the scan alone
             for (int s = 0; s < n_slabs; ++s) {
                 float a = 0.f;
-                cudaEventElapsedTime(&a, c->ev_slab[4 * (size_t)s], c->ev_slab[4 * (size_t)s + 3]);
+                cudaEventElapsedTime(&a, c->ev_slab[5 * (size_t)s], c->ev_slab[5 * (size_t)s + 3]);
                 (rp.candidates == MMALIGN_CAND_SAME_PAGE ? t_resc : t_scan) += a;
             }
         } else {
             for (int s = 0; s < n_slabs; ++s) {
                 float a = 0.f, b = 0.f, d = 0.f;
-                const cudaEvent_t *ev = &c->ev_slab[4 * (size_t)s];
+                const cudaEvent_t *ev = &c->ev_slab[5 * (size_t)s];
                 if (fused_launches) cudaEventElapsedTime(&a, ev[0], ev[1]);
-                cudaEventElapsedTime(&b, ev[1], ev[2]);
+                cudaEventElapsedTime(&b, ev[4], ev[2]);
                 cudaEventElapsedTime(&d, ev[2], ev[3]);
                 t_fused += a; t_resc += b; t_scan += d;
             }
         }
         const int64_t stats[16] = {n_fail, (int64_t)h.cand, imported ? 1 : fused_launches, launches + (imported ? 2 : 0), kprime_used,
                                    imported ? c->last_fused_us : (int64_t)(t_fused * 1000.0), (int64_t)(t_resc * 1000.0),
-                                   (int64_t)(t_scan * 1000.0), (int64_t)h.viol, n_slabs};
+                                   (int64_t)(t_scan * 1000.0), (int64_t)h.viol, n_slabs, overlap ? c->sm_count - k1_sms : 0};
         CU(c, cudaMemcpy(uo->stats, stats, sizeof stats, cudaMemcpyDefault));
     }
     tr.mark("status");

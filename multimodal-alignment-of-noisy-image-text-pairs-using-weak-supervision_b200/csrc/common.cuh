@@ -263,7 +263,7 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
-                           int32_t *cert_count, RowRange rows, cudaStream_t st);
+                           int32_t *cert_count, RowRange rows, cudaStream_t st, int64_t grid_limit = 0);
 // scratch of the two-stage exact scan: per failed row (slot) its threshold, and what stage 1 kept for it
 constexpr int kScanSlots = 2048, kScanCap = 1024;
 struct ScanScratch {

@@ -21,6 +21,24 @@
 
 namespace mma {
 
+#ifdef MMALIGN_PROFILE_EPI   // the profiling build (make prof): where the rescoring kernel's CTAs spend their cycles
+__device__ unsigned long long g_k2_prof[16];
+#define K2_T(var) const long long var = clock64()
+#define K2_ADD(slot, expr) do { if (threadIdx.x == 0) atomicAdd(&g_k2_prof[slot], (unsigned long long)(expr)); } while (0)
+extern "C" int mmalign_profile_k2(unsigned long long *out, int reset)
+{
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_k2_prof, sizeof(g_k2_prof));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[16] = {};
+        e = cudaMemcpyToSymbol(g_k2_prof, z, sizeof z);
+    }
+    return (int)e;
+}
+#else
+#define K2_T(var)
+#define K2_ADD(slot, expr)
+#endif
+
 constexpr int kThreads = 128;  // small CTAs: 8 rows in flight per SM hide the per-row chain of dependent loads
 constexpr int kWarps = kThreads / 32;
 constexpr int kEntCapMax = 1024;  // candidates + same-page entries handled per row (shared-memory sized per launch)
@@ -335,6 +353,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
     // depth the lists must be final to: the top-K lists, or the full exact depth when the caller takes deep_idx
     const int kcert = A.out.deep_idx ? rp.kneed : rp.kmax;
     // exact cosine of the candidates
+    K2_T(f0_);
     const float na = A.img_n2[i];
     for (int e = c + warp; e < n; e += 2 * kWarps) {
         const int e1 = e + kWarps;
@@ -357,7 +376,11 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         if (approx && certify && !(fabs(x - (double)approx[e - c]) <= eps)) s_viol = 1;
     }
     __syncthreads();
+    K2_T(f1_);
     sort_keys(sm.buf, n_ca);
+    K2_T(f2_);
+    K2_ADD(5, f1_ - f0_);   // candidate gathers + fp64 cosine
+    K2_ADD(6, f2_ - f1_);   // sort by exact score
     bool ok = !s_viol;
     if (s_viol && threadIdx.x == 0 && A.viol_counter) atomicAdd(A.viol_counter, 1ull);
     for (int si = 0; si < rp.S; ++si) {
@@ -423,6 +446,8 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
         if (cert_count && threadIdx.x == 0) cert_count[(int64_t)si * A.o_rows + io] = certify ? s_cert : rp.kneed;
         __syncthreads();
     }
+    K2_T(f3_);
+    K2_ADD(7, f3_ - f2_);   // per-schema merge, outputs
     return ok;
 }
 
@@ -489,10 +514,13 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
     unsigned long long *packed = reinterpret_cast<unsigned long long *>(sm.buf);  // the union, before it is re-scored
     for (int64_t b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
         const int64_t i = A.row0 + b;
+        K2_T(r0_);
         const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
         if (threadIdx.x == 0) { s_nca = 0; s_tau = -CUDART_INF_F; s_theta = ~0ull; }
         stage_row(A, sm, i);
         __syncthreads();
+        K2_T(r1_);
+        K2_ADD(0, r1_ - r0_);   // stage the query row
         bool ok = c <= A.sp_cap;
         unsigned long long thr = 0ull;  // lower bound of the row's kneed-th best exact cosine, for the exact scan
         if (!use_lists) {
@@ -515,6 +543,8 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                 if (threadIdx.x == 0) s_tau = t;
             }
             score_same_page(A, sm, i, c);  // (its barriers also publish s_tau / s_lcnt / s_lkeys)
+            K2_T(r2_);
+            K2_ADD(1, r2_ - r1_);   // list headers + same-page entries (weak terms, gathers, fp64 cosine)
             // the union of the lists is complete above this (fully sharded runs: the maximum over all ranks)
             const float tau_union = tau_global ? fmaxf(tau_global[i], s_tau) : s_tau;
             if (tau_union == CUDART_INF_F) ok = false;
@@ -545,10 +575,14 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                     }
                 }
                 __syncthreads();
+                K2_T(r3_);
+                K2_ADD(2, r3_ - r2_);   // sweep of the candidate lists
                 const int n_all = s_nca;
                 if (n_all + c > A.ent_cap) ok = false;
                 if (ok) {
                     sort_block<PackedOps>(packed, n_all);  // by approximate score, lower column first
+                    K2_T(r4_);
+                    K2_ADD(3, r4_ - r3_);   // sort by approximate score
                     for (int e = threadIdx.x; e < n_all; e += kThreads) sm.approx[e] = packed_score(packed[e]);
                     __syncthreads();
                     if (n_all >= rp.kneed) thr = ord64((double)sm.approx[rp.kneed - 1] - eps);
@@ -575,6 +609,9 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                     const double bound = (double)(n_ca < n_all ? fmaxf(sm.approx[n_ca], tau_union) : tau_union) + eps;
                     for (int e = threadIdx.x; e < n_ca; e += kThreads) sm.cols[c + e] = packed_col(packed[e]);
                     __syncthreads();
+                    K2_T(r5_);
+                    K2_ADD(4, r5_ - r4_);   // depth of the exact rescoring (theta)
+                    K2_ADD(8, 1);
                     if (threadIdx.x == 0 && cand_counter) atomicAdd(cand_counter, (unsigned long long)(n_ca + c));
                     if (tau_global) finish_row(A, sm, i, n_ca, bound, eps, nullptr, 0, cert_count);  // certified after the cross-rank count
                     else ok = finish_row(A, sm, i, n_ca, bound, eps, sm.approx, n_all);
@@ -774,7 +811,7 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
-                           int32_t *cert_count, RowRange range, cudaStream_t st)
+                           int32_t *cert_count, RowRange range, cudaStream_t st, int64_t grid_limit)
 {
     if (img.n == 0) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
@@ -787,6 +824,7 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     cudaError_t e = cudaFuncSetAttribute(rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int64_t grid = A.n_rows < (int64_t)sm_count() * 16 ? A.n_rows : (int64_t)sm_count() * 16;
+    if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;  // (the rows are handed out with a grid stride)
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
                                                            fail_count, fail_thr, cand_counter, tau_global, cert_count);
     return cudaGetLastError();

@@ -281,7 +281,8 @@ class AlignmentEngine:
                    stats=dict(rows_rescanned=int(stats[0]), candidates_rescored=int(stats[1]),
                               fused_launches=int(stats[2]), kernel_launches=int(stats[3]),
                               kprime=int(stats[4]), fused_us=int(stats[5]), rescore_us=int(stats[6]),
-                              exact_scan_us=int(stats[7]), eps_violations=int(stats[8]), slabs=int(stats[9])),
+                              exact_scan_us=int(stats[7]), eps_violations=int(stats[8]), slabs=int(stats[9]),
+                              k2_sms=int(stats[10])),
                    schemas=[s for s in SCHEMAS if SCHEMA_BITS[s] & mask], k_values=ks)
         return res
 

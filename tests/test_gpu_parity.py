@@ -362,6 +362,30 @@ def test_first_slab_by_column_groups(oracle, pkg, synthetic, order, eps_scale):
         e.close()
 
 
+@pytest.mark.parametrize("eps_scale", [0.0, 100.0])
+@pytest.mark.parametrize("inputs", ["device", "pinned"])
+def test_rescoring_beside_contraction(oracle, pkg, synthetic, eps_scale, inputs):
+    """mmalign_set_option k2_sms: the exact rescoring of slab s on a few SMs while slab s+1 is contracted (two
+    streams, alternating list buffers).  Same bytes as the oracle, also when every row goes through the exact scan."""
+    img, chk, _ = synthetic.make_numpy(900, 4000, 128, T=64, seed=59)
+    e = pkg.AlignmentEngine(0)
+    try:
+        e.set_option("k2_sms", 8)
+        for pr, slabs in [(128, 8), (256, 4), (512, 2), (1024, 1)]:
+            r = check_against_oracle(oracle, e, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 5, 10), cutoff=30,
+                                     eps_scale=eps_scale, pipeline_rows=pr, inputs=inputs, pinned_outputs=inputs == "pinned")
+            assert r["stats"]["slabs"] == slabs and r["stats"]["k2_sms"] == (8 if slabs > 1 else 0)
+        # the automatic slab size (four waves of the contraction's SMs) at a size that has several of them
+        big_i, big_c, _ = synthetic.make_numpy(80000, 2000, 64, T=64, seed=61)
+        load(e, big_i, big_c, 64)
+        r = e.run(ALL4, candidates="all", k_values=(1, 5, 10), mrr_cutoff=30, weak_weight=(0.3, 0.2))
+        o = oracle.evaluate(big_i, big_c, T=64, schema_mask=15, candidates="all", lam=(0.3, 0.2, 0.5), kmax=10, cutoff=30)
+        assert r["stats"]["slabs"] == 3 and r["stats"]["k2_sms"] == 8   # 2 x 2 waves of 140 row blocks + the rest
+        assert np.array_equal(r["topk_idx"], o["topk_idx"]) and np.array_equal(r["pair_rank"], o["pair_rank"])
+    finally:
+        e.close()
+
+
 def test_slab_pipeline_with_row_range_and_empty_tables(oracle, eng, synthetic):
     img, chk, _ = synthetic.make_numpy(500, 3000, 128, T=64, seed=17)
     load(eng, img, chk, 64)

@@ -26,11 +26,20 @@ eng = pkg.AlignmentEngine(0)
 eng.set_images(img["emb"], img["key"], img["bbox"], None)
 eng.set_chunks(chk["emb"], chk["key"], chk["bbox"], chk["terms"], n_terms=512)
 buf = (C.c_ulonglong * 16)()
+k2 = (C.c_ulonglong * 16)()
 for rep in range(a.reps):
     L.mmalign_profile_counters(buf, 1)
+    L.mmalign_profile_k2(k2, 1)
     r = eng.run(["vanilla_clip", "clip_lexical", "clip_positional", "clip_combined"], candidates="all",
                 k_values=(1, 5, 10, 20), mrr_cutoff=100, weak_weight=(0.3, 0.2), device_outputs=True)
     L.mmalign_profile_counters(buf, 0)
+    L.mmalign_profile_k2(k2, 0)
+    w = [int(x) for x in k2]
+    rows_ = max(w[8], 1)
+    names = ["stage row", "same-page entries", "list sweep", "sort approx", "theta", "candidate gathers + cosine", "sort exact",
+             "merge + outputs"]
+    print(f"rep {rep}: rescore {r['stats']['rescore_us'] / 1e3:.2f} ms; cycles per row (one CTA): " +
+          ", ".join(f"{n} {w[q] / rows_:.0f}" for q, n in enumerate(names)) + f"; total {sum(w[:8]) / rows_:.0f}", flush=True)
     v = [int(x) for x in buf]
     tiles, warps = max(v[4], 1), max(v[7], 1)
     us = r["stats"]["fused_us"]
