@@ -157,6 +157,38 @@ int mmalign_set_option(mmalign_ctx *ctx, const char *name, int64_t value);
  * inputs may be reused or freed) */
 int mmalign_sync(mmalign_ctx *ctx);
 
+/* Encoder output in half precision (the batched CLIP encode of
+ * src/insert_clip_embeddings.py:91-141, :281-353 stays on OpenCLIP; its fp16 / bf16 batch can feed this path
+ * without an fp32 hop through the host).  emb [n][D] of emb_dtype, host or device; the rows are widened (exactly)
+ * into fp32 master rows owned by the context.  Everything else as mmalign_set_images / mmalign_set_chunks. */
+enum { MMALIGN_F32 = 0, MMALIGN_F16 = 1, MMALIGN_BF16 = 2 };
+int mmalign_set_images_half(mmalign_ctx *ctx, const void *emb, int32_t emb_dtype, const uint64_t *page_key,
+                            const double *bbox, const uint64_t *terms, int64_t n, int32_t D, int32_t term_words);
+int mmalign_set_chunks_half(mmalign_ctx *ctx, const void *emb, int32_t emb_dtype, const uint64_t *page_key,
+                            const double *bbox, const uint64_t *terms, int64_t m_local, int32_t D, int32_t term_words,
+                            int64_t n_terms, int64_t col_offset);
+
+/* pgvector interop: the `images` / `text_chunks` tables of src/setup_vector_db.py:102-131
+ * as a PostgreSQL binary COPY stream, e.g.
+ *   COPY (SELECT image_id, manual_id, page, bbox, clip_embedding FROM s.images ORDER BY id) TO STDOUT (FORMAT binary)
+ * mmalign_copy_scan   host-only walk of the tuples (variable-length fields): field_off [rows][n_cols] = byte offset
+ *                     of each field's data, field_len = its length, -1 = NULL.  Returns the number of tuples
+ *                     (with field_off == NULL it only counts), or -1 bad signature / WITH OIDS, -2 truncated stream,
+ *                     -3 a tuple with another field count, -4 more than `cap` tuples.
+ * mmalign_copy_decode GPU decode of the bulk columns into the arrays set_images / set_chunks take: the `vector(D)`
+ *                     column (pgvector vector_send: int16 dim, int16 0, float4[dim], big-endian) -> emb [n][D] fp32;
+ *                     the REAL[] bbox column -> bbox [n][4] doubles (NULL / wrong-length / NULL-element boxes -> zeros,
+ *                     which score 0.0 like src/insert_clip_embeddings.py:161-169); the INTEGER page column -> page [n],
+ *                     page_null [n].  data / outputs host or device; field_off / field_len host or device; any output
+ *                     may be NULL; bbox_col / page_col < 0 = column absent.  MMALIGN_EINVAL if a vector field is NULL
+ *                     or not of dimension D. */
+int64_t mmalign_copy_scan(const uint8_t *data, int64_t n_bytes, int32_t n_cols, int64_t *field_off, int32_t *field_len,
+                          int64_t cap);
+int mmalign_copy_decode(mmalign_ctx *ctx, const uint8_t *data, int64_t n_bytes, const int64_t *field_off,
+                        const int32_t *field_len, int64_t n, int32_t n_cols, int32_t vec_col, int32_t bbox_col,
+                        int32_t page_col, int32_t D, float *emb, double *bbox, int32_t *page, uint8_t *page_null,
+                        void *stream);
+
 /* replaces get_image_text_pairs(): src/evaluate_alignments.py:48-69.  Pairs are
  * ordered by (image index, chunk index).  pair_offsets [N+1], pair_chunk [P]
  * (global chunk index); either may be NULL. */

@@ -41,7 +41,8 @@ EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_
            "mmalign_reduce_metrics", "mmalign_debug_scores", "mmalign_fused_pass", "mmalign_chunk_err_max",
            "mmalign_rescore_pass", "mmalign_rescan_rows", "mmalign_list_stride", "mmalign_export_lists",
            "mmalign_rescore_slab", "mmalign_num_pairs_range", "mmalign_term_bitsets", "mmalign_sync",
-           "mmalign_prep_rows", "mmalign_set_chunks_prepared", "mmalign_rescore_after", "mmalign_debug_operands", "mmalign_set_option"]
+           "mmalign_prep_rows", "mmalign_set_chunks_prepared", "mmalign_rescore_after", "mmalign_debug_operands", "mmalign_set_option",
+           "mmalign_set_images_half", "mmalign_set_chunks_half", "mmalign_copy_scan", "mmalign_copy_decode"]
 ABI_VERSION = 3
 
 _lib = None
@@ -103,9 +104,14 @@ def load():
     L.mmalign_rescore_after.argtypes = [vp, vp]
     L.mmalign_debug_operands.argtypes = [vp, vp, vp, vp]
     L.mmalign_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.mmalign_set_images_half.argtypes = [vp, vp, i32, vp, vp, vp, i64, i32, i32]
+    L.mmalign_set_chunks_half.argtypes = [vp, vp, i32, vp, vp, vp, i64, i32, i32, i64, i64]
+    L.mmalign_copy_scan.argtypes = [vp, i64, i32, vp, vp, i64]
+    L.mmalign_copy_scan.restype = C.c_int64
+    L.mmalign_copy_decode.argtypes = [vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         getattr(L, name)
-        if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version"):
+        if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version", "mmalign_copy_scan"):
             getattr(L, name).restype = C.c_int
     if L.mmalign_abi_version() != ABI_VERSION:
         raise RuntimeError(f"{path} has ABI version {L.mmalign_abi_version()}, this package needs {ABI_VERSION}: rebuild it")

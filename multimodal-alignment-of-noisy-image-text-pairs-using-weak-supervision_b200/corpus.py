@@ -44,15 +44,9 @@ def bbox_array(records: Sequence[dict]) -> np.ndarray:
     return out
 
 
-_ENGINE = None
-
-
 def _engine():
-    global _ENGINE
-    if _ENGINE is None:
-        from .engine import AlignmentEngine
-        _ENGINE = AlignmentEngine(0)
-    return _ENGINE
+    from .engine import default_engine
+    return default_engine(0, "scratch")
 
 
 def term_bitsets(chunks: Sequence[dict], terms: Sequence[str], engine=None) -> np.ndarray:

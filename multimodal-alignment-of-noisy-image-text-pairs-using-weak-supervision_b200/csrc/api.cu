@@ -121,6 +121,7 @@ struct mmalign_ctx {
     DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     DevBuf term_table, text_off, text_bytes;  // mmalign_term_bitsets: term table, uploads of host texts
+    DevBuf copy_off, copy_len, half_up;       // mmalign_copy_decode: field tables; set_*_half: upload of host halves
     CandLists lists;               // written by the last fused pass
     bool lists_valid = false;
     int64_t lists_col0 = 0;        // first chunk row of the column range the lists were built on
@@ -223,7 +224,7 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     c->chk.destroy_events();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
                       &c->list_keys2, &c->list_tau2, &c->list_count2, &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
-                      &c->term_table, &c->text_off, &c->text_bytes};
+                      &c->term_table, &c->text_off, &c->text_bytes, &c->copy_off, &c->copy_len, &c->half_up};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_slab) if (e) cudaEventDestroy(e);
@@ -1519,5 +1520,113 @@ extern "C" int mmalign_debug_operands(mmalign_ctx *c, void *img_bf16, void *chk_
     if (img_bf16 && img.n > 0) CU(c, cudaMemcpyAsync(img_bf16, img.emb_bf16, (size_t)img.n * img.D * 2, cudaMemcpyDefault, st));
     if (chk_bf16 && chk.n > 0) CU(c, cudaMemcpyAsync(chk_bf16, chk.emb_bf16, (size_t)chk.n * chk.D * 2, cudaMemcpyDefault, st));
     CU(c, cudaStreamSynchronize(st));
+    return MMALIGN_OK;
+}
+
+// ---- half-precision encoder rows ---------------------------------------------------
+static int set_side_half(mmalign_ctx *c, bool chunks, const void *emb, int32_t dtype, const uint64_t *key, const double *bbox,
+                         const uint64_t *terms, int64_t n, int32_t D, int32_t term_words, int64_t n_terms, int64_t col_offset)
+{
+    const char *what = chunks ? "mmalign_set_chunks_half" : "mmalign_set_images_half";
+    if (!c) return fail(nullptr, MMALIGN_EINVAL, "%s: ctx is NULL", what);
+    if (dtype == MMALIGN_F32)
+        return chunks ? mmalign_set_chunks(c, (const float *)emb, key, bbox, terms, n, D, term_words, n_terms, col_offset)
+                      : mmalign_set_images(c, (const float *)emb, key, bbox, terms, n, D, term_words);
+    if (dtype != MMALIGN_F16 && dtype != MMALIGN_BF16) return fail(c, MMALIGN_EINVAL, "%s: emb_dtype=%d unknown", what, dtype);
+    if (n < 0 || n > 0x7FFFFFF0ll || D <= 0 || D % 4 != 0 || D > 4096) return fail(c, MMALIGN_EINVAL, "%s: bad n / D", what);
+    if (n > 0 && !emb) return fail(c, MMALIGN_EINVAL, "%s: emb is required", what);
+    CU(c, cudaSetDevice(c->device));
+    SideStore &ss = chunks ? c->chk : c->img;
+    // the widened rows live in the side's upload buffer; earlier work may still read it
+    int rc;
+    if ((rc = mmalign_sync(c))) return rc;
+    CU(c, cudaStreamSynchronize(0));
+    const size_t count = (size_t)n * D;
+    CU(c, ss.up[0].reserve((count ? count : 1) * sizeof(float)));
+    const void *src = emb;
+    if (count && !is_device_ptr(emb)) {
+        CU(c, c->half_up.reserve(count * 2));
+        CU(c, cudaMemcpyAsync(c->half_up.p, emb, count * 2, cudaMemcpyHostToDevice, 0));
+        src = c->half_up.p;
+    }
+    CU(c, launch_widen_rows(src, dtype, (int64_t)count, (float *)ss.up[0].p, 0));
+    const float *master = n > 0 ? (const float *)ss.up[0].p : nullptr;
+    if (n == 0) {
+        static const float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+        master = dummy;  // (never read: n == 0)
+    }
+    return chunks ? mmalign_set_chunks(c, master, key, bbox, terms, n, D, term_words, n_terms, col_offset)
+                  : mmalign_set_images(c, master, key, bbox, terms, n, D, term_words);
+}
+
+extern "C" int mmalign_set_images_half(mmalign_ctx *c, const void *emb, int32_t dtype, const uint64_t *key, const double *bbox,
+                                       const uint64_t *terms, int64_t n, int32_t D, int32_t term_words)
+{
+    return set_side_half(c, false, emb, dtype, key, bbox, terms, n, D, term_words, 0, 0);
+}
+
+extern "C" int mmalign_set_chunks_half(mmalign_ctx *c, const void *emb, int32_t dtype, const uint64_t *key, const double *bbox,
+                                       const uint64_t *terms, int64_t m, int32_t D, int32_t term_words, int64_t n_terms,
+                                       int64_t col_offset)
+{
+    return set_side_half(c, true, emb, dtype, key, bbox, terms, m, D, term_words, n_terms, col_offset);
+}
+
+// ---- pgvector interop: binary COPY streams -----------------------------------------
+extern "C" int64_t mmalign_copy_scan(const uint8_t *data, int64_t n_bytes, int32_t n_cols, int64_t *field_off, int32_t *field_len,
+                                     int64_t cap)
+{
+    if (!data || n_bytes < 0 || n_cols < 1 || n_cols > 1600 || (field_off && !field_len)) return -1;
+    return copy_scan(data, n_bytes, n_cols, field_off, field_len, cap);
+}
+
+extern "C" int mmalign_copy_decode(mmalign_ctx *c, const uint8_t *data, int64_t n_bytes, const int64_t *field_off,
+                                   const int32_t *field_len, int64_t n, int32_t n_cols, int32_t vec_col, int32_t bbox_col,
+                                   int32_t page_col, int32_t D, float *emb, double *bbox, int32_t *page, uint8_t *page_null,
+                                   void *stream)
+{
+    if (!c || !data || !field_off || !field_len) return fail(c, MMALIGN_EINVAL, "mmalign_copy_decode: NULL argument");
+    if (n < 0 || n_cols < 1 || vec_col >= n_cols || bbox_col >= n_cols || page_col >= n_cols || (emb && (vec_col < 0 || D <= 0)))
+        return fail(c, MMALIGN_EINVAL, "mmalign_copy_decode: bad column indices / D");
+    if (n == 0) return MMALIGN_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(c, cudaSetDevice(c->device));
+    const uint8_t *d_data = data;
+    if (!is_device_ptr(data)) {
+        CU(c, c->text_bytes.reserve((size_t)n_bytes + 8));  // (+8: the unaligned 32-bit reads look one word past a field's end)
+        CU(c, cudaMemcpyAsync(c->text_bytes.p, data, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
+        d_data = (const uint8_t *)c->text_bytes.p;
+    }
+    const int64_t *d_off = field_off;
+    const int32_t *d_len = field_len;
+    if (!is_device_ptr(field_off)) {
+        CU(c, c->copy_off.reserve((size_t)n * n_cols * sizeof(int64_t)));
+        CU(c, cudaMemcpyAsync(c->copy_off.p, field_off, (size_t)n * n_cols * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        d_off = (const int64_t *)c->copy_off.p;
+    }
+    if (!is_device_ptr(field_len)) {
+        CU(c, c->copy_len.reserve((size_t)n * n_cols * sizeof(int32_t)));
+        CU(c, cudaMemcpyAsync(c->copy_len.p, field_len, (size_t)n * n_cols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        d_len = (const int32_t *)c->copy_len.p;
+    }
+    Stager sg{c, st};
+    float *d_emb = nullptr;
+    double *d_bbox = nullptr;
+    int32_t *d_page = nullptr;
+    uint8_t *d_null = nullptr;
+    sg.map(emb, (size_t)n * (D > 0 ? D : 0), &d_emb);
+    sg.map(bbox, (size_t)n * 4, &d_bbox);
+    sg.map(page, (size_t)n, &d_page);
+    sg.map(page_null, (size_t)n, &d_null);
+    int rc;
+    if ((rc = sg.commit())) return rc;
+    int32_t *err = (int32_t *)((char *)c->small.p + 192);
+    CU(c, cudaMemsetAsync(err, 0, sizeof(int32_t), st));
+    CU(c, launch_copy_decode(d_data, d_off, d_len, n, n_cols, vec_col, bbox_col, page_col, D, d_emb, d_bbox, d_page, d_null, err, st));
+    int32_t h_err = 0;
+    CU(c, cudaMemcpyAsync(&h_err, err, sizeof h_err, cudaMemcpyDeviceToHost, st));
+    if ((rc = sg.copy_back())) return rc;
+    CU(c, cudaStreamSynchronize(st));
+    if (h_err) return fail(c, MMALIGN_EINVAL, "mmalign_copy_decode: a vector field is NULL or not of dimension %d", D);
     return MMALIGN_OK;
 }

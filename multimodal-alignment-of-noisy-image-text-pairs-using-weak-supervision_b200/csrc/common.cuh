@@ -304,6 +304,11 @@ cudaError_t launch_term_bitsets(const uint8_t *text, const int64_t *text_off, in
                                 const int32_t *term_off, const int32_t *bucket_start, const int32_t *bucket_term,
                                 const uint32_t *hash, int hash_bits, const int32_t *group_term,
                                 const uint32_t *always, int term_words, uint64_t *bits, cudaStream_t st);
+int64_t copy_scan(const uint8_t *data, int64_t n_bytes, int n_cols, int64_t *field_off, int32_t *field_len, int64_t cap);
+cudaError_t launch_copy_decode(const uint8_t *data, const int64_t *field_off, const int32_t *field_len, int64_t n, int n_cols,
+                               int vec_col, int bbox_col, int page_col, int D, float *emb, double *bbox, int32_t *page,
+                               uint8_t *page_null, int32_t *err, cudaStream_t st);
+cudaError_t launch_widen_rows(const void *src, int dtype, int64_t count, float *dst, cudaStream_t st);
 // fused_tc.cu
 struct FusedPlan {
     int64_t n_row_blocks;

@@ -15,6 +15,8 @@
 // position, no comparison needed on a hit); one-byte terms go through a first-byte bucket list.  Each text byte is
 // read from HBM once.  Algorithmic bytes per chunk: its text length + 8 * term_words.
 #include "common.cuh"
+#include <cuda_fp16.h>
+#include <string.h>
 #include <algorithm>
 #include <vector>
 
@@ -188,6 +190,128 @@ cudaError_t launch_term_bitsets(const uint8_t *text, const int64_t *text_off, in
     int64_t grid = (m + kIngestWarps - 1) / kIngestWarps;
     if (grid > (int64_t)sm_count() * 8) grid = (int64_t)sm_count() * 8;
     term_bitsets_kernel<<<(unsigned)grid, kIngestThreads, smem, st>>>(text, text_off, m, tt, term_words, always, bits);
+    return cudaGetLastError();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// pgvector interop: the `images` / `text_chunks` tables of
+// src/setup_vector_db.py:102-131 arrive as a PostgreSQL binary COPY stream
+//     COPY (SELECT image_id, manual_id, page, bbox, clip_embedding FROM <schema>.images ORDER BY id) TO STDOUT (FORMAT binary)
+// Tuples are variable-length (VARCHAR ids, text), so their boundaries are found by one sequential walk on the host
+// (copy_scan: a few loads per field); the bulk -- n x D big-endian float4 of the `vector` column (pgvector
+// vector_send: int16 dim, int16 unused, float4[dim]), the REAL[] boxes and the INTEGER pages -- is decoded on the
+// GPU straight into the layout mmalign_set_images / set_chunks take.
+// ---------------------------------------------------------------------------------------------
+static inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+static inline uint16_t be16(const uint8_t *p) { return (uint16_t)(((uint16_t)p[0] << 8) | p[1]); }
+
+// Walks the stream: field_off [rows][n_cols] = byte offset of each field's DATA, field_len = its length (-1 = NULL).
+// Returns the number of tuples, or a negative code: -1 bad signature / flags, -2 truncated, -3 field count differs,
+// -4 more tuples than `cap`.
+int64_t copy_scan(const uint8_t *data, int64_t n_bytes, int n_cols, int64_t *field_off, int32_t *field_len, int64_t cap)
+{
+    static const uint8_t sig[11] = {'P', 'G', 'C', 'O', 'P', 'Y', '\n', 0xFF, '\r', '\n', 0};
+    if (n_bytes < 19 || memcmp(data, sig, 11) != 0) return -1;
+    if (be32(data + 11) & (1u << 16)) return -1;  // WITH OIDS
+    int64_t o = 19 + (int64_t)be32(data + 15);
+    int64_t rows = 0;
+    for (;;) {
+        if (o + 2 > n_bytes) return -2;
+        const int16_t nf = (int16_t)be16(data + o);
+        o += 2;
+        if (nf == -1) return rows;
+        if (nf != n_cols) return -3;
+        if (rows >= cap && field_off) return -4;
+        for (int f = 0; f < n_cols; ++f) {
+            if (o + 4 > n_bytes) return -2;
+            const int32_t ln = (int32_t)be32(data + o);
+            o += 4;
+            if (field_off) { field_off[rows * n_cols + f] = o; field_len[rows * n_cols + f] = ln; }
+            if (ln > 0) o += ln;
+            if (o > n_bytes) return -2;
+        }
+        ++rows;
+    }
+}
+
+__device__ __forceinline__ uint32_t load_be32_unaligned(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t lo = w[0], hi = sh ? w[1] : 0u;          // little-endian words holding the four bytes
+    return __byte_perm(__funnelshift_r(lo, hi, sh), 0u, 0x0123);  // bytes reversed: big-endian value
+}
+
+// One warp per tuple.  err: 1 = vector field malformed (NULL, wrong dim), set once; rows with a malformed box get zeros
+// (corpus.bbox_array: missing / wrong-length boxes score 0.0, src/insert_clip_embeddings.py:161-169).
+__global__ void __launch_bounds__(256)
+copy_decode_kernel(const uint8_t *__restrict__ data, const int64_t *__restrict__ field_off, const int32_t *__restrict__ field_len,
+                   int64_t n, int n_cols, int vec_col, int bbox_col, int page_col, int D, float *__restrict__ emb,
+                   double *__restrict__ bbox, int32_t *__restrict__ page, uint8_t *__restrict__ page_null, int32_t *err)
+{
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; r < n; r += ((int64_t)gridDim.x * blockDim.x) >> 5) {
+        const int64_t *off = field_off + r * n_cols;
+        const int32_t *len = field_len + r * n_cols;
+        if (emb) {
+            const uint8_t *v = data + off[vec_col];
+            bool ok = len[vec_col] == 4 + 4 * D;
+            if (ok) ok = (load_be32_unaligned(v) == ((uint32_t)D << 16));  // int16 dim, int16 unused (0)
+            if (!ok) { if (lane == 0) atomicExch(err, 1); }
+            else
+                for (int k = lane; k < D; k += 32) emb[r * D + k] = __uint_as_float(load_be32_unaligned(v + 4 + 4 * k));
+        }
+        if (bbox && lane < 4) {
+            double x = 0.0;
+            bool ok = false;
+            if (bbox_col >= 0 && len[bbox_col] == 20 + 4 * 8) {  // ndim, has-null, oid, (size, lower bound), 4 x (len, float4)
+                const uint8_t *b = data + off[bbox_col];
+                ok = load_be32_unaligned(b) == 1u && load_be32_unaligned(b + 8) == 700u && load_be32_unaligned(b + 12) == 4u;
+                if (ok) {
+                    for (int q = 0; q < 4; ++q) ok = ok && load_be32_unaligned(b + 20 + 8 * q) == 4u;  // no NULL element
+                    if (ok) x = (double)__uint_as_float(load_be32_unaligned(b + 24 + 8 * lane));
+                }
+            }
+            bbox[r * 4 + lane] = ok ? x : 0.0;
+        }
+        if (page && lane == 0) {
+            const bool null = page_col < 0 || len[page_col] != 4;
+            page[r] = null ? 0 : (int32_t)load_be32_unaligned(data + off[page_col]);
+            if (page_null) page_null[r] = null ? 1 : 0;
+        }
+    }
+}
+
+cudaError_t launch_copy_decode(const uint8_t *data, const int64_t *field_off, const int32_t *field_len, int64_t n, int n_cols,
+                               int vec_col, int bbox_col, int page_col, int D, float *emb, double *bbox, int32_t *page,
+                               uint8_t *page_null, int32_t *err, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    int64_t grid = (n * 32 + 255) / 256;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    copy_decode_kernel<<<(unsigned)grid, 256, 0, st>>>(data, field_off, field_len, n, n_cols, vec_col, bbox_col, page_col, D,
+                                                       emb, bbox, page, page_null, err);
+    return cudaGetLastError();
+}
+
+// Encoder output in half precision (fp16 / bf16 rows, e.g. an OpenCLIP batch on the device): widened to the fp32
+// master rows the exact rescoring reads -- every 16-bit value is exactly representable, so nothing is lost.
+template <typename T>
+__global__ void widen_rows_kernel(const T *__restrict__ src, int64_t count, float *__restrict__ dst)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+
+cudaError_t launch_widen_rows(const void *src, int dtype, int64_t count, float *dst, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    int64_t grid = (count + 255) / 256;
+    if (grid > (int64_t)sm_count() * 16) grid = (int64_t)sm_count() * 16;
+    if (dtype == MMALIGN_F16) widen_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const __half *>(src), count, dst);
+    else widen_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(src), count, dst);
     return cudaGetLastError();
 }
 

@@ -95,8 +95,19 @@ class AlignmentEngine:
             raise MMAlignError(rc, self._L.mmalign_last_error(self._ctx).decode())
 
     # -- corpus -----------------------------------------------------------------
+    @staticmethod
+    def _half_dtype(emb):
+        """1 / 2 (MMALIGN_F16 / MMALIGN_BF16) for half-precision rows (an encoder batch), else 0."""
+        name = str(getattr(emb, "dtype", ""))
+        return 1 if name.endswith("float16") and "bfloat16" not in name else (2 if "bfloat16" in name else 0)
+
     def _set(self, which, emb, key, bbox, terms, n_terms=0, col_offset=0):
-        e, pe = _prep(emb, np.float32, "float32")
+        half = self._half_dtype(emb)
+        if half:  # fp16 / bf16 rows go down as they are (mmalign_set_*_half widens them on the device)
+            e = emb.contiguous() if _is_torch(emb) else np.ascontiguousarray(emb)
+            pe = e.data_ptr() if _is_torch(e) else e.ctypes.data
+        else:
+            e, pe = _prep(emb, np.float32, "float32")
         k, pk = _prep(key, np.uint64, "int64")
         b, pb = _prep(bbox, np.float64, "float64")
         t, pt = _prep(terms, np.uint64, "int64")
@@ -105,10 +116,12 @@ class AlignmentEngine:
             raise ValueError("page_key length differs from the number of embedding rows")
         W = 0 if t is None else int(t.shape[1])
         if which == "images":
-            rc = self._L.mmalign_set_images(self._ctx, pe, pk, pb, pt, n, D, W)
+            rc = self._L.mmalign_set_images_half(self._ctx, pe, half, pk, pb, pt, n, D, W) if half else \
+                self._L.mmalign_set_images(self._ctx, pe, pk, pb, pt, n, D, W)
             self.N, self.D = n, D
         else:
-            rc = self._L.mmalign_set_chunks(self._ctx, pe, pk, pb, pt, n, D, W, int(n_terms), int(col_offset))
+            rc = self._L.mmalign_set_chunks_half(self._ctx, pe, half, pk, pb, pt, n, D, W, int(n_terms), int(col_offset)) \
+                if half else self._L.mmalign_set_chunks(self._ctx, pe, pk, pb, pt, n, D, W, int(n_terms), int(col_offset))
             self.M, self.col_offset = n, int(col_offset)
         self._keep[which] = (e, k, b, t)  # device inputs are borrowed by the library
         self._check(rc)
@@ -335,6 +348,32 @@ class AlignmentEngine:
         self._check(self._L.mmalign_debug_scores(self._ctx, out.ctypes.data, None))
         return out
 
+    def copy_decode(self, data: bytes, n_cols: int, vec_col: int, bbox_col: int = -1, page_col: int = -1, D: int = 0):
+        """A PostgreSQL binary COPY stream -> (field_off [n, n_cols], field_len [n, n_cols], emb [n, D] f32, bbox [n, 4] f64,
+        page [n] i32, page_null [n] bool): tuple walk on the host (mmalign_copy_scan), bulk columns decoded on the GPU
+        (mmalign_copy_decode).  D = 0: taken from the first row's vector field."""
+        buf = np.frombuffer(data, np.uint8)
+        n = int(self._L.mmalign_copy_scan(buf.ctypes.data, len(buf), n_cols, None, None, 0))
+        if n < 0:
+            raise ValueError(f"not a usable binary COPY stream (mmalign_copy_scan code {n})")
+        off = np.zeros((max(n, 1), n_cols), np.int64)
+        ln = np.zeros((max(n, 1), n_cols), np.int32)
+        got = int(self._L.mmalign_copy_scan(buf.ctypes.data, len(buf), n_cols, off.ctypes.data, ln.ctypes.data, n))
+        assert got == n
+        off, ln = off[:n], ln[:n]
+        if n and D == 0 and vec_col >= 0:
+            D = (int(ln[0, vec_col]) - 4) // 4
+        emb = np.zeros((n, max(D, 0)), np.float32)
+        bbox = np.zeros((n, 4), np.float64)
+        page = np.zeros(n, np.int32)
+        null = np.zeros(n, np.uint8)
+        if n:
+            self._check(self._L.mmalign_copy_decode(self._ctx, buf.ctypes.data, len(buf), off.ctypes.data, ln.ctypes.data, n,
+                                                    n_cols, vec_col, bbox_col, page_col, D,
+                                                    emb.ctypes.data if vec_col >= 0 else None, bbox.ctypes.data,
+                                                    page.ctypes.data, null.ctypes.data, None))
+        return off, ln, emb, bbox, page, null.astype(bool)
+
     def debug_operands(self):
         """The bf16 operands of the fused kernel as float32 arrays (validation hook)."""
         a = np.zeros((self.N, self.D), np.uint16)
@@ -407,6 +446,19 @@ class AlignmentEngine:
                                                    ks.ctypes.data, len(ks), int(mrr_cutoff), hits.ctypes.data,
                                                    rr.ctypes.data, sim.ctypes.data, None))
         return hits, rr, float(sim[0])
+
+
+_DEFAULT = {}
+
+
+def default_engine(device: int = 0, role: str = "main") -> AlignmentEngine:
+    """The process-wide engine of a device, shared by the modules that mirror the reference (one context per role:
+    "main" holds the registered schema's tables, "scratch" serves one-off calls that must not disturb them)."""
+    key = (int(device), role)
+    eng = _DEFAULT.get(key)
+    if eng is None or not eng._ctx.value:
+        eng = _DEFAULT[key] = AlignmentEngine(device)
+    return eng
 
 
 class _ShardedSession:

@@ -7,6 +7,9 @@ an in-process registry filled by `register_schema()` (arrays + record lists, the
 content of the `images` / `text_chunks` tables).  A schema that was never registered
 behaves like a schema missing from the database.
 
+Limits the reference does not have (the library answers MMALIGN_ELIMIT / MMALIGN_EINVAL = MMAlignError): k and
+the MRR cut-off at most 256, at most 512 chunks on one (manual, page).
+
 Two knobs the reference does not have (both default to the reference's behaviour):
   CANDIDATES   "same_page": rank an image against the chunks of its own manual+page
                only (the SQL join, :128-131); "all": rank against every chunk.
@@ -23,7 +26,7 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 from .corpus import Corpus
-from .engine import AlignmentEngine, SCHEMAS as _ALL_SCHEMAS
+from .engine import AlignmentEngine, SCHEMAS as _ALL_SCHEMAS, default_engine
 from .insert_clip_embeddings import compute_alignment_records
 
 # Schemas to evaluate (src/evaluate_alignments.py:29)
@@ -39,14 +42,10 @@ DEVICE = 0
 _FLAGS = {"vanilla_clip": (False, False), "clip_lexical": (True, False),
           "clip_positional": (False, True), "clip_combined": (True, True)}
 _REGISTRY: Dict[str, "_Schema"] = {}
-_ENGINE = None
 
 
 def _engine() -> AlignmentEngine:
-    global _ENGINE
-    if _ENGINE is None:
-        _ENGINE = AlignmentEngine(DEVICE)
-    return _ENGINE
+    return default_engine(DEVICE)
 
 
 class _Schema:
@@ -113,13 +112,10 @@ def compute_similarity(image_id: str, chunk_id: str, schema: str) -> float:
     p = off[i] + np.searchsorted(pc[off[i]:off[i + 1]], j)
     if p < off[i + 1] and pc[p] == j:
         return float(r["pair_sim"][p])
-    eng = AlignmentEngine(DEVICE)  # not a true pair: score it alone
-    try:
-        eng.set_images(c.img["emb"][i:i + 1], np.zeros(1, np.uint64))
-        eng.set_chunks(c.chk["emb"][j:j + 1], np.zeros(1, np.uint64))
-        return float(eng.run("vanilla_clip", k_values=[1], want=("pairs",))["pair_sim"][0])
-    finally:
-        eng.close()
+    eng = default_engine(DEVICE, "scratch")  # not a true pair: score it alone, beside the schema's tables
+    eng.set_images(c.img["emb"][i:i + 1], np.zeros(1, np.uint64))
+    eng.set_chunks(c.chk["emb"][j:j + 1], np.zeros(1, np.uint64))
+    return float(eng.run("vanilla_clip", k_values=[1], want=("pairs",))["pair_sim"][0])
 
 
 def get_top_k_similar_chunks(image_id: str, schema: str, k: int = 10) -> List[Tuple[str, float]]:
@@ -140,9 +136,9 @@ def get_weak_supervision_scores(schema: str) -> Dict[str, List[float]]:
     s = _get(schema)
     ul, up = _FLAGS.get(schema, (False, False))
     by_type = defaultdict(list)
-    for _, _, score, ty in sorted(compute_alignment_records(s.corpus, ul, up, _engine()), key=lambda r: r[3]):
+    for _, _, score, ty in sorted(compute_alignment_records(s.corpus, ul, up, default_engine(DEVICE, "scratch")),
+                                  key=lambda r: r[3]):
         by_type[ty].append(float(np.float32(score)))
-    s.cache.clear()  # the engine now holds this corpus with other buffers
     return dict(by_type)
 
 

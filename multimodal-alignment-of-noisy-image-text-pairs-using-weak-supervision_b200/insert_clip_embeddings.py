@@ -11,16 +11,11 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 from .corpus import bbox_array, term_bitsets
-from .engine import AlignmentEngine
-
-_ENGINE = None
+from .engine import AlignmentEngine, default_engine
 
 
 def _engine() -> AlignmentEngine:
-    global _ENGINE
-    if _ENGINE is None:
-        _ENGINE = AlignmentEngine(0)
-    return _ENGINE
+    return default_engine(0, "scratch")
 
 
 def _records(eng, images, chunks, img_key, chk_key, terms, schema, raw=False):

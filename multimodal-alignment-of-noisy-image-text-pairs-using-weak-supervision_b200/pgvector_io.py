@@ -17,7 +17,9 @@ and pgvector's `vector_send` (int16 dim, int16 unused, dim big-endian float4).  
 the build environment: the tests round-trip streams built to those specifications ("parity unpinned" against a
 live server, like the cosine itself -- DESIGN.md section 2).
 
-Host-side plumbing only: byte order conversion and array assembly in numpy; all scoring stays on the GPU.
+Two decoders: read_copy_binary (pure Python / numpy, field by field -- the specification written down, and the
+checker of the other one) and records_from_copy(..., engine=...), which walks the tuples in C (mmalign_copy_scan)
+and decodes the bulk columns -- vectors, boxes, pages -- on the GPU (mmalign_copy_decode, csrc/ingest.cu).
 """
 from __future__ import annotations
 
@@ -165,9 +167,39 @@ CHUNK_COLUMNS = [("chunk_id", TEXT), ("manual_id", TEXT), ("page", INT4), ("text
                  ("clip_embedding", VECTOR)]
 
 
-def records_from_copy(data: bytes, columns: Sequence[Tuple[str, str]]):
+def _records_from_copy_gpu(data: bytes, columns: Sequence[Tuple[str, str]], engine):
+    names = [n for n, _ in columns]
+    kinds = dict(columns)
+    col = lambda name: names.index(name) if name in names else -1
+    off, ln, emb, bbox, page, page_null = engine.copy_decode(data, len(columns), col("clip_embedding"), col("bbox"), col("page"))
+    mv = memoryview(data)
+    recs = []
+    for i in range(off.shape[0]):
+        r = {}
+        for f, name in enumerate(names):
+            if name == "clip_embedding":
+                continue
+            if name == "page":
+                r[name] = None if page_null[i] else int(page[i])
+            elif name == "bbox":  # NULL stays None; anything else that is not four numbers decoded to zeros (scores 0.0)
+                r[name] = None if ln[i, f] < 0 else [float(x) for x in bbox[i]]
+            elif ln[i, f] < 0:
+                r[name] = None
+            elif kinds[name] == TEXT:
+                r[name] = bytes(mv[off[i, f]:off[i, f] + ln[i, f]]).decode("utf-8")
+            else:
+                r[name] = _decode_field(kinds[name], mv[off[i, f]:off[i, f] + ln[i, f]])
+        recs.append(r)
+    return recs, emb
+
+
+def records_from_copy(data: bytes, columns: Sequence[Tuple[str, str]], engine=None):
     """COPY stream of the `images` / `text_chunks` table -> (records like the reference's JSON files, embeddings [n, D]).
-    The records feed corpus.build_corpus unchanged."""
+    The records feed corpus.build_corpus unchanged.  With an engine the tuple walk runs in C and the bulk columns are
+    decoded on the GPU; a bbox that is not four non-NULL numbers then reads as [0, 0, 0, 0], which scores 0.0 exactly like
+    the missing box it stands for (src/insert_clip_embeddings.py:161-169)."""
+    if engine is not None and hasattr(engine, "copy_decode"):
+        return _records_from_copy_gpu(data, columns, engine)
     cols = read_copy_binary(data, columns)
     names = [n for n, _ in columns if n != "clip_embedding"]
     n = len(cols[columns[0][0]])
@@ -187,8 +219,8 @@ def corpus_from_copy(images_copy: bytes, chunks_copy: bytes, lexical_components=
     evaluate_alignments.register_schema.  bbox values are float4 on this route (the table type is REAL[]); the
     reference computes its alignment records from the JSON doubles before they are stored."""
     from .corpus import build_corpus
-    images, ie = records_from_copy(images_copy, IMAGE_COLUMNS)
-    chunks, ce = records_from_copy(chunks_copy, CHUNK_COLUMNS)
+    images, ie = records_from_copy(images_copy, IMAGE_COLUMNS, engine)
+    chunks, ce = records_from_copy(chunks_copy, CHUNK_COLUMNS, engine)
     return build_corpus(images, chunks, ie, ce, lexical_components, engine=engine)
 
 

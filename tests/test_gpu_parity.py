@@ -444,6 +444,29 @@ def test_image_term_sets(oracle, eng, synthetic, cand, path):
         assert si == 0 or np.count_nonzero(rec) > 0
 
 
+# ----------------------------------------------------------------------------- half-precision encoder rows
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("where", ["device", "host"])
+def test_half_precision_rows(oracle, eng, synthetic, dtype, where):
+    """fp16 / bf16 rows (an encoder batch) through mmalign_set_*_half: exactly the result of the same values as fp32."""
+    import torch
+    img, chk, _ = synthetic.make_numpy(300, 3000, 128, T=64, seed=67)
+    td = getattr(torch, dtype)
+    hi, hc = torch.from_numpy(img["emb"]).to(td), torch.from_numpy(chk["emb"]).to(td)
+    img32, chk32 = dict(img, emb=hi.float().numpy()), dict(chk, emb=hc.float().numpy())   # the values the halves hold
+    if where == "device":
+        hi, hc = hi.cuda(), hc.cuda()
+    elif dtype == "float16":
+        hi, hc = hi.numpy(), hc.numpy()      # numpy float16 arrays on the host
+    eng.set_images(hi, img["key"], img["bbox"], None)
+    eng.set_chunks(hc, chk["key"], chk["bbox"], chk["terms"], n_terms=64)
+    for cand in ("all", "same_page"):
+        r = eng.run(ALL4, candidates=cand, k_values=(1, 5, 10), mrr_cutoff=30, weak_weight=(0.3, 0.2))
+        o = oracle.evaluate(img32, chk32, T=64, schema_mask=15, candidates=cand, lam=(0.3, 0.2, 0.5), kmax=10, cutoff=30)
+        assert np.array_equal(r["topk_idx"], o["topk_idx"]) and np.array_equal(r["topk_score"], o["topk_score"])
+        assert np.array_equal(r["pair_rank"], o["pair_rank"]) and np.array_equal(r["pair_sim"], o["pair_sim"])
+
+
 # ----------------------------------------------------------------------------- deep lists, error model
 def test_deep_lists_are_exact_to_the_full_depth(oracle, eng, synthetic):
     """deep_idx / deep_score on the fused path (include/mmalign.h): final to max(Kmax, mrr_cutoff) entries."""
