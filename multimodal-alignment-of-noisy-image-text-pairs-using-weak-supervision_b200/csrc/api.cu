@@ -100,7 +100,7 @@ struct SideStore {
 
 constexpr int kMaxSlabs = 512;          // slabs of one mmalign_run (their failure counters live in `small`)
 constexpr int kSlabWaves = 4;           // auto slab = this many waves of 128-row blocks over the SMs
-constexpr size_t kSmallBytes = 8192;    // 0: fail_count | 8: cand_counter | 16: error_flag | 24: eps violations | 64: k_list | 128: eps | 1024: slab counters
+constexpr size_t kSmallBytes = 8192;    // 0: fail_count | 8: cand_counter | 16: error_flag | 24: eps violations | 64: k_list | 128: eps | 1024: slab counters | 4096: slab counters of the rows left to the block-per-row rescoring
 
 struct mmalign_ctx {
     int device = 0;
@@ -119,6 +119,7 @@ struct mmalign_ctx {
     DevBuf list_keys, list_tau, list_count;
     DevBuf list_keys2, list_tau2, list_count2;  // second set: slab s+1 is contracted while slab s is re-scored
     DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;
+    DevBuf big_rows;               // rows the warp-per-row rescoring hands to the block-per-row kernel
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     DevBuf term_table, text_off, text_bytes;  // mmalign_term_bitsets: term table, uploads of host texts
     DevBuf copy_off, copy_len, half_up;       // mmalign_copy_decode: field tables; set_*_half: upload of host halves
@@ -223,7 +224,7 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     c->img.destroy_events();
     c->chk.destroy_events();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
-                      &c->list_keys2, &c->list_tau2, &c->list_count2, &c->fail_rows, &c->fail_thr, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
+                      &c->list_keys2, &c->list_tau2, &c->list_count2, &c->fail_rows, &c->fail_thr, &c->big_rows, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
                       &c->term_table, &c->text_off, &c->text_bytes, &c->copy_off, &c->copy_len, &c->half_up};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
@@ -914,6 +915,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     if (fused_path) {
         CU(c, c->fail_rows.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(int32_t)));
         CU(c, c->fail_thr.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(unsigned long long)));
+        CU(c, c->big_rows.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(int32_t)));
         CU(c, c->scan_buf.reserve(scan_scratch_bytes()));
         CU(c, c->scan_cnt.reserve(sizeof(int32_t) * kScanSlots));
         if (!imported) {
@@ -952,6 +954,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     tr.mark("params + staging");
     // ---- small device state
     int32_t *slab_fail = (int32_t *)((char *)c->small.p + 1024);  // [n_slabs] rows of the slab that missed the certificate
+    int32_t *slab_big = (int32_t *)((char *)c->small.p + 4096);   // [n_slabs] rows of the slab left to the block-per-row rescoring
     unsigned long long *cand_counter = (unsigned long long *)((char *)c->small.p + 8);
     int32_t *error_flag = (int32_t *)((char *)c->small.p + 16);
     int32_t *k_list_dev = (int32_t *)((char *)c->small.p + 64);
@@ -968,6 +971,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
     c->chk_consumed = true;
     CU(c, cudaMemsetAsync(c->small.p, 0, 64, st));
     CU(c, cudaMemsetAsync(slab_fail, 0, sizeof(int32_t) * kMaxSlabs, st));
+    CU(c, cudaMemsetAsync(slab_big, 0, sizeof(int32_t) * kMaxSlabs, st));
     CU(c, cudaMemcpyAsync(k_list_dev, rp.k_list, sizeof(int32_t) * kMaxK, cudaMemcpyHostToDevice, st));
     if (out.pair_rank && SP) CU(c, cudaMemsetAsync(out.pair_rank, 0, SP * sizeof(int32_t), st));
     long long launches = 0, fused_launches = 0, kprime_used = 0;
@@ -1049,7 +1053,8 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             // beside the next slab's contraction the rescoring gets the SMs that were left free: 8 CTAs on each
             const int64_t k2_grid = overlap && s + 1 < n_slabs ? (int64_t)(c->sm_count - k1_sms) * 8 : 0;
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, fail_rows, slab_fail + s, pre.thr,
-                                 cand_counter, error_flag, nullptr, nullptr, range, sk2, k2_grid));
+                                 cand_counter, error_flag, nullptr, nullptr, range, sk2, k2_grid,
+                                 (int32_t *)c->big_rows.p + r0, slab_big + s));
             CU(c, cudaEventRecord(ev[2], sk2));
             CU(c, launch_exact_scan(img, chk, c->px, rp, fail_rows, slab_fail + s, 0, out, error_flag, range, &pre, sk2));
             launches += 3;

@@ -171,6 +171,44 @@ __device__ __forceinline__ void warp_dot2(const float4 *__restrict__ a, const fl
     r0 = s; r1 = t;
 }
 
+// Four independent canonical dot products, the loads of all four in flight together (warp-per-row rescoring:
+// 16 x 512 B per warp).  Each result is bit-identical to warp_dot().
+__device__ __forceinline__ void warp_dot4(const float4 *__restrict__ a, const float4 *__restrict__ b0,
+                                          const float4 *__restrict__ b1, const float4 *__restrict__ b2,
+                                          const float4 *__restrict__ b3, int d4, int lane, float (&r)[4])
+{
+    float acc[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[q][k] = 0.f;
+    for (int c = lane; c < d4; c += 128) {
+        float4 y[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + 32 * u < d4) {
+                y[0][u] = __ldg(b0 + c + 32 * u); y[1][u] = __ldg(b1 + c + 32 * u);
+                y[2][u] = __ldg(b2 + c + 32 * u); y[3][u] = __ldg(b3 + c + 32 * u);
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (c + 32 * u < d4) {
+                const float4 x = a[c + 32 * u];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    acc[q][0] = fmaf(x.x, y[q][u].x, acc[q][0]); acc[q][1] = fmaf(x.y, y[q][u].y, acc[q][1]);
+                    acc[q][2] = fmaf(x.z, y[q][u].z, acc[q][2]); acc[q][3] = fmaf(x.w, y[q][u].w, acc[q][3]);
+                }
+            }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = r[q] + __shfl_xor_sync(0xFFFFFFFFu, r[q], off);
+}
+
 // pgvector cosine as SQL sees it, 1 - (a <=> b): evaluate_alignments.py:97, :128
 __device__ __forceinline__ double sim_from_sums(float dot, float na, float nb)
 {
@@ -263,7 +301,8 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
-                           int32_t *cert_count, RowRange rows, cudaStream_t st, int64_t grid_limit = 0);
+                           int32_t *cert_count, RowRange rows, cudaStream_t st, int64_t grid_limit = 0,
+                           int32_t *big_rows = nullptr, int32_t *big_count = nullptr);  // scratch of the warp-per-row kernel: [rows], [1] zeroed
 // scratch of the two-stage exact scan: per failed row (slot) its threshold, and what stage 1 kept for it
 constexpr int kScanSlots = 2048, kScanCap = 1024;
 struct ScanScratch {

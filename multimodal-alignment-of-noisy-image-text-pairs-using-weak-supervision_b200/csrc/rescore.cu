@@ -302,17 +302,21 @@ __device__ void score_same_page(const RowArgs &A, const RowSmem &sm, int64_t i, 
     __syncthreads();
 }
 
-// ranking score of same-page entry p in schema s (cosine + weighted alignment records)
-__device__ __forceinline__ double same_page_score(const RunParams &rp, const RowSmem &sm, int s, int p)
+// ranking score of a same-page entry in schema s: cosine + weighted alignment records
+__device__ __forceinline__ double ranking_score(const RunParams &rp, int s, double cosine, double lex, double pos)
 {
     double w = 0.0;
     if (s != 0) {
         double rec[3];
-        weak_records(schema_uses_lex(s), schema_uses_pos(s), schema_uses_lex(s) ? sm.sp_lex[p] : 0.0,
-                     schema_uses_pos(s) ? sm.sp_pos[p] : 0.0, rec);
+        weak_records(schema_uses_lex(s), schema_uses_pos(s), schema_uses_lex(s) ? lex : 0.0,
+                     schema_uses_pos(s) ? pos : 0.0, rec);
         w = rp.lam_lex * rec[0] + rp.lam_pos * rec[1] + rp.lam_comb * rec[2];
     }
-    return sm.cosv[p] + w;
+    return cosine + w;
+}
+__device__ __forceinline__ double same_page_score(const RunParams &rp, const RowSmem &sm, int s, int p)
+{
+    return ranking_score(rp, s, sm.cosv[p], sm.sp_lex[p], sm.sp_pos[p]);
 }
 
 // Number of values > x in approx[0, n), sorted descending.
@@ -471,7 +475,7 @@ __device__ __forceinline__ void stage_row(const RowArgs &A, const RowSmem &sm, i
 // global chunk indices, cnt < 0 = the source could not fit the row into the exchange stride.
 constexpr int kMaxListsPerRow = 128;
 struct ListView { const uint64_t *keys; int cnt; float tau; };
-__device__ __forceinline__ int lists_per_row(const CandLists &L) { return L.imp_keys ? L.imp_src : L.n_splits * 2; }
+__host__ __device__ __forceinline__ int lists_per_row(const CandLists &L) { return L.imp_keys ? L.imp_src : L.n_splits * 2; }
 __device__ __forceinline__ ListView list_view(const CandLists &L, int64_t i, int64_t row0, int l)
 {
     ListView v;
@@ -500,7 +504,7 @@ __device__ __forceinline__ ListView list_view(const CandLists &L, int64_t i, int
 __global__ void __launch_bounds__(kThreads, 8)
 rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_max,
                int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr, unsigned long long *cand_counter,
-               const float *tau_global, int32_t *cert_count)
+               const float *tau_global, int32_t *cert_count, const int32_t *row_list, const int32_t *row_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RowSmem sm = carve(smem_raw, A.ent_cap, A.sp_cap);
@@ -512,8 +516,10 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const RunParams &rp = A.rp;
     unsigned long long *packed = reinterpret_cast<unsigned long long *>(sm.buf);  // the union, before it is re-scored
-    for (int64_t b = blockIdx.x; b < A.n_rows; b += gridDim.x) {
-        const int64_t i = A.row0 + b;
+    // row_list: the rows the warp-per-row kernel handed over (wider than its registers), instead of a range
+    const int64_t n_todo = row_list ? (int64_t)*row_count : A.n_rows;
+    for (int64_t b = blockIdx.x; b < n_todo; b += gridDim.x) {
+        const int64_t i = row_list ? (int64_t)row_list[b] : A.row0 + b;
         K2_T(r0_);
         const int c = (int)(A.offsets[i + 1] - A.offsets[i]);
         if (threadIdx.x == 0) { s_nca = 0; s_tau = -CUDART_INF_F; s_theta = ~0ull; }
@@ -627,6 +633,409 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
         }
         __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------
+// K2, one WARP per image row
+// ---------------------------------------------------------------------------
+// The same computation as rescore_kernel's lists mode -- same formulas, same order of floating-point operations,
+// same outputs bit for bit -- organised for the common shape of a row (at most 32 lists, at most 32 same-page
+// chunks, a union of at most 256 candidates): no block barriers, sorts in registers (8 keys per lane, blocked
+// layout: strides 1-4 never leave the lane), 4 row gathers = 16 x 512 B in flight per warp, 16 warps per SM.
+// Rows outside that shape are handed to rescore_kernel through big_rows (row-list mode).
+// Measured at config 5 against the block-per-row kernel: DESIGN.md section 4.
+constexpr int kW2Warps = 4;     // warps (= rows in flight) per CTA
+constexpr int kW2Cap = 256;     // union entries per row
+constexpr int kW2Sp = 32;       // same-page chunks per row: one per lane
+constexpr int kW2Fixed = kW2Cap * (8 + 8 + 4 + 4) + kW2Sp * (8 + 8 + 8 + 8 + 4);  // bytes per warp besides the query row
+
+struct WarpSmem {
+    float4 *a;                  // [D/4]  the query row
+    unsigned long long *pk;     // [256]  union of the lists, packed, sorted by approximate score (descending)
+    unsigned long long *xk;     // [256]  re-scored candidates: ordered exact cosine, sorted (descending, lower column first)
+    unsigned long long *spk;    // [32]   ordered ranking score of the same-page entries in the current schema
+    double *sp_cos, *sp_lex, *sp_pos;  // [32]
+    int32_t *xj;                // [256]  columns of xk
+    float *dotv;                // [256]  fp32 dot products of the candidates, in pk order
+    int32_t *spcol;             // [32]   same-page columns (increasing)
+};
+__host__ __device__ inline size_t warp_smem_bytes(int D) { return (size_t)D * sizeof(float) + kW2Fixed; }
+
+__device__ __forceinline__ WarpSmem carve_warp(unsigned char *base, int D)
+{
+    WarpSmem w;
+    w.a = reinterpret_cast<float4 *>(base); base += (size_t)D * sizeof(float);
+    w.pk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
+    w.xk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
+    w.spk = reinterpret_cast<unsigned long long *>(base); base += kW2Sp * 8;
+    w.sp_cos = reinterpret_cast<double *>(base); base += kW2Sp * 8;
+    w.sp_lex = reinterpret_cast<double *>(base); base += kW2Sp * 8;
+    w.sp_pos = reinterpret_cast<double *>(base); base += kW2Sp * 8;
+    w.xj = reinterpret_cast<int32_t *>(base); base += kW2Cap * 4;
+    w.dotv = reinterpret_cast<float *>(base); base += kW2Cap * 4;
+    w.spcol = reinterpret_cast<int32_t *>(base);
+    return w;
+}
+
+// Bitonic sort of 32 * KPT keys held KPT per lane, element index = lane * KPT + r, best first.  Strides below KPT
+// are compare-exchanges inside the lane, the others one shuffle per key.
+struct WKey { unsigned long long k; int32_t j; };
+__device__ __forceinline__ bool wbefore(unsigned long long a, unsigned long long b) { return a > b; }
+__device__ __forceinline__ bool wbefore(const WKey &a, const WKey &b) { return key_before(a.k, a.j, b.k, b.j); }
+__device__ __forceinline__ unsigned long long wshfl(unsigned long long x, int m) { return __shfl_xor_sync(0xFFFFFFFFu, x, m); }
+__device__ __forceinline__ WKey wshfl(const WKey &x, int m)
+{
+    WKey o;
+    o.k = __shfl_xor_sync(0xFFFFFFFFu, x.k, m);
+    o.j = __shfl_xor_sync(0xFFFFFFFFu, x.j, m);
+    return o;
+}
+// `n` keys matter (the rest are pads that sort last): the network stops at the next power of two >= n.  The loops
+// over k and the shuffle strides are real loops -- the kernel's code has to stay inside the instruction cache (a
+// fully unrolled network was measured 6x slower: 16 warps per SM at 16 different places of 750 KB of code).
+template <int KPT, typename T>
+__device__ __forceinline__ void warp_sort(T (&me)[KPT], int lane, int n)
+{
+    const int i0 = lane * KPT;
+#pragma unroll 1
+    for (int k = 2; (k >> 1) < n && k <= 32 * KPT; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j >= KPT; j >>= 1) {
+            const int lj = j / KPT;
+            const bool lower = (lane & lj) == 0;
+            const bool want_first = lower == ((i0 & k) == 0);  // (k >= 2 * KPT here: the lane's keys share the direction)
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const T o = wshfl(me[r], lj);
+                const bool o_first = wbefore(o, me[r]);
+                if (want_first ? o_first : !o_first) me[r] = o;
+            }
+        }
+#pragma unroll
+        for (int j = KPT / 2; j >= 1; j >>= 1) {
+            if (j < k) {
+#pragma unroll
+                for (int r = 0; r < KPT; ++r) {
+                    const int x = r ^ j;
+                    if (x > r) {
+                        const bool up = ((i0 + r) & k) == 0;
+                        const T a = me[r], b = me[x];
+                        const bool b_first = wbefore(b, a);
+                        if (up ? b_first : !b_first) { me[r] = b; me[x] = a; }
+                    }
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ int count_above_packed(const unsigned long long *pk, int n, double x)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((double)packed_score(pk[mid]) > x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ double unord64(unsigned long long k)
+{
+    return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
+}
+
+// exact cosine of candidates [0, n_ca) (dot products in w.dotv, columns in w.pk), sorted into w.xk / w.xj;
+// returns true when some candidate broke |exact - approximate| <= eps
+__device__ __forceinline__ bool warp_sort_exact(const RowArgs &A, const WarpSmem &w, int n_ca, float na, double eps, int lane)
+{
+    constexpr int KPT = kW2Cap / 32;
+    bool viol = false;
+    // one copy of the fp64 division in the code: the keys go through shared memory
+#pragma unroll 1
+    for (int e = lane; e < n_ca; e += 32) {
+        const unsigned long long p = w.pk[e];
+        const int32_t col = packed_col(p);
+        const double x = sim_from_sums(w.dotv[e], na, A.chk_n2[col]);
+        if (!(fabs(x - (double)packed_score(p)) <= eps)) viol = true;
+        w.xk[e] = ord64(x); w.xj[e] = col;
+    }
+    __syncwarp();
+    WKey me[KPT];
+#pragma unroll
+    for (int r = 0; r < KPT; ++r) {
+        const int e = lane * KPT + r;
+        me[r].k = e < n_ca ? w.xk[e] : 0ull;
+        me[r].j = e < n_ca ? w.xj[e] : 0x7FFFFFFF;
+    }
+    __syncwarp();
+    warp_sort<KPT>(me, lane, n_ca);
+#pragma unroll
+    for (int r = 0; r < KPT; ++r) { w.xk[lane * KPT + r] = me[r].k; w.xj[lane * KPT + r] = me[r].j; }
+    return viol;
+}
+
+__global__ void __launch_bounds__(kW2Warps * 32, 4)
+rescore_warp_kernel(RowArgs A, CandLists L, const float *__restrict__ eps_chunk_max, int32_t *fail_rows,
+                    int32_t *fail_count, unsigned long long *fail_thr, unsigned long long *cand_counter,
+                    int32_t *big_rows, int32_t *big_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const WarpSmem w = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(A.D), A.D);
+    const RunParams &rp = A.rp;
+    const int n_l = lists_per_row(L);
+    const int d4 = A.D >> 2;
+    const float eps_chunk = eps_chunk_max[0];
+    unsigned long long cand_total = 0ull;
+    const int64_t n_warps = (int64_t)gridDim.x * kW2Warps;
+    for (int64_t b = (int64_t)blockIdx.x * kW2Warps + warp; b < A.n_rows; b += n_warps) {
+        const int64_t i = A.row0 + b;
+        K2_T(r0_);
+        const int64_t off0 = A.offsets[i];
+        const int c = (int)(A.offsets[i + 1] - off0);
+        bool big = c > kW2Sp;
+        // ---- the query row, its same-page chunks, its list headers: independent loads, issued together
+        __syncwarp();
+        if (!big) {
+            const float4 *src = reinterpret_cast<const float4 *>(A.img_emb + i * A.D);
+            for (int q = lane; q < d4; q += 32) w.a[q] = src[q];
+        }
+        int spj = -1;
+        if (!big && lane < c) spj = A.sorted_chunk[A.sp_start[i] + lane];
+        w.spcol[lane] = spj;
+        ListView v;
+        v.keys = nullptr; v.cnt = 0; v.tau = -CUDART_INF_F;
+        if (lane < n_l) v = list_view(L, i, A.row0, lane);
+        float tau_union = lane < n_l ? (v.cnt < 0 ? CUDART_INF_F : v.tau) : -CUDART_INF_F;  // an overflowed list certifies nothing
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) tau_union = fmaxf(tau_union, __shfl_xor_sync(FULL, tau_union, off));
+        const float na = A.img_n2[i];
+        const double eps = (double)rp.eps_scale *
+                           (double)(A.img_err[i] * 1.001f + eps_chunk * 1.001f + (float)A.D * 2.4e-7f + 2e-6f);
+        __syncwarp();
+        K2_T(r1_);
+        K2_ADD(0, r1_ - r0_);
+        // ---- same-page entries: weak terms (lane p), exact cosine (four gathers per batch)
+        double lex = 0.0, pos = 0.0, cosp = 0.0;
+        if (!big) {
+            if (lane < c) {
+                if (A.need_lex)
+                    lex = lexical_score(term_hits(A.chk_terms + (int64_t)spj * A.term_words,
+                                                  A.img_terms ? A.img_terms + i * A.term_words : nullptr, A.term_words), rp.n_terms);
+                if (A.need_pos) pos = positional_score(A.img_bbox + 4 * i, A.chk_bbox + 4 * (int64_t)spj);
+            }
+            float spdot = 0.f;
+            for (int e = 0; e < c; e += 4) {
+                const float4 *bp[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = __shfl_sync(FULL, spj, e + q < c ? e + q : c - 1);
+                    bp[q] = reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)col * A.D);
+                }
+                float r[4];
+                warp_dot4(w.a, bp[0], bp[1], bp[2], bp[3], d4, lane, r);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (lane == e + q) spdot = r[q];
+            }
+            if (lane < c) {
+                cosp = sim_from_sums(spdot, na, A.chk_n2[spj]);
+                if (A.out.pair_sim) A.out.pair_sim[off0 - A.pair0 + lane] = cosp;
+            }
+            w.sp_cos[lane] = cosp; w.sp_lex[lane] = lex; w.sp_pos[lane] = pos;
+        }
+        K2_T(r2_);
+        K2_ADD(1, r2_ - r1_);
+        bool ok = tau_union != CUDART_INF_F;
+        unsigned long long thr = 0ull;  // lower bound of the row's kneed-th best exact cosine, for the exact scan
+        // ---- sweep of the lists: entries above tau_union that are not same-page (those enter through the pair index)
+        int n_all = 0;
+        if (!big && ok) {
+            for (int l = 0; l < n_l; ++l) {
+                const int cnt = __shfl_sync(FULL, v.cnt, l);
+                const uint64_t *keys = reinterpret_cast<const uint64_t *>(__shfl_sync(FULL, (unsigned long long)v.keys, l));
+                for (int e0 = 0; e0 < cnt; e0 += 128) {
+                    uint64_t kk[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + 32 * u + lane;
+                        kk[u] = e < cnt ? __ldg(keys + e) : 0ull;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (e0 + 32 * u >= cnt) break;
+                        const int e = e0 + 32 * u + lane;
+                        const uint32_t col = cand_col(kk[u]);
+                        const float sa = cand_score(kk[u]);
+                        bool keep = e < cnt && sa > tau_union;
+                        if (keep) for (int q = 0; q < c; ++q) keep = keep && w.spcol[q] != (int32_t)col;
+                        const unsigned m = __ballot_sync(FULL, keep);
+                        const int at = n_all + __popc(m & lt_mask);
+                        if (keep && at < kW2Cap) w.pk[at] = pack_approx(sa, col);
+                        n_all += __popc(m);
+                    }
+                }
+            }
+            big = n_all > kW2Cap;
+        }
+        if (big) {  // wider than this kernel's registers: the block-per-row kernel takes the row
+            if (lane == 0) big_rows[atomicAdd(big_count, 1)] = (int32_t)i;
+            K2_ADD(9, 1);
+            continue;
+        }
+        __syncwarp();
+        K2_T(r3_);
+        K2_ADD(2, r3_ - r2_);
+        if (ok) {
+            // ---- sort by approximate score (lower column first)
+            {
+                unsigned long long me[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) me[r] = lane * 8 + r < n_all ? w.pk[lane * 8 + r] : 0ull;
+                __syncwarp();
+                warp_sort<8>(me, lane, n_all);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) w.pk[lane * 8 + r] = me[r];
+                __syncwarp();
+            }
+            K2_T(r4_);
+            K2_ADD(3, r4_ - r3_);
+            if (n_all >= rp.kneed) thr = ord64((double)packed_score(w.pk[rp.kneed - 1]) - eps);
+            // ---- depth of the exact rescoring (see rescore_kernel): the lowest line that needs exact scores
+            unsigned long long theta = ~0ull;
+            if (n_all >= rp.kmax) theta = ord64((double)packed_score(w.pk[rp.kmax - 1]) - 2.0 * eps);
+            for (int t = lane; t < c * rp.S; t += 32) {
+                const int p = t % c;
+                const double y = ranking_score(rp, rp.schema[t / c], w.sp_cos[p], w.sp_lex[p], w.sp_pos[p]);
+                if (count_above_packed(w.pk, n_all, y + eps) < rp.kneed) {
+                    const unsigned long long o = ord64(y - eps);
+                    theta = o < theta ? o : theta;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(FULL, theta, off);
+                theta = o < theta ? o : theta;
+            }
+            if (n_all < rp.kmax) theta = 0ull;
+            int n_ca;
+            {
+                int lo = 0, hi = n_all;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (ord64((double)packed_score(w.pk[mid])) >= theta) lo = mid + 1; else hi = mid;
+                }
+                n_ca = lo;
+            }
+            // nothing that is not re-scored can have an exact cosine above this
+            const double bound = (double)(n_ca < n_all ? fmaxf(packed_score(w.pk[n_ca]), tau_union) : tau_union) + eps;
+            K2_T(r5_);
+            K2_ADD(4, r5_ - r4_);
+            K2_ADD(8, 1);
+            K2_ADD(10, n_all);
+            K2_ADD(11, n_ca);
+            cand_total += (unsigned long long)(n_ca + c);
+            // ---- exact cosine of the candidates: four gathers per batch
+            for (int e = 0; e < n_ca; e += 4) {
+                const float4 *bp[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int32_t col = packed_col(w.pk[e + q < n_ca ? e + q : n_ca - 1]);
+                    bp[q] = reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)col * A.D);
+                }
+                float r[4];
+                warp_dot4(w.a, bp[0], bp[1], bp[2], bp[3], d4, lane, r);
+                float mine = r[0];
+#pragma unroll
+                for (int q = 1; q < 4; ++q) if (lane == q) mine = r[q];
+                if (lane < 4 && e + lane < n_ca) w.dotv[e + lane] = mine;
+            }
+            __syncwarp();
+            K2_T(r6_);
+            K2_ADD(5, r6_ - r5_);
+            // ---- one sort of the candidates by exact cosine (every schema ranks them alike)
+            bool viol = warp_sort_exact(A, w, n_ca, na, eps, lane);
+            viol = __any_sync(FULL, viol);
+            if (viol) {  // an input the error model does not cover: the row is ranked by the exact scan
+                ok = false;
+                if (lane == 0 && A.viol_counter) atomicAdd(A.viol_counter, 1ull);
+            }
+            __syncwarp();
+            K2_T(r7_);
+            K2_ADD(6, r7_ - r6_);
+            // ---- per schema: the same-page entries are merged by counting (finish_row)
+            const int64_t io = i - A.o_row0;
+            const int64_t p0 = off0 - A.pair0;
+            const int n = n_ca + c;
+            const int n_top = n_ca < rp.kmax ? n_ca : rp.kmax;  // candidates that can reach the top-K lists
+            for (int si = 0; si < rp.S; ++si) {
+                const int s = rp.schema[si];
+                double sc_p = 0.0;
+                if (lane < c) {
+                    sc_p = ranking_score(rp, s, cosp, lex, pos);
+                    if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P_out + p0 + lane] = sc_p;
+                }
+                w.spk[lane] = ord64(sc_p);
+                __syncwarp();
+                const int64_t o_top = ((int64_t)si * A.o_rows + io) * rp.kmax;
+                bool bad = false, have_kth = false;
+                double kth = -CUDART_INF;
+                for (int t = lane; t < c + n_top; t += 32) {
+                    unsigned long long k;
+                    int j, at;
+                    double sc;
+                    if (t < c) {  // a same-page entry: binary search in the sorted candidates, count the other same-page entries
+                        k = w.spk[t]; j = w.spcol[t]; sc = sc_p;
+                        int lo = 0, hi = n_ca;
+                        while (lo < hi) {
+                            const int mid = (lo + hi) >> 1;
+                            if (key_before(w.xk[mid], w.xj[mid], k, j)) lo = mid + 1; else hi = mid;
+                        }
+                        at = lo;
+                        for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
+                        if (at < rp.kneed) {
+                            bool known = true;  // `at` is the pair's rank ...
+                            if (!(sc > bound)) {  // ... unless a column that was not re-scored may beat it
+                                const int ahead = count_above_packed(w.pk, n_all, sc + eps) - n_ca;
+                                known = false;
+                                if (at + (ahead > 0 ? ahead : 0) < rp.kneed) bad = true;  // else: beyond the cutoff either way
+                            }
+                            if (known && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P_out + p0 + t] = at + 1;
+                        }
+                    } else {      // a candidate: its sorted position + the same-page entries that beat it
+                        k = w.xk[t - c]; j = w.xj[t - c]; sc = unord64(k);
+                        at = t - c;
+                        for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
+                    }
+                    if (at < rp.kmax && A.out.topk_idx) {
+                        A.out.topk_idx[o_top + at] = (int64_t)j + rp.col_offset;
+                        A.out.topk_score[o_top + at] = sc;
+                    }
+                    if (at == rp.kmax - 1) { kth = sc; have_kth = true; }
+                }
+                if (A.out.topk_idx)
+                    for (int r = n + lane; r < rp.kmax; r += 32) {  // fewer entries than the lists are wide
+                        A.out.topk_idx[o_top + r] = -1; A.out.topk_score[o_top + r] = -CUDART_INF;
+                    }
+                const unsigned hk = __ballot_sync(FULL, have_kth);
+                if (hk) {
+                    const int srcl = __ffs(hk) - 1;
+                    kth = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(kth), srcl));
+                }
+                bad = __any_sync(FULL, bad);
+                ok = ok && !bad && (kth > bound);
+                __syncwarp();
+            }
+            K2_T(r8_);
+            K2_ADD(7, r8_ - r7_);
+        }
+        if (!ok && lane == 0) {
+            const int slot = atomicAdd(fail_count, 1);
+            fail_rows[slot] = (int32_t)i;
+            if (fail_thr) fail_thr[slot] = thr;
+        }
+    }
+    if (lane == 0 && cand_counter && cand_total) atomicAdd(cand_counter, cand_total);
 }
 
 // ---------------------------------------------------------------------------
@@ -811,7 +1220,8 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            const CandLists *lists, const float *eps_chunk_max, const Outputs &out,
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
-                           int32_t *cert_count, RowRange range, cudaStream_t st, int64_t grid_limit)
+                           int32_t *cert_count, RowRange range, cudaStream_t st, int64_t grid_limit,
+                           int32_t *big_rows, int32_t *big_count)
 {
     if (img.n == 0) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
@@ -825,8 +1235,29 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     if (e != cudaSuccess) return e;
     int64_t grid = A.n_rows < (int64_t)sm_count() * 16 ? A.n_rows : (int64_t)sm_count() * 16;
     if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;  // (the rows are handed out with a grid stride)
+    // The warp-per-row kernel ranks every row of the common shape; what it hands over (big_count rows) goes through
+    // the block-per-row kernel in row-list mode.  Runs that certify across ranks or return the deep lists, and
+    // same-page mode, are the block kernel's alone.
+    const size_t wsmem = warp_smem_bytes(img.D) * kW2Warps;
+    const bool by_warp = lists && big_rows && big_count && fail_rows && fail_count && !tau_global && !cert_count &&
+                         !out.deep_idx && lists_per_row(L) <= 32 && wsmem * 2 <= 200 * 1024;
+    if (by_warp) {
+        e = cudaFuncSetAttribute(rescore_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+        if (e != cudaSuccess) return e;
+        int per_sm = (int)(200 * 1024 / wsmem);
+        if (per_sm > 4) per_sm = 4;
+        int64_t wgrid = (A.n_rows + kW2Warps - 1) / kW2Warps;
+        if (wgrid > (int64_t)sm_count() * per_sm) wgrid = (int64_t)sm_count() * per_sm;
+        if (grid_limit > 0 && wgrid > grid_limit / 8 * per_sm) wgrid = grid_limit / 8 * per_sm > 0 ? grid_limit / 8 * per_sm : 1;
+        rescore_warp_kernel<<<(unsigned)wgrid, kW2Warps * 32, wsmem, st>>>(A, L, eps_chunk_max, fail_rows, fail_count,
+                                                                          fail_thr, cand_counter, big_rows, big_count);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (grid > (int64_t)sm_count() * 2) grid = (int64_t)sm_count() * 2;  // (few rows, if any)
+    }
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
-                                                           fail_count, fail_thr, cand_counter, tau_global, cert_count);
+                                                           fail_count, fail_thr, cand_counter, tau_global, cert_count,
+                                                           by_warp ? big_rows : nullptr, by_warp ? big_count : nullptr);
     return cudaGetLastError();
 }
 
