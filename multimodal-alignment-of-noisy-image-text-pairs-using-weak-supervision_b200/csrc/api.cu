@@ -2,6 +2,7 @@
 // K0 -> K1 -> K2 -> exact scan -> K4 pipeline.  No CPU fallback anywhere: every
 // result is produced by the kernels in prep.cu / fused_tc.cu / rescore.cu.
 #include "common.cuh"
+#include <algorithm>
 #include <cuda.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -119,7 +120,7 @@ struct mmalign_ctx {
     DevBuf list_keys, list_tau, list_count;
     DevBuf list_keys2, list_tau2, list_count2;  // second set: slab s+1 is contracted while slab s is re-scored
     DevBuf fail_rows, fail_thr, scan_buf, scan_cnt, small;
-    DevBuf big_rows;               // rows the warp-per-row rescoring hands to the block-per-row kernel
+    DevBuf big_rows, k2_scratch;   // rows the warp-per-row rescoring hands to the block-per-row kernel; its per-row records
     DevBuf metrics_scratch, stage; // stage: device copies of host outputs
     DevBuf term_table, text_off, text_bytes;  // mmalign_term_bitsets: term table, uploads of host texts
     DevBuf copy_off, copy_len, half_up;       // mmalign_copy_decode: field tables; set_*_half: upload of host halves
@@ -224,7 +225,7 @@ extern "C" void mmalign_destroy(mmalign_ctx *c)
     c->img.destroy_events();
     c->chk.destroy_events();
     DevBuf *bufs[] = {&c->px_offsets, &c->px_sorted, &c->px_start, &c->px_scratch, &c->list_keys, &c->list_tau, &c->list_count,
-                      &c->list_keys2, &c->list_tau2, &c->list_count2, &c->fail_rows, &c->fail_thr, &c->big_rows, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
+                      &c->list_keys2, &c->list_tau2, &c->list_count2, &c->fail_rows, &c->fail_thr, &c->big_rows, &c->k2_scratch, &c->scan_buf, &c->scan_cnt, &c->small, &c->metrics_scratch, &c->stage,
                       &c->term_table, &c->text_off, &c->text_bytes, &c->copy_off, &c->copy_len, &c->half_up};
     for (DevBuf *b : bufs) b->release();
     for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
@@ -916,6 +917,11 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         CU(c, c->fail_rows.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(int32_t)));
         CU(c, c->fail_thr.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(unsigned long long)));
         CU(c, c->big_rows.reserve((size_t)(img.n > 0 ? img.n : 1) * sizeof(int32_t)));
+        {   // per-row records of the warp-per-row rescoring: the rescoring of one slab at a time uses them
+            int64_t most_rows = 1;
+            for (int s = 0; s < n_slabs; ++s) most_rows = std::max<int64_t>(most_rows, bounds[s + 1] - bounds[s]);
+            CU(c, c->k2_scratch.reserve(k2_scratch_bytes(most_rows)));
+        }
         CU(c, c->scan_buf.reserve(scan_scratch_bytes()));
         CU(c, c->scan_cnt.reserve(sizeof(int32_t) * kScanSlots));
         if (!imported) {
@@ -1054,7 +1060,7 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             const int64_t k2_grid = overlap && s + 1 < n_slabs ? (int64_t)(c->sm_count - k1_sms) * 8 : 0;
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, fail_rows, slab_fail + s, pre.thr,
                                  cand_counter, error_flag, nullptr, nullptr, range, sk2, k2_grid,
-                                 (int32_t *)c->big_rows.p + r0, slab_big + s));
+                                 (int32_t *)c->big_rows.p + r0, slab_big + s, c->k2_scratch.p));
             CU(c, cudaEventRecord(ev[2], sk2));
             CU(c, launch_exact_scan(img, chk, c->px, rp, fail_rows, slab_fail + s, 0, out, error_flag, range, &pre, sk2));
             launches += 3;

@@ -302,7 +302,9 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
                            int32_t *cert_count, RowRange rows, cudaStream_t st, int64_t grid_limit = 0,
-                           int32_t *big_rows = nullptr, int32_t *big_count = nullptr);  // scratch of the warp-per-row kernel: [rows], [1] zeroed
+                           int32_t *big_rows = nullptr, int32_t *big_count = nullptr,  // scratch of the warp-per-row kernels: [rows], [1] zeroed,
+                           void *k2_scratch = nullptr);                                 // and k2_scratch_bytes(rows)
+size_t k2_scratch_bytes(int64_t rows);
 // scratch of the two-stage exact scan: per failed row (slot) its threshold, and what stage 1 kept for it
 constexpr int kScanSlots = 2048, kScanCap = 1024;
 struct ScanScratch {

@@ -636,49 +636,57 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
 }
 
 // ---------------------------------------------------------------------------
-// K2, one WARP per image row
+// K2 in three kernels, one WARP per image row
 // ---------------------------------------------------------------------------
 // The same computation as rescore_kernel's lists mode -- same formulas, same order of floating-point operations,
-// same outputs bit for bit -- organised for the common shape of a row (at most 32 lists, at most 32 same-page
-// chunks, a union of at most 256 candidates): no block barriers, sorts in registers (8 keys per lane, blocked
-// layout: strides 1-4 never leave the lane), 4 row gathers = 16 x 512 B in flight per warp, 16 warps per SM.
-// Rows outside that shape are handed to rescore_kernel through big_rows (row-list mode).
-// Measured at config 5 against the block-per-row kernel: DESIGN.md section 4.
+// same outputs bit for bit -- cut where its character changes, for the common shape of a row (at most 32 lists, at
+// most 32 same-page chunks, a union of at most 256 candidates; other rows go to rescore_kernel in row-list mode):
+//   select_kernel  K2a  list headers, same-page entries (weak terms, exact cosine), sweep of the lists, sort by
+//                       approximate score, depth of the exact rescoring.  Latency/issue-bound: many light warps.
+//   gather_kernel  K2b  the row gathers and canonical dot products of the candidates, nothing else: two 2 KB rows
+//                       in flight per warp, which is what tools/gather_probe.cu measures at 7.3 TB/s.
+//   rank_kernel    K2c  fp64 cosine, sort by exact score, per-schema merge, outputs, certificate.
+// In one kernel (block per row, and a first warp-per-row version) the gathers ran 40 % of each row's time and the
+// row's serial phases the rest, with too few rows resident to cover either; apart they are each near their own limit.
+// State between them travels through a per-row scratch record (K2Scratch, 3.9 KB per row).
+// No block barriers; sorts in registers (8 keys per lane, blocked layout: strides 1-4 never leave the lane) with real
+// loops over the network's stages -- a fully unrolled network (750 KB of code, 16 warps at 16 different places of it)
+// was measured 6x slower than the instruction cache allows.
 constexpr int kW2Warps = 4;     // warps (= rows in flight) per CTA
 constexpr int kW2Cap = 256;     // union entries per row
 constexpr int kW2Sp = 32;       // same-page chunks per row: one per lane
-constexpr int kW2Fixed = kW2Cap * (8 + 8 + 4 + 4) + kW2Sp * (8 + 8 + 8 + 8 + 4);  // bytes per warp besides the query row
 
-struct WarpSmem {
-    float4 *a;                  // [D/4]  the query row
-    unsigned long long *pk;     // [256]  union of the lists, packed, sorted by approximate score (descending)
-    unsigned long long *xk;     // [256]  re-scored candidates: ordered exact cosine, sorted (descending, lower column first)
-    unsigned long long *spk;    // [32]   ordered ranking score of the same-page entries in the current schema
-    double *sp_cos, *sp_lex, *sp_pos;  // [32]
-    int32_t *xj;                // [256]  columns of xk
-    float *dotv;                // [256]  fp32 dot products of the candidates, in pk order
-    int32_t *spcol;             // [32]   same-page columns (increasing)
+struct K2Row {                  // scratch header of a row
+    int32_t n_all, n_ca;        // union entries above tau_union; re-scored candidates
+    int32_t state;              // 0 = ranked by these kernels, 1 = left to rescore_kernel, 2 = uncertifiable (already on the fail list)
+    float tau_union;
+    unsigned long long thr;     // lower bound of the row's kneed-th best exact cosine, for the exact scan
+    unsigned long long pad;
 };
-__host__ __device__ inline size_t warp_smem_bytes(int D) { return (size_t)D * sizeof(float) + kW2Fixed; }
-
-__device__ __forceinline__ WarpSmem carve_warp(unsigned char *base, int D)
+struct K2Scratch {
+    K2Row *hdr;                 // [rows]
+    unsigned long long *pk;     // [rows][256] union, packed, sorted by approximate score (descending)
+    float *dotv;                // [rows][256] fp32 dot products of the re-scored candidates, in pk order
+    double *sp;                 // [rows][3][32] exact cosine, lexical, positional term of the same-page entries
+};
+size_t k2_scratch_bytes(int64_t rows)
 {
-    WarpSmem w;
-    w.a = reinterpret_cast<float4 *>(base); base += (size_t)D * sizeof(float);
-    w.pk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
-    w.xk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
-    w.spk = reinterpret_cast<unsigned long long *>(base); base += kW2Sp * 8;
-    w.sp_cos = reinterpret_cast<double *>(base); base += kW2Sp * 8;
-    w.sp_lex = reinterpret_cast<double *>(base); base += kW2Sp * 8;
-    w.sp_pos = reinterpret_cast<double *>(base); base += kW2Sp * 8;
-    w.xj = reinterpret_cast<int32_t *>(base); base += kW2Cap * 4;
-    w.dotv = reinterpret_cast<float *>(base); base += kW2Cap * 4;
-    w.spcol = reinterpret_cast<int32_t *>(base);
-    return w;
+    return (size_t)rows * (sizeof(K2Row) + kW2Cap * 8 + kW2Cap * 4 + 3 * kW2Sp * 8) + 1024;
+}
+static K2Scratch carve_scratch(void *base, int64_t rows)
+{
+    K2Scratch k;
+    unsigned char *p = reinterpret_cast<unsigned char *>(base);
+    k.pk = reinterpret_cast<unsigned long long *>(p); p += (size_t)rows * kW2Cap * 8;
+    k.sp = reinterpret_cast<double *>(p); p += (size_t)rows * 3 * kW2Sp * 8;
+    k.hdr = reinterpret_cast<K2Row *>(p); p += (size_t)rows * sizeof(K2Row);
+    k.dotv = reinterpret_cast<float *>(p);
+    return k;
 }
 
 // Bitonic sort of 32 * KPT keys held KPT per lane, element index = lane * KPT + r, best first.  Strides below KPT
-// are compare-exchanges inside the lane, the others one shuffle per key.
+// are compare-exchanges inside the lane, the others one shuffle per key.  `n` keys matter (the rest are pads that
+// sort last): the network stops at the next power of two >= n.
 struct WKey { unsigned long long k; int32_t j; };
 __device__ __forceinline__ bool wbefore(unsigned long long a, unsigned long long b) { return a > b; }
 __device__ __forceinline__ bool wbefore(const WKey &a, const WKey &b) { return key_before(a.k, a.j, b.k, b.j); }
@@ -690,9 +698,6 @@ __device__ __forceinline__ WKey wshfl(const WKey &x, int m)
     o.j = __shfl_xor_sync(0xFFFFFFFFu, x.j, m);
     return o;
 }
-// `n` keys matter (the rest are pads that sort last): the network stops at the next power of two >= n.  The loops
-// over k and the shuffle strides are real loops -- the kernel's code has to stay inside the instruction cache (a
-// fully unrolled network was measured 6x slower: 16 warps per SM at 16 different places of 750 KB of code).
 template <int KPT, typename T>
 __device__ __forceinline__ void warp_sort(T (&me)[KPT], int lane, int n)
 {
@@ -729,9 +734,11 @@ __device__ __forceinline__ void warp_sort(T (&me)[KPT], int lane, int n)
     }
 }
 
+// number of values > x among the n approximate scores of pk (sorted descending)
 __device__ __forceinline__ int count_above_packed(const unsigned long long *pk, int n, double x)
 {
-    int lo = 0, hi = n;
+    if (n == 0 || (double)packed_score(pk[n - 1]) > x) return n;  // (the usual answer for a pair far below the cutoff)
+    int lo = 0, hi = n - 1;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if ((double)packed_score(pk[mid]) > x) lo = mid + 1; else hi = mid;
@@ -742,47 +749,32 @@ __device__ __forceinline__ double unord64(unsigned long long k)
 {
     return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k));
 }
-
-// exact cosine of candidates [0, n_ca) (dot products in w.dotv, columns in w.pk), sorted into w.xk / w.xj;
-// returns true when some candidate broke |exact - approximate| <= eps
-__device__ __forceinline__ bool warp_sort_exact(const RowArgs &A, const WarpSmem &w, int n_ca, float na, double eps, int lane)
+__device__ __forceinline__ double row_eps(const RowArgs &A, int64_t i, float eps_chunk)
 {
-    constexpr int KPT = kW2Cap / 32;
-    bool viol = false;
-    // one copy of the fp64 division in the code: the keys go through shared memory
-#pragma unroll 1
-    for (int e = lane; e < n_ca; e += 32) {
-        const unsigned long long p = w.pk[e];
-        const int32_t col = packed_col(p);
-        const double x = sim_from_sums(w.dotv[e], na, A.chk_n2[col]);
-        if (!(fabs(x - (double)packed_score(p)) <= eps)) viol = true;
-        w.xk[e] = ord64(x); w.xj[e] = col;
-    }
-    __syncwarp();
-    WKey me[KPT];
-#pragma unroll
-    for (int r = 0; r < KPT; ++r) {
-        const int e = lane * KPT + r;
-        me[r].k = e < n_ca ? w.xk[e] : 0ull;
-        me[r].j = e < n_ca ? w.xj[e] : 0x7FFFFFFF;
-    }
-    __syncwarp();
-    warp_sort<KPT>(me, lane, n_ca);
-#pragma unroll
-    for (int r = 0; r < KPT; ++r) { w.xk[lane * KPT + r] = me[r].k; w.xj[lane * KPT + r] = me[r].j; }
-    return viol;
+    return (double)A.rp.eps_scale * (double)(A.img_err[i] * 1.001f + eps_chunk * 1.001f + (float)A.D * 2.4e-7f + 2e-6f);
 }
 
-__global__ void __launch_bounds__(kW2Warps * 32, 4)
-rescore_warp_kernel(RowArgs A, CandLists L, const float *__restrict__ eps_chunk_max, int32_t *fail_rows,
-                    int32_t *fail_count, unsigned long long *fail_thr, unsigned long long *cand_counter,
-                    int32_t *big_rows, int32_t *big_count)
+// ---- K2a
+struct SelectSmem { float4 *a; unsigned long long *pk; double *sp; int32_t *spcol; };
+__host__ __device__ inline size_t select_smem_bytes(int D) { return (size_t)D * 4 + kW2Cap * 8 + 3 * kW2Sp * 8 + kW2Sp * 4; }
+
+__global__ void __launch_bounds__(kW2Warps * 32, 8)
+select_kernel(RowArgs A, CandLists L, K2Scratch K, const float *__restrict__ eps_chunk_max, int32_t *fail_rows,
+              int32_t *fail_count, unsigned long long *fail_thr, unsigned long long *cand_counter, int32_t *big_rows,
+              int32_t *big_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
-    const WarpSmem w = carve_warp(smem_raw + (size_t)warp * warp_smem_bytes(A.D), A.D);
+    SelectSmem w;
+    {
+        unsigned char *base = smem_raw + (size_t)warp * select_smem_bytes(A.D);
+        w.a = reinterpret_cast<float4 *>(base); base += (size_t)A.D * 4;
+        w.pk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
+        w.sp = reinterpret_cast<double *>(base); base += 3 * kW2Sp * 8;
+        w.spcol = reinterpret_cast<int32_t *>(base);
+    }
     const RunParams &rp = A.rp;
     const int n_l = lists_per_row(L);
     const int d4 = A.D >> 2;
@@ -811,43 +803,39 @@ rescore_warp_kernel(RowArgs A, CandLists L, const float *__restrict__ eps_chunk_
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) tau_union = fmaxf(tau_union, __shfl_xor_sync(FULL, tau_union, off));
         const float na = A.img_n2[i];
-        const double eps = (double)rp.eps_scale *
-                           (double)(A.img_err[i] * 1.001f + eps_chunk * 1.001f + (float)A.D * 2.4e-7f + 2e-6f);
+        const double eps = row_eps(A, i, eps_chunk);
         __syncwarp();
         K2_T(r1_);
         K2_ADD(0, r1_ - r0_);
-        // ---- same-page entries: weak terms (lane p), exact cosine (four gathers per batch)
-        double lex = 0.0, pos = 0.0, cosp = 0.0;
+        // ---- same-page entries: weak terms (lane p), exact cosine (two gathers per batch)
         if (!big) {
+            double lex = 0.0, pos = 0.0, cosp = 0.0;
+            float nb = 1.f;
             if (lane < c) {
+                nb = A.chk_n2[spj];
                 if (A.need_lex)
                     lex = lexical_score(term_hits(A.chk_terms + (int64_t)spj * A.term_words,
                                                   A.img_terms ? A.img_terms + i * A.term_words : nullptr, A.term_words), rp.n_terms);
                 if (A.need_pos) pos = positional_score(A.img_bbox + 4 * i, A.chk_bbox + 4 * (int64_t)spj);
             }
             float spdot = 0.f;
-            for (int e = 0; e < c; e += 4) {
-                const float4 *bp[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int col = __shfl_sync(FULL, spj, e + q < c ? e + q : c - 1);
-                    bp[q] = reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)col * A.D);
-                }
-                float r[4];
-                warp_dot4(w.a, bp[0], bp[1], bp[2], bp[3], d4, lane, r);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (lane == e + q) spdot = r[q];
+            for (int e = 0; e < c; e += 2) {
+                const int c0 = __shfl_sync(FULL, spj, e), c1 = __shfl_sync(FULL, spj, e + 1 < c ? e + 1 : e);
+                float d0, d1;
+                warp_dot2(w.a, reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)c0 * A.D),
+                          reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)c1 * A.D), d4, lane, d0, d1);
+                if (lane == e) spdot = d0;
+                if (lane == e + 1) spdot = d1;
             }
             if (lane < c) {
-                cosp = sim_from_sums(spdot, na, A.chk_n2[spj]);
+                cosp = sim_from_sums(spdot, na, nb);
                 if (A.out.pair_sim) A.out.pair_sim[off0 - A.pair0 + lane] = cosp;
             }
-            w.sp_cos[lane] = cosp; w.sp_lex[lane] = lex; w.sp_pos[lane] = pos;
+            w.sp[lane] = cosp; w.sp[kW2Sp + lane] = lex; w.sp[2 * kW2Sp + lane] = pos;
         }
         K2_T(r2_);
         K2_ADD(1, r2_ - r1_);
-        bool ok = tau_union != CUDART_INF_F;
-        unsigned long long thr = 0ull;  // lower bound of the row's kneed-th best exact cosine, for the exact scan
+        const bool ok = tau_union != CUDART_INF_F;
         // ---- sweep of the lists: entries above tau_union that are not same-page (those enter through the pair index)
         int n_all = 0;
         if (!big && ok) {
@@ -878,164 +866,286 @@ rescore_warp_kernel(RowArgs A, CandLists L, const float *__restrict__ eps_chunk_
             }
             big = n_all > kW2Cap;
         }
-        if (big) {  // wider than this kernel's registers: the block-per-row kernel takes the row
-            if (lane == 0) big_rows[atomicAdd(big_count, 1)] = (int32_t)i;
+        K2Row h;
+        h.n_all = n_all; h.n_ca = 0; h.state = big ? 1 : (ok ? 0 : 2); h.tau_union = tau_union; h.thr = 0ull; h.pad = 0ull;
+        if (big) {  // wider than these kernels' registers: the block-per-row kernel takes the row
+            if (lane == 0) { big_rows[atomicAdd(big_count, 1)] = (int32_t)i; K.hdr[b] = h; }
             K2_ADD(9, 1);
+            continue;
+        }
+        if (!ok) {  // nothing certifies this row: straight to the exact scan
+            if (lane == 0) {
+                const int slot = atomicAdd(fail_count, 1);
+                fail_rows[slot] = (int32_t)i;
+                if (fail_thr) fail_thr[slot] = 0ull;
+                K.hdr[b] = h;
+            }
             continue;
         }
         __syncwarp();
         K2_T(r3_);
         K2_ADD(2, r3_ - r2_);
-        if (ok) {
-            // ---- sort by approximate score (lower column first)
-            {
-                unsigned long long me[8];
+        // ---- sort by approximate score (lower column first)
+        {
+            unsigned long long me[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) me[r] = lane * 8 + r < n_all ? w.pk[lane * 8 + r] : 0ull;
-                __syncwarp();
-                warp_sort<8>(me, lane, n_all);
+            for (int r = 0; r < 8; ++r) me[r] = lane * 8 + r < n_all ? w.pk[lane * 8 + r] : 0ull;
+            __syncwarp();
+            warp_sort<8>(me, lane, n_all);
+            unsigned long long *dst = K.pk + b * kW2Cap + lane * 8;
 #pragma unroll
-                for (int r = 0; r < 8; ++r) w.pk[lane * 8 + r] = me[r];
-                __syncwarp();
-            }
-            K2_T(r4_);
-            K2_ADD(3, r4_ - r3_);
-            if (n_all >= rp.kneed) thr = ord64((double)packed_score(w.pk[rp.kneed - 1]) - eps);
-            // ---- depth of the exact rescoring (see rescore_kernel): the lowest line that needs exact scores
-            unsigned long long theta = ~0ull;
-            if (n_all >= rp.kmax) theta = ord64((double)packed_score(w.pk[rp.kmax - 1]) - 2.0 * eps);
-            for (int t = lane; t < c * rp.S; t += 32) {
-                const int p = t % c;
-                const double y = ranking_score(rp, rp.schema[t / c], w.sp_cos[p], w.sp_lex[p], w.sp_pos[p]);
-                if (count_above_packed(w.pk, n_all, y + eps) < rp.kneed) {
-                    const unsigned long long o = ord64(y - eps);
-                    theta = o < theta ? o : theta;
-                }
-            }
+            for (int r = 0; r < 8; ++r) { w.pk[lane * 8 + r] = me[r]; }
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(FULL, theta, off);
+            for (int r = 0; r < 8; r += 2) if (lane * 8 + r < n_all) *reinterpret_cast<ulonglong2 *>(dst + r) = make_ulonglong2(me[r], me[r + 1]);
+            __syncwarp();
+        }
+        K2_T(r4_);
+        K2_ADD(3, r4_ - r3_);
+        if (n_all >= rp.kneed) h.thr = ord64((double)packed_score(w.pk[rp.kneed - 1]) - eps);
+        // ---- depth of the exact rescoring (see rescore_kernel): the lowest line that needs exact scores
+        unsigned long long theta = ~0ull;
+        if (n_all >= rp.kmax) theta = ord64((double)packed_score(w.pk[rp.kmax - 1]) - 2.0 * eps);
+        for (int t = lane; t < c * rp.S; t += 32) {
+            const int p = t % c;
+            const double y = ranking_score(rp, rp.schema[t / c], w.sp[p], w.sp[kW2Sp + p], w.sp[2 * kW2Sp + p]);
+            if (count_above_packed(w.pk, n_all, y + eps) < rp.kneed) {
+                const unsigned long long o = ord64(y - eps);
                 theta = o < theta ? o : theta;
             }
-            if (n_all < rp.kmax) theta = 0ull;
-            int n_ca;
-            {
-                int lo = 0, hi = n_all;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (ord64((double)packed_score(w.pk[mid])) >= theta) lo = mid + 1; else hi = mid;
-                }
-                n_ca = lo;
-            }
-            // nothing that is not re-scored can have an exact cosine above this
-            const double bound = (double)(n_ca < n_all ? fmaxf(packed_score(w.pk[n_ca]), tau_union) : tau_union) + eps;
-            K2_T(r5_);
-            K2_ADD(4, r5_ - r4_);
-            K2_ADD(8, 1);
-            K2_ADD(10, n_all);
-            K2_ADD(11, n_ca);
-            cand_total += (unsigned long long)(n_ca + c);
-            // ---- exact cosine of the candidates: four gathers per batch
-            for (int e = 0; e < n_ca; e += 4) {
-                const float4 *bp[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int32_t col = packed_col(w.pk[e + q < n_ca ? e + q : n_ca - 1]);
-                    bp[q] = reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)col * A.D);
-                }
-                float r[4];
-                warp_dot4(w.a, bp[0], bp[1], bp[2], bp[3], d4, lane, r);
-                float mine = r[0];
-#pragma unroll
-                for (int q = 1; q < 4; ++q) if (lane == q) mine = r[q];
-                if (lane < 4 && e + lane < n_ca) w.dotv[e + lane] = mine;
-            }
-            __syncwarp();
-            K2_T(r6_);
-            K2_ADD(5, r6_ - r5_);
-            // ---- one sort of the candidates by exact cosine (every schema ranks them alike)
-            bool viol = warp_sort_exact(A, w, n_ca, na, eps, lane);
-            viol = __any_sync(FULL, viol);
-            if (viol) {  // an input the error model does not cover: the row is ranked by the exact scan
-                ok = false;
-                if (lane == 0 && A.viol_counter) atomicAdd(A.viol_counter, 1ull);
-            }
-            __syncwarp();
-            K2_T(r7_);
-            K2_ADD(6, r7_ - r6_);
-            // ---- per schema: the same-page entries are merged by counting (finish_row)
-            const int64_t io = i - A.o_row0;
-            const int64_t p0 = off0 - A.pair0;
-            const int n = n_ca + c;
-            const int n_top = n_ca < rp.kmax ? n_ca : rp.kmax;  // candidates that can reach the top-K lists
-            for (int si = 0; si < rp.S; ++si) {
-                const int s = rp.schema[si];
-                double sc_p = 0.0;
-                if (lane < c) {
-                    sc_p = ranking_score(rp, s, cosp, lex, pos);
-                    if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P_out + p0 + lane] = sc_p;
-                }
-                w.spk[lane] = ord64(sc_p);
-                __syncwarp();
-                const int64_t o_top = ((int64_t)si * A.o_rows + io) * rp.kmax;
-                bool bad = false, have_kth = false;
-                double kth = -CUDART_INF;
-                for (int t = lane; t < c + n_top; t += 32) {
-                    unsigned long long k;
-                    int j, at;
-                    double sc;
-                    if (t < c) {  // a same-page entry: binary search in the sorted candidates, count the other same-page entries
-                        k = w.spk[t]; j = w.spcol[t]; sc = sc_p;
-                        int lo = 0, hi = n_ca;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (key_before(w.xk[mid], w.xj[mid], k, j)) lo = mid + 1; else hi = mid;
-                        }
-                        at = lo;
-                        for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
-                        if (at < rp.kneed) {
-                            bool known = true;  // `at` is the pair's rank ...
-                            if (!(sc > bound)) {  // ... unless a column that was not re-scored may beat it
-                                const int ahead = count_above_packed(w.pk, n_all, sc + eps) - n_ca;
-                                known = false;
-                                if (at + (ahead > 0 ? ahead : 0) < rp.kneed) bad = true;  // else: beyond the cutoff either way
-                            }
-                            if (known && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P_out + p0 + t] = at + 1;
-                        }
-                    } else {      // a candidate: its sorted position + the same-page entries that beat it
-                        k = w.xk[t - c]; j = w.xj[t - c]; sc = unord64(k);
-                        at = t - c;
-                        for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
-                    }
-                    if (at < rp.kmax && A.out.topk_idx) {
-                        A.out.topk_idx[o_top + at] = (int64_t)j + rp.col_offset;
-                        A.out.topk_score[o_top + at] = sc;
-                    }
-                    if (at == rp.kmax - 1) { kth = sc; have_kth = true; }
-                }
-                if (A.out.topk_idx)
-                    for (int r = n + lane; r < rp.kmax; r += 32) {  // fewer entries than the lists are wide
-                        A.out.topk_idx[o_top + r] = -1; A.out.topk_score[o_top + r] = -CUDART_INF;
-                    }
-                const unsigned hk = __ballot_sync(FULL, have_kth);
-                if (hk) {
-                    const int srcl = __ffs(hk) - 1;
-                    kth = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(kth), srcl));
-                }
-                bad = __any_sync(FULL, bad);
-                ok = ok && !bad && (kth > bound);
-                __syncwarp();
-            }
-            K2_T(r8_);
-            K2_ADD(7, r8_ - r7_);
         }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(FULL, theta, off);
+            theta = o < theta ? o : theta;
+        }
+        if (n_all < rp.kmax) theta = 0ull;
+        {
+            int lo = 0, hi = n_all;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ord64((double)packed_score(w.pk[mid])) >= theta) lo = mid + 1; else hi = mid;
+            }
+            h.n_ca = lo;
+        }
+        if (lane == 0) K.hdr[b] = h;
+        if (lane < c) {
+            double *sp = K.sp + b * (3 * kW2Sp);
+            sp[lane] = w.sp[lane]; sp[kW2Sp + lane] = w.sp[kW2Sp + lane]; sp[2 * kW2Sp + lane] = w.sp[2 * kW2Sp + lane];
+        }
+        cand_total += (unsigned long long)(h.n_ca + c);
+        K2_T(r5_);
+        K2_ADD(4, r5_ - r4_);
+        K2_ADD(8, 1);
+        K2_ADD(10, n_all);
+        K2_ADD(11, h.n_ca);
+    }
+    if (lane == 0 && cand_counter && cand_total) atomicAdd(cand_counter, cand_total);
+}
+
+// ---- K2b
+__host__ __device__ inline size_t gather_smem_bytes(int D) { return (size_t)D * 4 + kW2Cap * 4; }
+
+__global__ void __launch_bounds__(kW2Warps * 32, 8)
+gather_kernel(RowArgs A, K2Scratch K)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *base = smem_raw + (size_t)warp * gather_smem_bytes(A.D);
+    float4 *a = reinterpret_cast<float4 *>(base);
+    int32_t *cols = reinterpret_cast<int32_t *>(base + (size_t)A.D * 4);
+    const int d4 = A.D >> 2;
+    const int64_t n_warps = (int64_t)gridDim.x * kW2Warps;
+    for (int64_t b = (int64_t)blockIdx.x * kW2Warps + warp; b < A.n_rows; b += n_warps) {
+        const K2Row h = K.hdr[b];
+        if (h.state != 0 || h.n_ca == 0) continue;
+        const int64_t i = A.row0 + b;
+        __syncwarp();
+        const float4 *src = reinterpret_cast<const float4 *>(A.img_emb + i * A.D);
+        for (int q = lane; q < d4; q += 32) a[q] = src[q];
+        const unsigned long long *pk = K.pk + b * kW2Cap;
+        for (int e = lane; e < h.n_ca; e += 32) cols[e] = packed_col(pk[e]);
+        __syncwarp();
+        float *dst = K.dotv + b * kW2Cap;
+        float keep = 0.f;  // lane l keeps the dot products of entries l, l + 32, ...: one coalesced store per 32
+        for (int e = 0; e < h.n_ca; e += 2) {
+            const int c0 = cols[e], c1 = cols[e + 1 < h.n_ca ? e + 1 : e];
+            float d0, d1;
+            warp_dot2(a, reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)c0 * A.D),
+                      reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)c1 * A.D), d4, lane, d0, d1);
+            if (lane == (e & 31)) keep = d0;
+            if (lane == ((e + 1) & 31)) keep = d1;
+            if ((e & 31) == 30 || e + 2 >= h.n_ca) {
+                const int e_w = (e & ~31) + lane;
+                if (e_w < h.n_ca) dst[e_w] = keep;
+            }
+        }
+    }
+}
+
+// ---- K2c
+struct RankSmem { unsigned long long *pk, *xk, *spk; int32_t *xj, *spcol; };
+__host__ __device__ inline size_t rank_smem_bytes() { return kW2Cap * (8 + 8 + 4) + kW2Sp * (8 + 4); }
+
+__global__ void __launch_bounds__(kW2Warps * 32, 6)
+rank_kernel(RowArgs A, K2Scratch K, const float *__restrict__ eps_chunk_max, int32_t *fail_rows, int32_t *fail_count,
+            unsigned long long *fail_thr)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr int KPT = kW2Cap / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    RankSmem w;
+    {
+        unsigned char *base = smem_raw + (size_t)warp * rank_smem_bytes();
+        w.pk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
+        w.xk = reinterpret_cast<unsigned long long *>(base); base += kW2Cap * 8;
+        w.spk = reinterpret_cast<unsigned long long *>(base); base += kW2Sp * 8;
+        w.xj = reinterpret_cast<int32_t *>(base); base += kW2Cap * 4;
+        w.spcol = reinterpret_cast<int32_t *>(base);
+    }
+    const RunParams &rp = A.rp;
+    const float eps_chunk = eps_chunk_max[0];
+    const int64_t n_warps = (int64_t)gridDim.x * kW2Warps;
+    for (int64_t b = (int64_t)blockIdx.x * kW2Warps + warp; b < A.n_rows; b += n_warps) {
+        const K2Row h = K.hdr[b];
+        if (h.state != 0) continue;
+        K2_T(r0_);
+        const int64_t i = A.row0 + b;
+        const int n_all = h.n_all, n_ca = h.n_ca;
+        const int64_t off0 = A.offsets[i];
+        const int c = (int)(A.offsets[i + 1] - off0);
+        const float na = A.img_n2[i];
+        const double eps = row_eps(A, i, eps_chunk);
+        __syncwarp();
+        // ---- the row's record: union (approximate scores, columns), dot products, same-page entries
+        const unsigned long long *gpk = K.pk + b * kW2Cap;
+        const float *gdot = K.dotv + b * kW2Cap;
+        double cosp = 0.0, lex = 0.0, pos = 0.0;
+        int spj = -1;
+        if (lane < c) {
+            const double *sp = K.sp + b * (3 * kW2Sp);
+            spj = A.sorted_chunk[A.sp_start[i] + lane];
+            cosp = sp[lane]; lex = sp[kW2Sp + lane]; pos = sp[2 * kW2Sp + lane];
+        }
+        w.spcol[lane] = spj;
+        bool viol = false;
+        WKey me[KPT];
+        {
+            unsigned long long p[KPT];
+            float dv[KPT], nb[KPT];
+#pragma unroll
+            for (int r = 0; r < KPT; r += 2) {
+                const int e = lane * KPT + r;
+                ulonglong2 t = make_ulonglong2(0ull, 0ull);
+                if (e < n_all) t = *reinterpret_cast<const ulonglong2 *>(gpk + e);
+                p[r] = t.x; p[r + 1] = t.y;
+            }
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const int e = lane * KPT + r;
+                w.pk[e] = p[r];
+                dv[r] = e < n_ca ? gdot[e] : 0.f;
+                nb[r] = e < n_ca ? A.chk_n2[packed_col(p[r])] : 1.f;
+            }
+            // exact cosine of the re-scored candidates.  The certificate rests on |exact - approximate| <= eps: every
+            // candidate tests that bound; a violation (an input the error model does not cover) withdraws the row's
+            // certificate, and the row is ranked by the exact scan instead.
+#pragma unroll
+            for (int r = 0; r < KPT; ++r) {
+                const int e = lane * KPT + r;
+                me[r].k = 0ull; me[r].j = 0x7FFFFFFF;
+                if (e < n_ca) {
+                    const double x = sim_from_sums(dv[r], na, nb[r]);
+                    if (!(fabs(x - (double)packed_score(p[r])) <= eps)) viol = true;
+                    me[r].k = ord64(x); me[r].j = packed_col(p[r]);
+                }
+            }
+        }
+        K2_T(r1_);
+        K2_ADD(5, r1_ - r0_);
+        // ---- one sort of the candidates by exact cosine (every schema ranks them alike)
+        warp_sort<KPT>(me, lane, n_ca);
+#pragma unroll
+        for (int r = 0; r < KPT; ++r) { w.xk[lane * KPT + r] = me[r].k; w.xj[lane * KPT + r] = me[r].j; }
+        bool ok = true;
+        if (__any_sync(FULL, viol)) {
+            ok = false;
+            if (lane == 0 && A.viol_counter) atomicAdd(A.viol_counter, 1ull);
+        }
+        __syncwarp();
+        K2_T(r2_);
+        K2_ADD(6, r2_ - r1_);
+        // nothing that was not re-scored can have an exact cosine above this
+        const double bound = (double)(n_ca < n_all ? fmaxf(packed_score(w.pk[n_ca]), h.tau_union) : h.tau_union) + eps;
+        // ---- per schema: the same-page entries are merged by counting (finish_row)
+        const int64_t io = i - A.o_row0;
+        const int64_t p0 = off0 - A.pair0;
+        const int n = n_ca + c;
+        const int n_top = n_ca < rp.kmax ? n_ca : rp.kmax;  // candidates that can reach the top-K lists
+        for (int si = 0; si < rp.S; ++si) {
+            const int s = rp.schema[si];
+            double sc_p = 0.0;
+            if (lane < c) {
+                sc_p = ranking_score(rp, s, cosp, lex, pos);
+                if (A.out.pair_score) A.out.pair_score[(int64_t)si * A.P_out + p0 + lane] = sc_p;
+            }
+            w.spk[lane] = ord64(sc_p);
+            __syncwarp();
+            const int64_t o_top = ((int64_t)si * A.o_rows + io) * rp.kmax;
+            bool bad = false, have_kth = false;
+            double kth = -CUDART_INF;
+            for (int t = lane; t < c + n_top; t += 32) {
+                unsigned long long k;
+                int j, at;
+                double sc;
+                if (t < c) {  // a same-page entry: binary search in the sorted candidates, count the other same-page entries
+                    k = w.spk[t]; j = w.spcol[t]; sc = sc_p;
+                    int lo = 0, hi = n_ca;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (key_before(w.xk[mid], w.xj[mid], k, j)) lo = mid + 1; else hi = mid;
+                    }
+                    at = lo;
+                    for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
+                    if (at < rp.kneed) {
+                        bool known = true;  // `at` is the pair's rank ...
+                        if (!(sc > bound)) {  // ... unless a column that was not re-scored may beat it
+                            const int ahead = count_above_packed(w.pk, n_all, sc + eps) - n_ca;
+                            known = false;
+                            if (at + (ahead > 0 ? ahead : 0) < rp.kneed) bad = true;  // else: beyond the cutoff either way
+                        }
+                        if (known && A.out.pair_rank) A.out.pair_rank[(int64_t)si * A.P_out + p0 + t] = at + 1;
+                    }
+                } else {      // a candidate: its sorted position + the same-page entries that beat it
+                    k = w.xk[t - c]; j = w.xj[t - c]; sc = unord64(k);
+                    at = t - c;
+                    for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
+                }
+                if (at < rp.kmax && A.out.topk_idx) {
+                    A.out.topk_idx[o_top + at] = (int64_t)j + rp.col_offset;
+                    A.out.topk_score[o_top + at] = sc;
+                }
+                if (at == rp.kmax - 1) { kth = sc; have_kth = true; }
+            }
+            if (A.out.topk_idx)
+                for (int r = n + lane; r < rp.kmax; r += 32) {  // fewer entries than the lists are wide
+                    A.out.topk_idx[o_top + r] = -1; A.out.topk_score[o_top + r] = -CUDART_INF;
+                }
+            const unsigned hk = __ballot_sync(FULL, have_kth);
+            if (hk) kth = __longlong_as_double(__shfl_sync(FULL, __double_as_longlong(kth), __ffs(hk) - 1));
+            bad = __any_sync(FULL, bad);
+            ok = ok && !bad && (kth > bound);
+            __syncwarp();
+        }
+        K2_T(r3_);
+        K2_ADD(7, r3_ - r2_);
+        K2_ADD(12, 1);
         if (!ok && lane == 0) {
             const int slot = atomicAdd(fail_count, 1);
             fail_rows[slot] = (int32_t)i;
-            if (fail_thr) fail_thr[slot] = thr;
+            if (fail_thr) fail_thr[slot] = h.thr;
         }
     }
-    if (lane == 0 && cand_counter && cand_total) atomicAdd(cand_counter, cand_total);
 }
 
 // ---------------------------------------------------------------------------
@@ -1221,7 +1331,7 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
                            int32_t *cert_count, RowRange range, cudaStream_t st, int64_t grid_limit,
-                           int32_t *big_rows, int32_t *big_count)
+                           int32_t *big_rows, int32_t *big_count, void *k2_scratch)
 {
     if (img.n == 0) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
@@ -1235,24 +1345,32 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     if (e != cudaSuccess) return e;
     int64_t grid = A.n_rows < (int64_t)sm_count() * 16 ? A.n_rows : (int64_t)sm_count() * 16;
     if (grid_limit > 0 && grid > grid_limit) grid = grid_limit;  // (the rows are handed out with a grid stride)
-    // The warp-per-row kernel ranks every row of the common shape; what it hands over (big_count rows) goes through
-    // the block-per-row kernel in row-list mode.  Runs that certify across ranks or return the deep lists, and
-    // same-page mode, are the block kernel's alone.
-    const size_t wsmem = warp_smem_bytes(img.D) * kW2Warps;
-    const bool by_warp = lists && big_rows && big_count && fail_rows && fail_count && !tau_global && !cert_count &&
-                         !out.deep_idx && lists_per_row(L) <= 32 && wsmem * 2 <= 200 * 1024;
+    // The warp-per-row kernels (select, gather, rank) take every row of the common shape; what they hand over
+    // (big_count rows) goes through the block-per-row kernel in row-list mode.  Runs that certify across ranks or
+    // return the deep lists, and same-page mode, are the block kernel's alone.
+    const size_t sm_a = select_smem_bytes(img.D) * kW2Warps, sm_b = gather_smem_bytes(img.D) * kW2Warps,
+                 sm_c = rank_smem_bytes() * kW2Warps;
+    const bool by_warp = lists && k2_scratch && big_rows && big_count && fail_rows && fail_count && !tau_global &&
+                         !cert_count && !out.deep_idx && lists_per_row(L) <= 32 && sm_a * 2 <= 200 * 1024;
     if (by_warp) {
-        e = cudaFuncSetAttribute(rescore_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
-        if (e != cudaSuccess) return e;
-        int per_sm = (int)(200 * 1024 / wsmem);
-        if (per_sm > 4) per_sm = 4;
-        int64_t wgrid = (A.n_rows + kW2Warps - 1) / kW2Warps;
-        if (wgrid > (int64_t)sm_count() * per_sm) wgrid = (int64_t)sm_count() * per_sm;
-        if (grid_limit > 0 && wgrid > grid_limit / 8 * per_sm) wgrid = grid_limit / 8 * per_sm > 0 ? grid_limit / 8 * per_sm : 1;
-        rescore_warp_kernel<<<(unsigned)wgrid, kW2Warps * 32, wsmem, st>>>(A, L, eps_chunk_max, fail_rows, fail_count,
-                                                                          fail_thr, cand_counter, big_rows, big_count);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        const K2Scratch K = carve_scratch(k2_scratch, A.n_rows);
+        auto grid_for = [&](size_t smem_cta, int max_per_sm) {
+            int per_sm = (int)(200 * 1024 / smem_cta);
+            if (per_sm > max_per_sm) per_sm = max_per_sm;
+            int64_t g = (A.n_rows + kW2Warps - 1) / kW2Warps;
+            if (g > (int64_t)sm_count() * per_sm) g = (int64_t)sm_count() * per_sm;
+            if (grid_limit > 0) { const int64_t lim = grid_limit / 8 * per_sm; if (g > lim) g = lim > 0 ? lim : 1; }
+            return (unsigned)g;
+        };
+        if ((e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b)) != cudaSuccess) return e;
+        select_kernel<<<grid_for(sm_a, 8), kW2Warps * 32, sm_a, st>>>(A, L, K, eps_chunk_max, fail_rows, fail_count, fail_thr,
+                                                                   cand_counter, big_rows, big_count);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        gather_kernel<<<grid_for(sm_b, 8), kW2Warps * 32, sm_b, st>>>(A, K);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        rank_kernel<<<grid_for(sm_c, 6), kW2Warps * 32, sm_c, st>>>(A, K, eps_chunk_max, fail_rows, fail_count, fail_thr);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (grid > (int64_t)sm_count() * 2) grid = (int64_t)sm_count() * 2;  // (few rows, if any)
     }
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,

@@ -39,7 +39,7 @@ for rep in range(a.reps):
     names = ["stage row", "same-page entries", "list sweep", "sort approx", "theta", "candidate gathers + cosine", "sort exact",
              "merge + outputs"]
     print(f"rep {rep}: rescore {r['stats']['rescore_us'] / 1e3:.2f} ms; cycles per row (one CTA): " +
-          ", ".join(f"{n} {w[q] / rows_:.0f}" for q, n in enumerate(names)) + f"; total {sum(w[:8]) / rows_:.0f}; sampled rows {w[8]}, handed to the block kernel {w[9]}, union entries per row {w[10] / rows_:.1f}, re-scored {w[11] / rows_:.1f}", flush=True)
+          ", ".join(f"{n} {w[q] / (max(w[12], 1) if q >= 5 and w[12] else rows_):.0f}" for q, n in enumerate(names)) + f"; total {sum(w[:8]) / rows_:.0f}; sampled rows {w[8]}, handed to the block kernel {w[9]}, union entries per row {w[10] / rows_:.1f}, re-scored {w[11] / rows_:.1f}", flush=True)
     v = [int(x) for x in buf]
     tiles, warps = max(v[4], 1), max(v[7], 1)
     us = r["stats"]["fused_us"]
