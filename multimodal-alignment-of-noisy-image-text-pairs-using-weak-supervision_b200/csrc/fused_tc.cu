@@ -875,6 +875,10 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
 #endif
     int need = p.kprime_list + kSlack + kCompactMargin + room;
     if (need > 512) need = p.kprime_list + kSlack + kCompactMargin + 32;
+    // A few slots short of the full room is worth the next smaller capacity (half the keys per lane in every
+    // compaction, half the list memory): 48 slots of room are accepted for it.
+    if (need > 256 && need - room + 48 <= 256) need = 256;
+    if (need > 128 && need - room + 48 <= 128) need = 128;
     if (need <= 128) p.cap = 128;
     else if (need <= 256) p.cap = 256;
     else if (need <= 512) p.cap = 512;

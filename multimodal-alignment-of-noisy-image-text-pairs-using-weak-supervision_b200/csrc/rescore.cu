@@ -664,6 +664,8 @@ struct K2Row {                  // scratch header of a row
     unsigned long long pad;
 };
 struct K2Scratch {
+    int claim;                  // rows a warp claims at a time from the launch's row counters (1 for short launches: no stragglers)
+    unsigned long long *next;   // [3] next unclaimed row of the select / gather / rank kernel (zeroed per launch)
     K2Row *hdr;                 // [rows]
     unsigned long long *pk;     // [rows][256] union, packed, sorted by approximate score (descending)
     float *dotv;                // [rows][256] fp32 dot products of the re-scored candidates, in pk order
@@ -680,7 +682,8 @@ static K2Scratch carve_scratch(void *base, int64_t rows)
     k.pk = reinterpret_cast<unsigned long long *>(p); p += (size_t)rows * kW2Cap * 8;
     k.sp = reinterpret_cast<double *>(p); p += (size_t)rows * 3 * kW2Sp * 8;
     k.hdr = reinterpret_cast<K2Row *>(p); p += (size_t)rows * sizeof(K2Row);
-    k.dotv = reinterpret_cast<float *>(p);
+    k.dotv = reinterpret_cast<float *>(p); p += (size_t)rows * kW2Cap * 4;
+    k.next = reinterpret_cast<unsigned long long *>(p);
     return k;
 }
 
@@ -780,8 +783,13 @@ select_kernel(RowArgs A, CandLists L, K2Scratch K, const float *__restrict__ eps
     const int d4 = A.D >> 2;
     const float eps_chunk = eps_chunk_max[0];
     unsigned long long cand_total = 0ull;
-    const int64_t n_warps = (int64_t)gridDim.x * kW2Warps;
-    for (int64_t b = (int64_t)blockIdx.x * kW2Warps + warp; b < A.n_rows; b += n_warps) {
+    for (;;) {  // rows are claimed a few at a time: their cost varies (40 to 250 gathers), a static split leaves stragglers
+        long long b0 = 0;
+        if (lane == 0) b0 = (long long)atomicAdd(K.next + 0, (unsigned long long)K.claim);
+        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        if (b0 >= A.n_rows) break;
+        const int64_t b_end = b0 + K.claim < A.n_rows ? b0 + K.claim : A.n_rows;
+    for (int64_t b = b0; b < b_end; ++b) {
         const int64_t i = A.row0 + b;
         K2_T(r0_);
         const int64_t off0 = A.offsets[i];
@@ -939,6 +947,7 @@ select_kernel(RowArgs A, CandLists L, K2Scratch K, const float *__restrict__ eps
         K2_ADD(10, n_all);
         K2_ADD(11, h.n_ca);
     }
+    }
     if (lane == 0 && cand_counter && cand_total) atomicAdd(cand_counter, cand_total);
 }
 
@@ -954,8 +963,13 @@ gather_kernel(RowArgs A, K2Scratch K)
     float4 *a = reinterpret_cast<float4 *>(base);
     int32_t *cols = reinterpret_cast<int32_t *>(base + (size_t)A.D * 4);
     const int d4 = A.D >> 2;
-    const int64_t n_warps = (int64_t)gridDim.x * kW2Warps;
-    for (int64_t b = (int64_t)blockIdx.x * kW2Warps + warp; b < A.n_rows; b += n_warps) {
+    for (;;) {  // rows are claimed a few at a time: their cost varies (40 to 250 gathers), a static split leaves stragglers
+        long long b0 = 0;
+        if (lane == 0) b0 = (long long)atomicAdd(K.next + 1, (unsigned long long)K.claim);
+        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        if (b0 >= A.n_rows) break;
+        const int64_t b_end = b0 + K.claim < A.n_rows ? b0 + K.claim : A.n_rows;
+    for (int64_t b = b0; b < b_end; ++b) {
         const K2Row h = K.hdr[b];
         if (h.state != 0 || h.n_ca == 0) continue;
         const int64_t i = A.row0 + b;
@@ -979,6 +993,7 @@ gather_kernel(RowArgs A, K2Scratch K)
                 if (e_w < h.n_ca) dst[e_w] = keep;
             }
         }
+    }
     }
 }
 
@@ -1005,8 +1020,13 @@ rank_kernel(RowArgs A, K2Scratch K, const float *__restrict__ eps_chunk_max, int
     }
     const RunParams &rp = A.rp;
     const float eps_chunk = eps_chunk_max[0];
-    const int64_t n_warps = (int64_t)gridDim.x * kW2Warps;
-    for (int64_t b = (int64_t)blockIdx.x * kW2Warps + warp; b < A.n_rows; b += n_warps) {
+    for (;;) {  // rows are claimed a few at a time: their cost varies (40 to 250 gathers), a static split leaves stragglers
+        long long b0 = 0;
+        if (lane == 0) b0 = (long long)atomicAdd(K.next + 2, (unsigned long long)K.claim);
+        b0 = __shfl_sync(0xFFFFFFFFu, b0, 0);
+        if (b0 >= A.n_rows) break;
+        const int64_t b_end = b0 + K.claim < A.n_rows ? b0 + K.claim : A.n_rows;
+    for (int64_t b = b0; b < b_end; ++b) {
         const K2Row h = K.hdr[b];
         if (h.state != 0) continue;
         K2_T(r0_);
@@ -1145,6 +1165,7 @@ rank_kernel(RowArgs A, K2Scratch K, const float *__restrict__ eps_chunk_max, int
             fail_rows[slot] = (int32_t)i;
             if (fail_thr) fail_thr[slot] = h.thr;
         }
+    }
     }
 }
 
@@ -1353,7 +1374,9 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
     const bool by_warp = lists && k2_scratch && big_rows && big_count && fail_rows && fail_count && !tau_global &&
                          !cert_count && !out.deep_idx && lists_per_row(L) <= 32 && sm_a * 2 <= 200 * 1024;
     if (by_warp) {
-        const K2Scratch K = carve_scratch(k2_scratch, A.n_rows);
+        K2Scratch K = carve_scratch(k2_scratch, A.n_rows);
+        K.claim = A.n_rows >= (int64_t)sm_count() * 32 * 64 ? 4 : 1;
+        if ((e = cudaMemsetAsync(K.next, 0, 3 * sizeof(unsigned long long), st)) != cudaSuccess) return e;
         auto grid_for = [&](size_t smem_cta, int max_per_sm) {
             int per_sm = (int)(200 * 1024 / smem_cta);
             if (per_sm > max_per_sm) per_sm = max_per_sm;
