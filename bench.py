@@ -539,7 +539,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel, timed with CUDA events inside the library
-    other = {"rescore_kernel": float(np.mean(resc_us)) / 1e3, "exact_scan_kernel": float(np.mean(scan_us)) / 1e3}
+    # (in `all` mode the rescoring is three kernels -- select_kernel, gather_kernel, rank_kernel -- plus rescore_kernel
+    # for the rows they hand over; in same-page mode rescore_kernel alone)
+    t_resc_ms = float(np.mean(resc_us)) / 1e3
+    other = {"rescore_kernel": t_resc_ms, "exact_scan_kernel": float(np.mean(scan_us)) / 1e3}
+    if fused_path and t_resc_ms > 0:
+        gathered = res["stats"]["candidates_rescored"] * D * 4.0  # algorithmic bytes of the rescoring: one fp32 row per re-scored candidate
+        other["rescoring_gather_GBps"] = gathered / t_resc_ms / 1e6
+        other["rescoring_frac_of_hbm"] = gathered / t_resc_ms / 1e6 / P["hbm"]
     if fused_path:
         t_fused = float(np.mean(fused_us)) * 1e-6
         flops_launch = 2.0 * N * (r1 - r0) * D  # algorithmic: 2*M_local*D per query x N queries

@@ -313,6 +313,12 @@ int mmalign_debug_scores(mmalign_ctx *ctx, float *out, void *stream);
 /* validation hook: the bf16 operands K0 prepared (L2-normalised rows, rounded to nearest even), [N][D] and
  * [m_local][D] 16-bit values; either may be NULL; host or device pointers. */
 int mmalign_debug_operands(mmalign_ctx *ctx, void *img_bf16, void *chk_bf16, void *stream);
+/* validation hook: the checked build of the library (csrc/Makefile `make check`: every kernel tests its own
+ * indices and invariants -- list capacities, shared-memory slots, chunk columns, output positions) reports what it
+ * saw since the process started.  out[9]: out[0] = 1 for a checked build, 0 for the release build (which compiles
+ * the checks out and reports zeros); then {violations, first failing source line} for fused_tc.cu, rescore.cu,
+ * prep.cu, ingest.cu.  Synchronises the device. */
+int mmalign_check_report(uint32_t *out);
 
 #ifdef __cplusplus
 }

@@ -42,7 +42,8 @@ EXPORTS = ["mmalign_abi_version", "mmalign_create", "mmalign_destroy", "mmalign_
            "mmalign_rescore_pass", "mmalign_rescan_rows", "mmalign_list_stride", "mmalign_export_lists",
            "mmalign_rescore_slab", "mmalign_num_pairs_range", "mmalign_term_bitsets", "mmalign_sync",
            "mmalign_prep_rows", "mmalign_set_chunks_prepared", "mmalign_rescore_after", "mmalign_debug_operands", "mmalign_set_option",
-           "mmalign_set_images_half", "mmalign_set_chunks_half", "mmalign_copy_scan", "mmalign_copy_decode"]
+           "mmalign_set_images_half", "mmalign_set_chunks_half", "mmalign_copy_scan", "mmalign_copy_decode",
+           "mmalign_check_report"]
 ABI_VERSION = 3
 
 _lib = None
@@ -109,6 +110,7 @@ def load():
     L.mmalign_copy_scan.argtypes = [vp, i64, i32, vp, vp, i64]
     L.mmalign_copy_scan.restype = C.c_int64
     L.mmalign_copy_decode.argtypes = [vp, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp]
+    L.mmalign_check_report.argtypes = [C.POINTER(C.c_uint32)]
     for name in EXPORTS:
         getattr(L, name)
         if name not in ("mmalign_destroy", "mmalign_last_error", "mmalign_abi_version", "mmalign_copy_scan"):
@@ -117,3 +119,14 @@ def load():
         raise RuntimeError(f"{path} has ABI version {L.mmalign_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
     _lib = L
     return L
+
+
+def check_report():
+    """mmalign_check_report: dict(checked=bool, violations={file: (count, first line)}).  `checked` is True only for
+    the checked build of the library (csrc/Makefile `make check`, selected with MMALIGN_LIB)."""
+    out = (C.c_uint32 * 9)()
+    rc = load().mmalign_check_report(out)
+    if rc != 0:
+        raise RuntimeError(f"mmalign_check_report failed with {rc}")
+    files = ("fused_tc.cu", "rescore.cu", "prep.cu", "ingest.cu")
+    return dict(checked=bool(out[0]), violations={f: (int(out[1 + 2 * q]), int(out[2 + 2 * q])) for q, f in enumerate(files)})

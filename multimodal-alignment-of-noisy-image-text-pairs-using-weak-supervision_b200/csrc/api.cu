@@ -1055,15 +1055,16 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
             }
             CU(c, cudaEventRecord(ev[4], sk2));
             int32_t *fail_rows = (int32_t *)c->fail_rows.p + r0;
+            long long k2_launched = 0;
             pre.thr = (unsigned long long *)c->fail_thr.p + r0; pre.buf = c->scan_buf.p; pre.cnt = (int32_t *)c->scan_cnt.p;
             // beside the next slab's contraction the rescoring gets the SMs that were left free: 8 CTAs on each
             const int64_t k2_grid = overlap && s + 1 < n_slabs ? (int64_t)(c->sm_count - k1_sms) * 8 : 0;
             CU(c, launch_rescore(img, chk, c->px, rp, &L, c->chk.err_max, out, fail_rows, slab_fail + s, pre.thr,
                                  cand_counter, error_flag, nullptr, nullptr, range, sk2, k2_grid,
-                                 (int32_t *)c->big_rows.p + r0, slab_big + s, c->k2_scratch.p));
+                                 (int32_t *)c->big_rows.p + r0, slab_big + s, c->k2_scratch.p, &k2_launched));
             CU(c, cudaEventRecord(ev[2], sk2));
             CU(c, launch_exact_scan(img, chk, c->px, rp, fail_rows, slab_fail + s, 0, out, error_flag, range, &pre, sk2));
-            launches += 3;
+            launches += k2_launched + 2;  // + the two stages of the exact scan
         }
         CU(c, cudaEventRecord(ev[3], fused_path ? sk2 : st));
     }
@@ -1128,6 +1129,27 @@ static int run_impl(mmalign_ctx *c, const mmalign_params *prm, mmalign_out *uo, 
         CU(c, cudaMemcpy(uo->stats, stats, sizeof stats, cudaMemcpyDefault));
     }
     tr.mark("status");
+    return MMALIGN_OK;
+}
+
+// Checked build only (make check): out[0] = 1, then {violations, first failing line} of fused_tc.cu, rescore.cu,
+// prep.cu, ingest.cu.  The release build reports out[0] = 0 and zeros.
+extern "C" int mmalign_check_report(uint32_t *out)
+{
+    if (!out) return MMALIGN_EINVAL;
+#ifdef MMALIGN_CHECKED
+    out[0] = 1u;
+#else
+    out[0] = 0u;
+#endif
+    out[1] = out[2] = out[3] = out[4] = out[5] = out[6] = out[7] = out[8] = 0u;
+    if (cudaDeviceSynchronize() != cudaSuccess) return MMALIGN_EDEVICE;
+    unsigned int w[2];
+    int (*readers[4])(unsigned int *) = {check_read_fused, check_read_rescore, check_read_prep, check_read_ingest};
+    for (int q = 0; q < 4; ++q) {
+        if (readers[q](w) != 0) return MMALIGN_EDEVICE;
+        out[1 + 2 * q] = w[0]; out[2 + 2 * q] = w[1];
+    }
     return MMALIGN_OK;
 }
 

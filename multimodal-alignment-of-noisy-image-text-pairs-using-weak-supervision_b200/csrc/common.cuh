@@ -11,7 +11,28 @@
 #include <vector>
 #include "../../include/mmalign.h"
 
+// ---------------------------------------------------------------------------
+// Checked build (make check -> libmmalign_check.so, run with MMALIGN_LIB=...): the kernels test their own indices
+// and invariants -- list capacities, shared-memory slots, chunk columns, output positions -- and count violations
+// per source file (first failing line kept).  compute-sanitizer is not available on the GPU pool this is developed
+// on; this is its stand-in, run over the whole -m gpu suite (profiles/sanitizer/).  Compiled out of the release build.
+// ---------------------------------------------------------------------------
+#ifdef MMALIGN_CHECKED
+#define MMA_CHECK_DECL static __device__ unsigned int g_chk_fail[2];
+#define MMA_CHECK(cond) do { if (!(cond)) { if (atomicAdd(&g_chk_fail[0], 1u) == 0u) g_chk_fail[1] = __LINE__; } } while (0)
+#define MMA_CHECK_READER(name) int name(unsigned int *out) { return (int)cudaMemcpyFromSymbol(out, g_chk_fail, sizeof(g_chk_fail)); }
+#else
+#define MMA_CHECK_DECL
+#define MMA_CHECK(cond) do { } while (0)
+#define MMA_CHECK_READER(name) int name(unsigned int *out) { out[0] = out[1] = 0u; return 0; }
+#endif
+
 namespace mma {
+
+int check_read_fused(unsigned int *out);    // {violations, first failing line} of fused_tc.cu
+int check_read_rescore(unsigned int *out);  // ... of rescore.cu
+int check_read_prep(unsigned int *out);     // ... of prep.cu
+int check_read_ingest(unsigned int *out);   // ... of ingest.cu
 
 constexpr int kMaxSchemas = 4;
 constexpr int kMaxK = 8;
@@ -303,7 +324,8 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
                            int32_t *cert_count, RowRange rows, cudaStream_t st, int64_t grid_limit = 0,
                            int32_t *big_rows = nullptr, int32_t *big_count = nullptr,  // scratch of the warp-per-row kernels: [rows], [1] zeroed,
-                           void *k2_scratch = nullptr);                                 // and k2_scratch_bytes(rows)
+                           void *k2_scratch = nullptr,                                  // and k2_scratch_bytes(rows)
+                           long long *n_launches = nullptr);                            // kernels this call launched
 size_t k2_scratch_bytes(int64_t rows);
 // scratch of the two-stage exact scan: per failed row (slot) its threshold, and what stage 1 kept for it
 constexpr int kScanSlots = 2048, kScanCap = 1024;

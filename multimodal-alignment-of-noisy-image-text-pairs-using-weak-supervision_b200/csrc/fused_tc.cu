@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 namespace mma {
+MMA_CHECK_DECL
 
 constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kFusedThreads = 384;
@@ -201,7 +202,14 @@ struct FusedArgs {
     int skip_final;        // tuning builds: no end-of-unit compaction
     uint32_t col_base;     // added to the column index of every entry (a launch over a column group of the table)
     uint32_t epi_sleep_ns; // the epilogue warps poll their accumulator barrier this many ns apart (0 = spin)
+    int diag;              // tuning builds (-DMMALIGN_TUNING, MMALIGN_K1_DIAG): 1 = the epilogue hands every accumulator back
+                           // unread, 2 = no operand loads after the ring's first fill; always 0 in the release build
 };
+#ifdef MMALIGN_TUNING
+#define K1_DIAG(bit) ((P.diag & (bit)) != 0)
+#else
+#define K1_DIAG(bit) false
+#endif
 
 // ---------------------------------------------------------------------------
 // Candidate lists.  An entry is 8 bytes: lo = chunk column, hi = fp32 score bits.
@@ -223,6 +231,7 @@ __device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, i
         const int src = __ffs(pending) - 1;
         pending &= pending - 1;
         const int cnt = __shfl_sync(0xFFFFFFFFu, n, src);
+        MMA_CHECK(cnt >= 0 && cnt <= CAP);  // a list never holds more than its capacity
         uint2 *L = reinterpret_cast<uint2 *>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_list), src));
         __syncwarp();
         uint32_t h[KPL], c[KPL];  // ordered score key, column
@@ -262,6 +271,7 @@ __device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, i
             base += __popc(m);
         }
         __syncwarp();
+        MMA_CHECK(base <= cnt && base <= CAP);
         if (lane == src) { n = base; tau = fmaxf(tau, f32_unordered(t)); }
     }
 }
@@ -331,6 +341,7 @@ __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t
             }
         }
         n = (int)(wp - list);
+        MMA_CHECK(n >= 0 && n <= CAP);  // 32 appends at most, behind a compaction that left 32 slots free
         EPI_T(p2_);
         EPI_ADD(11, p2_ - p1_);  // the hit path
     }
@@ -402,10 +413,14 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1u);
                         const uint32_t dst = sStage + stage * stage_bytes;
-                        mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
-                        tma_load_2d(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN));
-                        if (!A_RES)
-                            tma_load_2d(dst + kBStageBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
+                        if (K1_DIAG(2) && (t > t0 || kb >= P.stages || u != (int64_t)blockIdx.x)) {  // (diagnosis: the MMAs re-read what the ring holds)
+                            mbar_arrive(bar_full + 8u * stage);
+                        } else {
+                            mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
+                            tma_load_2d(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN));
+                            if (!A_RES)
+                                tma_load_2d(dst + kBStageBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
+                        }
                         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -474,7 +489,11 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
-                if (P.dump) {
+                if (K1_DIAG(1)) {  // (diagnosis: the contraction alone)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+                } else if (P.dump) {
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t v[32];
@@ -542,6 +561,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     compact_lists<KPL>(list, n, tau, P.kprime, n > P.kprime + kSlack);
             }
             if (!P.dump) {
+                MMA_CHECK(list_id >= 0 && list_id < P.n_row_blocks * P.n_splits * 256 && n <= CAP);
                 P.tau[list_id] = tau;
                 P.count[list_id] = n;
             }
@@ -689,10 +709,14 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1u);
                         const uint32_t dst = sStage + stage * stage_bytes;
-                        if (leader) mbar_expect_tx(bar_full + 8u * stage, 2u * stage_bytes);
-                        tma_load_2d_pair(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN + rank * (BN / 2)));
-                        if (!A_RES)
-                            tma_load_2d_pair(dst + kBHalfBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
+                        if (K1_DIAG(2) && (t > t0 || kb >= P.stages || u != cluster_id)) {  // (diagnosis: the MMAs re-read what the ring holds)
+                            if (leader) mbar_arrive(bar_full + 8u * stage);
+                        } else {
+                            if (leader) mbar_expect_tx(bar_full + 8u * stage, 2u * stage_bytes);
+                            tma_load_2d_pair(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN + rank * (BN / 2)));
+                            if (!A_RES)
+                                tma_load_2d_pair(dst + kBHalfBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
+                        }
                         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -757,7 +781,11 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
-                if (P.dump) {
+                if (K1_DIAG(1)) {  // (diagnosis: the contraction alone)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);
+                } else if (P.dump) {
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
                         uint32_t v[32];
@@ -805,6 +833,7 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                     compact_lists<KPL>(list, n, tau, P.kprime, n > P.kprime + kSlack);
             }
             if (!P.dump) {
+                MMA_CHECK(list_id >= 0 && list_id < P.n_row_blocks * P.n_splits * 256 && n <= CAP);
                 P.tau[list_id] = tau;
                 P.count[list_id] = n;
             }
@@ -979,6 +1008,7 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
 #ifdef MMALIGN_TUNING
     if (const char *e = getenv("MMALIGN_TAU_INIT")) a.tau_init = (float)atof(e);
     a.skip_final = getenv("MMALIGN_SKIP_FINAL") != nullptr;
+    if (const char *e = getenv("MMALIGN_K1_DIAG")) a.diag = atoi(e);
 #endif
     a.col_base = (uint32_t)col_base;
     a.epi_sleep_ns = (uint32_t)plan.epi_sleep_ns;
@@ -999,5 +1029,7 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
 #undef VARIANT
     return cudaErrorInvalidValue;
 }
+
+MMA_CHECK_READER(check_read_fused)
 
 } // namespace mma

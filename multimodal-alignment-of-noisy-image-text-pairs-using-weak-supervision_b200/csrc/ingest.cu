@@ -21,6 +21,7 @@
 #include <vector>
 
 namespace mma {
+MMA_CHECK_DECL
 
 constexpr int kIngestThreads = 256;
 constexpr int kIngestWarps = kIngestThreads / 32;
@@ -314,5 +315,7 @@ cudaError_t launch_widen_rows(const void *src, int dtype, int64_t count, float *
     else widen_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16 *>(src), count, dst);
     return cudaGetLastError();
 }
+
+MMA_CHECK_READER(check_read_ingest)
 
 } // namespace mma

@@ -13,6 +13,7 @@
 #include <cub/device/device_scan.cuh>
 
 namespace mma {
+MMA_CHECK_DECL
 
 // SM count of the current device (grids are sized in multiples of it); cached per device
 int sm_count()
@@ -133,6 +134,7 @@ __global__ void page_range_kernel(const uint64_t *__restrict__ img_key, int64_t 
             if (sorted_key[mid] <= k) lo = mid + 1; else hi = mid;
         }
         sp_start[i] = first;
+        MMA_CHECK(first >= 0 && first <= lo && lo <= M);
         const int64_t cnt = (k == MMALIGN_NULL_KEY) ? 0 : lo - first;  // SQL NULL never joins
         counts[i] = cnt;
         if (cnt > 0) atomicMax(c_max, (unsigned long long)cnt);
@@ -182,5 +184,7 @@ cudaError_t build_pair_index(const Side &img, const Side &chk, PairIndex &px, vo
 #undef CK
     return cudaSuccess;
 }
+
+MMA_CHECK_READER(check_read_prep)
 
 } // namespace mma

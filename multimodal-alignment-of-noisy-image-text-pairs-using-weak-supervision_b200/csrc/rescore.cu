@@ -20,6 +20,7 @@
 #include <math_constants.h>
 
 namespace mma {
+MMA_CHECK_DECL
 
 #ifdef MMALIGN_PROFILE_EPI   // the profiling build (make prof): where the rescoring kernel's CTAs spend their cycles
 __device__ unsigned long long g_k2_prof[16];
@@ -428,6 +429,7 @@ __device__ bool finish_row(const RowArgs &A, const RowSmem &sm, int64_t i, int n
                 pos = t - c;
                 for (int q = 0; q < c; ++q) pos += key_before(sm.sp_k[q], sm.cols[q], k, j);
             }
+            MMA_CHECK(pos >= 0 && pos < n && n <= A.ent_cap && j >= 0 && j < A.M && io >= 0 && io < A.o_rows);
             if (pos < rp.kmax && A.out.topk_idx) {
                 A.out.topk_idx[o_top + pos] = (int64_t)j + rp.col_offset;
                 A.out.topk_score[o_top + pos] = sc;
@@ -569,6 +571,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
                         const uint64_t k = keys[e];
                         const uint32_t col = cand_col(k);
                         const float sa = cand_score(k);
+                        MMA_CHECK((int64_t)col < A.M);
                         bool same_page = false;  // same-page chunks enter through the pair index, not through the lists
                         if (ik != MMALIGN_NULL_KEY) {
                             if (c <= 32) { for (int q = 0; q < c; ++q) same_page = same_page || sm.sp_cols[q] == (int32_t)col; }
@@ -655,6 +658,7 @@ rescore_kernel(RowArgs A, CandLists L, bool use_lists, const float *eps_chunk_ma
 constexpr int kW2Warps = 4;     // warps (= rows in flight) per CTA
 constexpr int kW2Cap = 256;     // union entries per row
 constexpr int kW2Sp = 32;       // same-page chunks per row: one per lane
+constexpr int kW2Keep = 208;    // what a union that outgrows kW2Cap is cut back to (>= the default depth K' = 192)
 
 struct K2Row {                  // scratch header of a row
     int32_t n_all, n_ca;        // union entries above tau_union; re-scored candidates
@@ -844,32 +848,47 @@ select_kernel(RowArgs A, CandLists L, K2Scratch K, const float *__restrict__ eps
         K2_T(r2_);
         K2_ADD(1, r2_ - r1_);
         const bool ok = tau_union != CUDART_INF_F;
-        // ---- sweep of the lists: entries above tau_union that are not same-page (those enter through the pair index)
+        // ---- sweep of the lists: entries above tau_union that are not same-page (those enter through the pair index).
+        // A union that outgrows the 256 slots (many lists per row: column groups, column splits of a remainder launch,
+        // lists imported from other ranks) is cut back to its best kW2Keep entries and the completeness threshold
+        // rises to the last kept score -- the union stays complete above it, which is all the certificate needs, as
+        // long as the depth the lists were planned for (L.kprime) fits; deeper plans go to the block-per-row kernel.
         int n_all = 0;
         if (!big && ok) {
+            const bool may_cut = L.kprime > 0 && L.kprime <= kW2Keep;
             for (int l = 0; l < n_l; ++l) {
                 const int cnt = __shfl_sync(FULL, v.cnt, l);
                 const uint64_t *keys = reinterpret_cast<const uint64_t *>(__shfl_sync(FULL, (unsigned long long)v.keys, l));
-                for (int e0 = 0; e0 < cnt; e0 += 128) {
-                    uint64_t kk[4];
+                // four batches of 32 entries in flight, one copy of the loop body
+                uint64_t k0 = lane < cnt ? __ldg(keys + lane) : 0ull, k1 = lane + 32 < cnt ? __ldg(keys + lane + 32) : 0ull;
+                uint64_t k2 = lane + 64 < cnt ? __ldg(keys + lane + 64) : 0ull, k3 = lane + 96 < cnt ? __ldg(keys + lane + 96) : 0ull;
+#pragma unroll 1
+                for (int e0 = 0; e0 < cnt; e0 += 32) {
+                    const int e = e0 + lane;
+                    const uint64_t k4 = e + 128 < cnt ? __ldg(keys + e + 128) : 0ull;
+                    if (may_cut && n_all > kW2Cap - 32) {  // (uniform)
+                        __syncwarp();
+                        unsigned long long me[8];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int e = e0 + 32 * u + lane;
-                        kk[u] = e < cnt ? __ldg(keys + e) : 0ull;
-                    }
+                        for (int r = 0; r < 8; ++r) me[r] = lane * 8 + r < n_all ? w.pk[lane * 8 + r] : 0ull;
+                        __syncwarp();
+                        warp_sort<8>(me, lane, n_all);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (e0 + 32 * u >= cnt) break;
-                        const int e = e0 + 32 * u + lane;
-                        const uint32_t col = cand_col(kk[u]);
-                        const float sa = cand_score(kk[u]);
-                        bool keep = e < cnt && sa > tau_union;
-                        if (keep) for (int q = 0; q < c; ++q) keep = keep && w.spcol[q] != (int32_t)col;
-                        const unsigned m = __ballot_sync(FULL, keep);
-                        const int at = n_all + __popc(m & lt_mask);
-                        if (keep && at < kW2Cap) w.pk[at] = pack_approx(sa, col);
-                        n_all += __popc(m);
+                        for (int r = 0; r < 8; ++r) w.pk[lane * 8 + r] = me[r];
+                        __syncwarp();
+                        tau_union = fmaxf(tau_union, packed_score(w.pk[kW2Keep - 1]));
+                        n_all = kW2Keep;
                     }
+                    const uint32_t col = cand_col(k0);
+                    const float sa = cand_score(k0);
+                    MMA_CHECK(e >= cnt || (int64_t)col < A.M);  // a list entry names a chunk of the table
+                    bool keep = e < cnt && sa > tau_union;
+                    if (keep) for (int q = 0; q < c; ++q) keep = keep && w.spcol[q] != (int32_t)col;
+                    const unsigned m = __ballot_sync(FULL, keep);
+                    const int at = n_all + __popc(m & lt_mask);
+                    if (keep && at < kW2Cap) w.pk[at] = pack_approx(sa, col);
+                    n_all += __popc(m);
+                    k0 = k1; k1 = k2; k2 = k3; k3 = k4;
                 }
             }
             big = n_all > kW2Cap;
@@ -935,6 +954,7 @@ select_kernel(RowArgs A, CandLists L, K2Scratch K, const float *__restrict__ eps
             }
             h.n_ca = lo;
         }
+        MMA_CHECK(h.n_ca >= 0 && h.n_ca <= n_all && n_all <= kW2Cap && c <= kW2Sp && b >= 0 && b < A.n_rows);
         if (lane == 0) K.hdr[b] = h;
         if (lane < c) {
             double *sp = K.sp + b * (3 * kW2Sp);
@@ -983,6 +1003,7 @@ gather_kernel(RowArgs A, K2Scratch K)
         float keep = 0.f;  // lane l keeps the dot products of entries l, l + 32, ...: one coalesced store per 32
         for (int e = 0; e < h.n_ca; e += 2) {
             const int c0 = cols[e], c1 = cols[e + 1 < h.n_ca ? e + 1 : e];
+            MMA_CHECK(h.n_ca <= kW2Cap && c0 >= 0 && c0 < A.M && c1 >= 0 && c1 < A.M);
             float d0, d1;
             warp_dot2(a, reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)c0 * A.D),
                       reinterpret_cast<const float4 *>(A.chk_emb + (int64_t)c1 * A.D), d4, lane, d0, d1);
@@ -1029,6 +1050,7 @@ rank_kernel(RowArgs A, K2Scratch K, const float *__restrict__ eps_chunk_max, int
     for (int64_t b = b0; b < b_end; ++b) {
         const K2Row h = K.hdr[b];
         if (h.state != 0) continue;
+        MMA_CHECK(h.n_ca >= 0 && h.n_ca <= h.n_all && h.n_all <= kW2Cap);
         K2_T(r0_);
         const int64_t i = A.row0 + b;
         const int n_all = h.n_all, n_ca = h.n_ca;
@@ -1141,6 +1163,8 @@ rank_kernel(RowArgs A, K2Scratch K, const float *__restrict__ eps_chunk_max, int
                     at = t - c;
                     for (int q = 0; q < c; ++q) at += key_before(w.spk[q], w.spcol[q], k, j);
                 }
+                MMA_CHECK(at >= 0 && at < n && j >= 0 && j < A.M && io >= 0 && io < A.o_rows &&
+                          (t >= c || (p0 + t >= 0 && p0 + t < A.P_out)));
                 if (at < rp.kmax && A.out.topk_idx) {
                     A.out.topk_idx[o_top + at] = (int64_t)j + rp.col_offset;
                     A.out.topk_score[o_top + at] = sc;
@@ -1284,6 +1308,7 @@ exact_scan_kernel(RowArgs A, const int32_t *rows, const int32_t *n_rows_dev, int
                     if (key_before(k, (int)j, thr, thr_j)) {
                         const int pos = atomicAdd(&s_cnt, 1);
                         Key x; x.k = k; x.j = (int32_t)j; x.e = 0;
+                        MMA_CHECK(pos >= 0 && pos < A.ent_cap);  // (a round adds at most kScanRound entries behind the shrink)
                         sm.buf[pos] = x;
                     }
                 }
@@ -1352,8 +1377,9 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
                            int32_t *fail_rows, int32_t *fail_count, unsigned long long *fail_thr,
                            unsigned long long *cand_counter, int32_t *error_flag, const float *tau_global,
                            int32_t *cert_count, RowRange range, cudaStream_t st, int64_t grid_limit,
-                           int32_t *big_rows, int32_t *big_count, void *k2_scratch)
+                           int32_t *big_rows, int32_t *big_count, void *k2_scratch, long long *n_launches)
 {
+    if (n_launches) *n_launches = 0;
     if (img.n == 0) return cudaSuccess;
     RowArgs A = make_args(img, chk, px, rp, out, error_flag, &range);
     if (A.n_rows == 0) return cudaSuccess;
@@ -1395,7 +1421,9 @@ cudaError_t launch_rescore(const Side &img, const Side &chk, const PairIndex &px
         rank_kernel<<<grid_for(sm_c, 6), kW2Warps * 32, sm_c, st>>>(A, K, eps_chunk_max, fail_rows, fail_count, fail_thr);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if (grid > (int64_t)sm_count() * 2) grid = (int64_t)sm_count() * 2;  // (few rows, if any)
+        if (n_launches) *n_launches += 3;
     }
+    if (n_launches) *n_launches += 1;
     rescore_kernel<<<(unsigned)grid, kThreads, smem, st>>>(A, L, lists != nullptr, eps_chunk_max, fail_rows,
                                                            fail_count, fail_thr, cand_counter, tau_global, cert_count,
                                                            by_warp ? big_rows : nullptr, by_warp ? big_count : nullptr);
@@ -1520,6 +1548,7 @@ __global__ void export_lists_kernel(CandLists L, int64_t N, int64_t total_rows, 
                     if (e < v.cnt) { k = v.keys[e]; keep = cand_score(k) > t; }
                     const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
                     const int pos = n + __popc(m & lt_mask);
+                    MMA_CHECK(e >= v.cnt || (int64_t)cand_col(k) + col_offset >= 0);
                     if (keep && pos < stride)
                         dst[pos] = (k & 0xFFFFFFFF00000000ull) | (uint64_t)((int64_t)cand_col(k) + col_offset);
                     n += __popc(m);
@@ -1744,5 +1773,7 @@ cudaError_t launch_count_beating(const int64_t *deep_idx, const double *deep_sco
                                                          q_score, counts);
     return cudaGetLastError();
 }
+
+MMA_CHECK_READER(check_read_rescore)
 
 } // namespace mma

@@ -72,3 +72,29 @@ def random_texts_and_terms(rng, m, T):
     terms[5] = "a" * 200                           # longer than every text
     texts[0] = ""
     return texts, terms
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """A run against the checked build of the library (MMALIGN_LIB=.../libmmalign_check.so: every kernel tests its own
+    indices and invariants) ends with its report: one line on stdout and in gpurun_out/, and a failing exit status if
+    any check fired."""
+    import os
+    if "check" not in os.path.basename(os.environ.get("MMALIGN_LIB", "")):
+        return
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return
+        rep = importlib.import_module(PKG_NAME + "._native").check_report()
+    except Exception as e:  # noqa: BLE001 -- the report must not mask the suite's own result
+        print(f"\nchecked build: no report ({e})")
+        return
+    bad = {f: v for f, v in rep["violations"].items() if v[0]}
+    line = (f"checked build: checked={rep['checked']}, tests exit status {int(exitstatus)}, "
+            f"violations {rep['violations']}")
+    print("\n" + line)
+    out = ROOT / "gpurun_out"
+    if out.is_dir():
+        (out / "checked_build_report.txt").write_text(line + "\n")
+    if rep["checked"] and bad and session.exitstatus == 0:
+        session.exitstatus = 1

@@ -595,6 +595,45 @@ def test_page_with_512_chunks_is_the_limit(oracle, eng, synthetic, pkg, cand):
     assert e.value.code == -5 and "512 same-page chunks" in str(e.value)
 
 
+@pytest.mark.parametrize("pipeline_rows,kprime", [(0, 0), (256, 0), (256, 300)])
+def test_rows_of_both_rescoring_kernels_in_one_launch(oracle, eng, synthetic, pipeline_rows, kprime):
+    """The warp-per-row kernels (select / gather / rank) rank rows with at most 32 same-page chunks and a union of at
+    most 256 candidates; the others are handed to the block-per-row kernel through a row list.  Here both kinds sit
+    in the same launch: every third image is on a page of 33-60 chunks, the rest on pages of one to eight, some have
+    no page at all; K' = 300 additionally pushes unions past 256 entries; several pipeline slabs offset the row lists."""
+    N, M, D = 700, 6000, 128
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=64, seed=33)
+    key = lambda manual, page: np.uint64((manual << 32) | page)
+    rng = np.random.default_rng(5)
+    pos, page = 0, 0
+    while pos < M:                                                   # chunk pages of 1..8 rows, every fifth one of 33..60
+        page += 1
+        n = int(rng.integers(33, 61)) if page % 5 == 0 else int(rng.integers(1, 9))
+        chk["key"][pos:pos + n] = key(page // 50, page)
+        pos += n
+    crowded = [p for p in range(1, page + 1) if p % 5 == 0]
+    light = [p for p in range(1, page + 1) if p % 5 != 0]
+    for i in range(N):
+        p = crowded[i % len(crowded)] if i % 3 == 0 else light[(7 * i) % len(light)]
+        img["key"][i] = np.uint64(0xFFFFFFFFFFFFFFFF) if i % 41 == 0 else key(p // 50, p)
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 5, 10, 20), cutoff=100,
+                             kprime=kprime, pipeline_rows=pipeline_rows)
+    assert r["stats"]["fused_launches"] >= 1
+    off, _ = eng.pairs()
+    c = np.diff(off)
+    assert (c > 32).sum() > 100 and ((c > 0) & (c <= 32)).sum() > 100 and (c == 0).sum() > 5
+
+
+@pytest.mark.parametrize("N,M,D", [(1900, 40000, 128), (2500, 60000, 64)])
+def test_unions_wider_than_the_warp_kernels_are_cut_back(oracle, eng, synthetic, N, M, D):
+    """Few row blocks against many columns: the fused kernel splits the columns ~10 ways to fill the GPU, a row then has
+    ~20 lists and their union above the completeness threshold outgrows the 256 slots of the warp-per-row rescoring,
+    which cuts it back to its best 208 entries and raises the threshold (select_kernel).  Exact all the same."""
+    img, chk, _ = synthetic.make_numpy(N, M, D, T=64, seed=61)
+    r = check_against_oracle(oracle, eng, img, chk, 64, candidates="all", lam=(0.3, 0.2), ks=(1, 5, 10, 20), cutoff=100)
+    assert r["stats"]["fused_launches"] >= 1
+
+
 def test_widest_lists_k256_and_cutoff256(oracle, eng, synthetic, pkg):
     """Kmax = mrr_cutoff = 256 (the documented maximum): K' = 491."""
     img, chk, _ = synthetic.make_numpy(300, 6000, 64, T=64, seed=23)

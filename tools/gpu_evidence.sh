@@ -21,7 +21,7 @@ san() {  # san <tool> <limit seconds> <pytest -k expression>
     tail -4 $log
 }
 
-if [ "$what" = all ] || [ "$what" = sanitizer ]; then
+if [ "$what" = sanitizer ]; then  # (compute-sanitizer is closed on this pool: exit code 86; kept for pools that have it)
     # memcheck: every kernel family at test size -- the three list widths (<4,.> <8,.> <16,.>), A resident (D <= 512)
     # and streamed (D = 768, 1024), CTA pairs, the slab pipeline with host pieces, the exact scan stages, ingest,
     # half-precision rows, COPY decode, the sharded passes
@@ -32,15 +32,24 @@ if [ "$what" = all ] || [ "$what" = sanitizer ]; then
     san initcheck 600 "(fused_path_matches_oracle and (1000-5000-512 or 200-3000-1024)) or (slab_pipeline_matches_oracle and device and all) or term_bitsets_golden"
 fi
 
+if [ "$what" = all ] || [ "$what" = checked ]; then
+    # the library's own checked build (csrc/Makefile `make check`) under the whole GPU suite; the report of
+    # tests/conftest.py::pytest_sessionfinish lands in gpurun_out/checked_build_report.txt
+    MMALIGN_LIB=$PWD/multimodal-alignment-of-noisy-image-text-pairs-using-weak-supervision_b200/csrc/libmmalign_check.so \
+        python -m pytest tests -m gpu -q -p no:cacheprovider > $out/${tag}_checked_pytest.log 2>&1
+    tail -4 $out/${tag}_checked_pytest.log
+fi
+
 if [ "$what" = all ] || [ "$what" = ncu ]; then
     cmd="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-verify"
     $cmd > $out/${tag}_plain.json 2> $out/${tag}_plain.err || { echo "bench failed without ncu"; tail -5 $out/${tag}_plain.err; exit 1; }
-    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
-        $cmd > $out/${tag}_ncu_l.log 2>&1
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^(mma::|fused_score|select_kernel|gather_kernel|rank_kernel|rescore_kernel|exact_|prep_rows|page_range|metrics_|max_float|iota_|Device)' \
+        -c 400 --csv --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_ncu_l.log 2>&1
     # one full capture of each: the timed step's first launch of K1 and of K2 (launches 0 and 1 belong to the warm-up step: whole waves, then the remainder)
     ncu --set full --clock-control none --import-source on -k regex:fused_score_topk -s 2 -c 1 -f \
         -o $out/${tag}_k1 $cmd > $out/${tag}_ncu_k1.log 2>&1
-    ncu --set full --clock-control none --import-source on -k regex:rescore_kernel -s 2 -c 1 -f \
+    # K2: the three kernels of the timed step's first slab (the warm-up step launched each twice)
+    ncu --set full --clock-control none --import-source on -k regex:'^(select_kernel|gather_kernel|rank_kernel)$' -s 6 -c 3 -f \
         -o $out/${tag}_k2 $cmd > $out/${tag}_ncu_k2.log 2>&1
     ls -la $out/${tag}_k1.ncu-rep $out/${tag}_k2.ncu-rep
 fi

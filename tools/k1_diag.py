@@ -1,0 +1,45 @@
+"""What paces the fused kernel (K1)?  The tuning build of the library (csrc: `make tune`) can take the kernel apart:
+MMALIGN_K1_DIAG=1 hands every accumulator back unread (no epilogue work), =2 stops the operand loads after the ring's
+first fill (the MMAs re-read shared memory), =3 both (the tensor pipe and its barriers alone).  Each variant runs
+K1 alone (mmalign_fused_pass) back to back for about a second, so that the power cap is in the number.
+   MMALIGN_LIB=.../csrc/libmmalign_tune.so python tools/k1_diag.py [--N rows] [--M cols] [--D dim]"""
+import argparse, importlib, os, pathlib, sys, time
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+PKG = "multimodal-alignment-of-noisy-image-text-pairs-using-weak-supervision_b200"
+os.environ.setdefault("MMALIGN_LIB", str(ROOT / PKG / "csrc" / "libmmalign_tune.so"))
+ap = argparse.ArgumentParser()
+ap.add_argument("--N", type=int, default=16 * 148 * 128)
+ap.add_argument("--M", type=int, default=1_000_000)
+ap.add_argument("--D", type=int, default=512)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--variants", default="0,1,2,3")
+ap.add_argument("--pairs", type=int, default=0)
+a = ap.parse_args()
+import torch
+pkg = importlib.import_module(PKG)
+synthetic = importlib.import_module(PKG + ".synthetic")
+img, chk, _ = synthetic.make_torch(a.N, a.M, a.D, T=512, device="cuda")
+eng = pkg.AlignmentEngine(0)
+eng.set_option("cta_pairs", a.pairs)
+eng.set_images(img["emb"], img["key"], img["bbox"], None)
+eng.set_chunks(chk["emb"], chk["key"], chk["bbox"], chk["terms"], n_terms=512)
+names = {0: "whole kernel", 1: "no epilogue work", 2: "no operand loads", 3: "neither (tensor pipe + barriers)"}
+for v in [int(x) for x in a.variants.split(",")]:
+    os.environ["MMALIGN_K1_DIAG"] = str(v)
+    kw = dict(shard=(0, a.M), k_values=(1, 5, 10, 20), mrr_cutoff=100, weak_weight=(0.3, 0.2))
+    eng.fused_pass(["vanilla_clip"], **kw)
+    torch.cuda.synchronize()
+    ts = []
+    for rep in range(a.reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.fused_pass(["vanilla_clip"], **kw)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sum(ts[-3:]) / len(ts[-3:])
+    print(f"cta_pairs={a.pairs} diag={v} ({names[v]}): {ms:.2f} ms = {2.0 * a.N * a.M * a.D / ms / 1e9:.0f} TFLOP/s  "
+          f"(all reps: {', '.join(f'{t:.1f}' for t in ts)})", flush=True)
+eng.close()
