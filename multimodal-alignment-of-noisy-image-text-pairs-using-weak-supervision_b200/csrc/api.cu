@@ -114,7 +114,7 @@ struct mmalign_ctx {
     bool chk_consumed = true;      // a run has read the chunk table since the last set_chunks
     int k2_sms = 0;                // SMs left to the exact rescoring of slab s while slab s+1 is contracted (0 = no overlap)
     int epi_sleep_ns = 0;          // mmalign_set_option: pause between polls of the epilogue's accumulator barrier
-    bool cta_pairs = false;        // the fused kernel on CTA pairs (tcgen05.mma.cta_group::2): mmalign_set_option
+    int cta_pairs = 0;             // the fused kernel on CTA pairs: 1 = tcgen05.mma.cta_group::2, 2 = B multicast (mmalign_set_option)
     size_t piece_bytes = (size_t)64 << 20;  // host embedding rows travel in pieces of about this size (mmalign_set_option)
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
     DevBuf list_keys, list_tau, list_count;
@@ -254,8 +254,8 @@ extern "C" int mmalign_set_option(mmalign_ctx *c, const char *name, int64_t valu
         return MMALIGN_OK;
     }
     if (!strcmp(name, "cta_pairs")) {
-        if (value != 0 && value != 1) return fail(c, MMALIGN_EINVAL, "cta_pairs=%lld must be 0 or 1", (long long)value);
-        c->cta_pairs = value != 0;
+        if (value < 0 || value > 2) return fail(c, MMALIGN_EINVAL, "cta_pairs=%lld must be 0, 1 or 2", (long long)value);
+        c->cta_pairs = (int)value;
         return MMALIGN_OK;
     }
     return fail(c, MMALIGN_EINVAL, "mmalign_set_option: unknown option '%s'", name);

@@ -386,10 +386,12 @@ struct FusedPlan {
     int stages;
     bool a_resident;
     int epi_sleep_ns;      // pause between the epilogue warps' polls of their accumulator barrier
-    bool pairs;            // CTA pairs (tcgen05.mma.cta_group::2): tensor map B carries 128-row boxes
+    bool pairs;            // clusters of two CTAs (tensor map B carries 128-row boxes): tcgen05.mma.cta_group::2, or
+    bool mc;               // ... cta_group::1 MMAs per CTA over a B ring the two CTAs fill together by multicast
 };
+// cluster: 0 = one CTA per SM on its own, 1 = CTA pairs (cta_group::2), 2 = CTA pairs sharing B by multicast
 int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan,
-               bool pairs = false);
+               int cluster = 0);
 cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan, const void *tmap_a,
                          const void *tmap_b, CandLists &lists, float *dump, cudaStream_t st, int64_t col_base = 0);
 int encode_tensor_map(void *tmap_out, const void *base, int64_t rows, int D, int box_rows,

@@ -347,13 +347,42 @@ __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t
     }
 }
 
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// B multicast (the MC variant of the kernel below): this CTA's half of a B k-slice lands at the same offset of BOTH
+// CTAs of the cluster and completes bytes on the full barrier of each; a commit frees the stage in both.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void *tmap, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar)  // arrives on `bar` in both CTAs when this CTA's MMAs retire
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------
-template <int KPL, bool A_RES>
-__global__ void __launch_bounds__(kFusedThreads, 1)
-fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                        const FusedArgs P)
+// MC = true: launched as clusters of two CTAs (the two SMs of a TPC) that contract two row blocks against the SAME
+// column tiles in lock step and share the B ring: each CTA loads half of every B k-slice and multicasts it into
+// both, so every B byte leaves L2 once per pair instead of once per SM -- the operand traffic that paces the plain
+// kernel (tools/k1_diag.py) halves -- while MMAs, accumulators and epilogues stay private to each CTA (unlike the
+// cta_group::2 kernel further down, whose pair meets on one accumulator barrier every tile).  The CTAs are coupled
+// through the ring only: a stage is refilled when BOTH have consumed it (empty barriers count two commits).
+template <int KPL, bool A_RES, bool MC>
+__device__ __forceinline__ void fused_body(const CUtensorMap &tmap_a, const CUtensorMap &tmap_b, const FusedArgs &P)
 {
     constexpr int CAP = 32 * KPL;
     extern __shared__ unsigned char smem_raw[];
@@ -372,7 +401,7 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const uint32_t tmem_slot = bar_aempty + 8u;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, MC ? 2 : 1); }  // MC: a commit of each CTA
         for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 8); }  // one arrival per epilogue warp
         mbar_init(bar_afull, 1);
         mbar_init(bar_aempty, 1);
@@ -384,11 +413,17 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // the peer's barriers exist before anything signals them
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    const int64_t n_units = P.n_row_blocks * P.n_splits;
+    // work units: (row block, column split); MC: (pair of row blocks, column split), this CTA takes block 2p + rank
+    const uint32_t rank = MC ? cluster_ctarank() : 0u;
+    const int64_t u_first = MC ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+    const int64_t u_step = MC ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+    const int64_t n_rbu = MC ? P.n_row_blocks / 2 : P.n_row_blocks;  // (the plan pads the row blocks to whole pairs)
+    const int64_t n_units = n_rbu * P.n_splits;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -397,9 +432,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
             int stage = 0;
             uint32_t phase = 0, uphase = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int64_t rb = u % P.n_row_blocks;
-                const int sp = (int)(u / P.n_row_blocks);
+            for (int64_t u = u_first; u < n_units; u += u_step) {
+                const int64_t rb = MC ? 2 * (u % n_rbu) + rank : u % n_rbu;
+                const int sp = (int)(u / n_rbu);
                 const int64_t t0 = (int64_t)sp * P.tiles_per_split;
                 const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
                 if (A_RES) {
@@ -413,11 +448,13 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     for (int kb = 0; kb < num_kb; ++kb) {
                         mbar_wait_relaxed(bar_empty + 8u * stage, phase ^ 1u);
                         const uint32_t dst = sStage + stage * stage_bytes;
-                        if (K1_DIAG(2) && (t > t0 || kb >= P.stages || u != (int64_t)blockIdx.x)) {  // (diagnosis: the MMAs re-read what the ring holds)
+                        if (K1_DIAG(2) && (t > t0 || kb >= P.stages || u != u_first)) {  // (diagnosis: the MMAs re-read what the ring holds)
                             mbar_arrive(bar_full + 8u * stage);
                         } else {
-                            mbar_expect_tx(bar_full + 8u * stage, stage_bytes);
-                            tma_load_2d(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN));
+                            mbar_expect_tx(bar_full + 8u * stage, stage_bytes);  // (MC: half of it arrives from the peer)
+                            if (MC) tma_load_2d_mc(dst + rank * (kBStageBytes / 2), &tmap_b, bar_full + 8u * stage, kb * BK,
+                                                   (int)(t * BN + rank * (BN / 2)));
+                            else tma_load_2d(dst, &tmap_b, bar_full + 8u * stage, kb * BK, (int)(t * BN));
                             if (!A_RES)
                                 tma_load_2d(dst + kBStageBytes, &tmap_a, bar_full + 8u * stage, kb * BK, (int)(rb * BM));
                         }
@@ -431,8 +468,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         if (lane == 0) {
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, uphase = 0;
-            for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int sp = (int)(u / P.n_row_blocks);
+            for (int64_t u = u_first; u < n_units; u += u_step) {
+                const int sp = (int)(u / n_rbu);
                 const int64_t t0 = (int64_t)sp * P.tiles_per_split;
                 const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
                 if (A_RES) { mbar_wait(bar_afull, uphase); uphase ^= 1u; }
@@ -451,7 +488,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         for (int k = 0; k < BK / 16; ++k)  // +32 bytes per K=16 step inside the swizzle atom
                             tc_mma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), kIdesc,
                                         (uint32_t)((kb | k) != 0));
-                        tc_commit(bar_empty + 8u * stage);  // frees the stage when these MMAs retire
+                        if (MC) tc_commit_mc(bar_empty + 8u * stage);  // frees the stage (in both CTAs) when these MMAs retire
+                        else tc_commit(bar_empty + 8u * stage);
                         if (++stage == P.stages) { stage = 0; phase ^= 1u; }
                     }
                     tc_commit(bar_tfull + 8u * acc);
@@ -471,9 +509,9 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         long long prof[12] = {};
         const long long prof_t0 = clock64();
 #endif
-        for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int64_t rb = u % P.n_row_blocks;
-            const int sp = (int)(u / P.n_row_blocks);
+        for (int64_t u = u_first; u < n_units; u += u_step) {
+            const int64_t rb = MC ? 2 * (u % n_rbu) + rank : u % n_rbu;
+            const int sp = (int)(u / n_rbu);
             const int64_t t0 = (int64_t)sp * P.tiles_per_split;
             const int64_t t1 = min(t0 + P.tiles_per_split, P.n_tiles);
             const int64_t list_id = (((int64_t)sp * P.n_row_blocks + rb) * 2 + half) * 128 + r;
@@ -489,7 +527,8 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
-                if (K1_DIAG(1)) {  // (diagnosis: the contraction alone)
+                if (K1_DIAG(1) || (K1_DIAG(8) && quad == 1) || (K1_DIAG(16) && quad == 2)) {  // (diagnosis: the contraction alone; 8 / 16: without
+                                                                                                  //  the epilogue warps of quadrant 1 (the MMA warp's scheduler) / 2)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
@@ -576,10 +615,27 @@ fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (MC) cluster_sync_all();  // neither CTA leaves while the other may still write its ring or signal its barriers
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+}
+
+template <int KPL, bool A_RES>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fused_score_topk_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const FusedArgs P)
+{
+    fused_body<KPL, A_RES, false>(tmap_a, tmap_b, P);
+}
+
+template <int KPL, bool A_RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFusedThreads, 1)
+fused_score_topk_mc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                           const FusedArgs P)
+{
+    fused_body<KPL, A_RES, true>(tmap_a, tmap_b, P);
 }
 
 
@@ -602,17 +658,6 @@ constexpr uint32_t kBHalfBytes = (BN / 2) * BK * 2;  // 16 KiB: this CTA's half 
 constexpr uint32_t kIdescPair = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                 ((uint32_t)((2 * BM) >> 4) << 24);
 
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void *tmap, uint32_t leader_bar, int c0, int c1)
 {
     asm volatile(
@@ -800,6 +845,31 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);
+                } else if (K1_DIAG(4)) {  // (diagnosis: what an epilogue that hands the accumulator back right after its loads would
+                    uint32_t va[32], vb[32];  //  buy -- the chunks are processed from two buffers, so the lists are NOT valid)
+                    __syncwarp();
+                    tmem_ld32(taddr, va);
+                    tmem_ld32(taddr + 32, vb);
+                    tmem_ld_wait(va);
+                    tmem_ld_wait(vb);
+                    tmem_ld32(taddr + 64, va);
+                    tmem_ld32(taddr + 96, vb);
+                    tmem_ld_wait(va);
+                    tmem_ld_wait(vb);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);
+                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    __syncwarp();
+                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    __syncwarp();
+                    for (int k = 0; k < 32; ++k) { va[k] ^= 0x00000100u; vb[k] ^= 0x00000100u; }
+                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    __syncwarp();
+                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    __syncwarp();
+                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
+                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin);
                 } else {
                     uint32_t va[32], vb[32];
                     __syncwarp();
@@ -851,12 +921,13 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
 // ---------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------
-int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan, bool pairs)
+int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_count, int n_ranks, FusedPlan *plan, int cluster)
 {
     if (D % BK != 0 || D < BK || N <= 0 || M <= 0) return -1;
     FusedPlan p = {};
     p.n_row_blocks = (N + BM - 1) / BM;
-    p.pairs = pairs && sm_count % 2 == 0;
+    p.pairs = cluster != 0 && sm_count % 2 == 0;  // clusters of two CTAs: whole pairs of row blocks, an even grid
+    p.mc = p.pairs && cluster == 2;                // ... that share the B ring by multicast (cta_group::1 MMAs)
     if (p.pairs) p.n_row_blocks = (p.n_row_blocks + 1) & ~(int64_t)1;  // whole pairs; a phantom block's lists are never read
     const int64_t n_tiles = (M + BN - 1) / BN;
     // column splits: the fewest that keep the last wave of persistent CTAs >= 95 % full
@@ -918,10 +989,11 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     if (const char *e = getenv("MMALIGN_A_RESIDENT")) p.a_resident = p.a_resident && atoi(e) != 0;
 #endif
     const size_t a_bytes = p.a_resident ? (size_t)(D / BK) * kABlockBytes : 0;
-    const size_t stage_bytes = (p.pairs ? kBHalfBytes : kBStageBytes) + (p.a_resident ? 0 : kABlockBytes);
+    const bool pair_mma = p.pairs && !p.mc;  // the cta_group::2 kernel: half a B k-slice per CTA and stage
+    const size_t stage_bytes = (pair_mma ? kBHalfBytes : kBStageBytes) + (p.a_resident ? 0 : kABlockBytes);
     const size_t fixed = 1024 /*alignment slack*/ + a_bytes + 256 /*barriers*/;
     int stages = (int)((kSmemLimit - fixed) / stage_bytes);
-    if (stages > (p.pairs ? kMaxPairStages : kMaxStages)) stages = p.pairs ? kMaxPairStages : kMaxStages;
+    if (stages > (pair_mma ? kMaxPairStages : kMaxStages)) stages = pair_mma ? kMaxPairStages : kMaxStages;
     if (stages < 2) return -3;
     p.stages = stages;
     p.smem_bytes = fixed + (size_t)stages * stage_bytes;
@@ -978,6 +1050,17 @@ static cudaError_t launch_pair_variant(const CUtensorMap &ta, const CUtensorMap 
 }
 
 template <int KPL, bool A_RES>
+static cudaError_t launch_mc_variant(const CUtensorMap &ta, const CUtensorMap &tb, const FusedArgs &args,
+                                     const FusedPlan &plan, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(fused_score_topk_mc_kernel<KPL, A_RES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem_bytes);
+    if (e != cudaSuccess) return e;
+    fused_score_topk_mc_kernel<KPL, A_RES><<<plan.grid, kFusedThreads, plan.smem_bytes, st>>>(ta, tb, args);  // __cluster_dims__(2)
+    return cudaGetLastError();
+}
+
+template <int KPL, bool A_RES>
 static cudaError_t launch_variant(const CUtensorMap &ta, const CUtensorMap &tb, const FusedArgs &args,
                                   const FusedPlan &plan, cudaStream_t st)
 {
@@ -1017,7 +1100,9 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;
     lists.kprime = plan.kprime;
     lists.kprime_list = plan.kprime_list;
-#define VARIANT(KPL) (plan.pairs ? (plan.a_resident ? launch_pair_variant<KPL, true>(ta, tb, a, plan, st)      \
+#define VARIANT(KPL) (plan.mc    ? (plan.a_resident ? launch_mc_variant<KPL, true>(ta, tb, a, plan, st)        \
+                                                    : launch_mc_variant<KPL, false>(ta, tb, a, plan, st))   \
+                      : plan.pairs ? (plan.a_resident ? launch_pair_variant<KPL, true>(ta, tb, a, plan, st)    \
                                                     : launch_pair_variant<KPL, false>(ta, tb, a, plan, st)) \
                                   : (plan.a_resident ? launch_variant<KPL, true>(ta, tb, a, plan, st)           \
                                                     : launch_variant<KPL, false>(ta, tb, a, plan, st)))

@@ -22,11 +22,12 @@ def eng(pkg):
     e.close()
 
 
-@pytest.fixture(scope="module")
-def eng_pairs(pkg):
-    """An engine whose fused kernel runs on CTA pairs (tcgen05.mma.cta_group::2)."""
+@pytest.fixture(scope="module", params=[1, 2], ids=["cta_group2", "b_multicast"])
+def eng_pairs(pkg, request):
+    """An engine whose fused kernel runs on CTA pairs: 1 = tcgen05.mma.cta_group::2 (one M = 256 MMA per pair),
+    2 = two cta_group::1 kernels in a cluster that fill one B ring together by TMA multicast."""
     e = pkg.AlignmentEngine(0)
-    e.set_option("cta_pairs", 1)
+    e.set_option("cta_pairs", request.param)
     yield e
     e.close()
 
