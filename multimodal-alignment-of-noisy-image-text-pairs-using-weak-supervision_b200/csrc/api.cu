@@ -114,6 +114,8 @@ struct mmalign_ctx {
     bool chk_consumed = true;      // a run has read the chunk table since the last set_chunks
     int k2_sms = 0;                // SMs left to the exact rescoring of slab s while slab s+1 is contracted (0 = no overlap)
     int epi_sleep_ns = 0;          // mmalign_set_option: pause between polls of the epilogue's accumulator barrier
+    int compact_one = 0;           // mmalign_set_option: routine list compaction all flagged lists at once (0, default), one list per tile gap (1),
+                                   // split over two gaps (2: loads under the next tile's filtering) -- measured alike
     int cta_pairs = 0;             // the fused kernel on CTA pairs: 1 = tcgen05.mma.cta_group::2, 2 = B multicast (mmalign_set_option)
     size_t piece_bytes = (size_t)64 << 20;  // host embedding rows travel in pieces of about this size (mmalign_set_option)
     DevBuf px_offsets, px_sorted, px_start, px_scratch;
@@ -246,6 +248,11 @@ extern "C" int mmalign_set_option(mmalign_ctx *c, const char *name, int64_t valu
     if (!strcmp(name, "k2_sms")) {
         if (value < 0 || value > c->sm_count / 2) return fail(c, MMALIGN_EINVAL, "k2_sms=%lld must be in 0..%d", (long long)value, c->sm_count / 2);
         c->k2_sms = (int)value;
+        return MMALIGN_OK;
+    }
+    if (!strcmp(name, "compact_one")) {
+        if (value < 0 || value > 2) return fail(c, MMALIGN_EINVAL, "compact_one=%lld must be 0, 1 or 2", (long long)value);
+        c->compact_one = (int)value;
         return MMALIGN_OK;
     }
     if (!strcmp(name, "epi_sleep_ns")) {
@@ -789,6 +796,7 @@ static int plan_fused(mmalign_ctx *c, const RunParams &rp, int kprime_req, int n
     const int prc = fused_plan(n_rows, n_cols, c->img.s.D, rp.kneed, kprime_req, sms > 0 ? sms : c->sm_count, n_ranks, plan, c->cta_pairs);
     if (prc) return fail(c, MMALIGN_ELIMIT, "no fused plan for N=%lld M=%lld D=%d K'=%d (code %d)", (long long)n_rows, (long long)n_cols, c->img.s.D, kprime_req, prc);
     plan->epi_sleep_ns = c->epi_sleep_ns;
+    plan->compact_one = c->compact_one;
     return MMALIGN_OK;
 }
 

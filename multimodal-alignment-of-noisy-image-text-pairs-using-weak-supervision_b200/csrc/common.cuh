@@ -386,6 +386,7 @@ struct FusedPlan {
     int stages;
     bool a_resident;
     int epi_sleep_ns;      // pause between the epilogue warps' polls of their accumulator barrier
+    int compact_one;       // routine list compaction split over two tile gaps (2), one list per gap (1), all flagged lists at once (0)
     bool pairs;            // clusters of two CTAs (tensor map B carries 128-row boxes): tcgen05.mma.cta_group::2, or
     bool mc;               // ... cta_group::1 MMAs per CTA over a B ring the two CTAs fill together by multicast
 };

@@ -202,6 +202,7 @@ struct FusedArgs {
     int skip_final;        // tuning builds: no end-of-unit compaction
     uint32_t col_base;     // added to the column index of every entry (a launch over a column group of the table)
     uint32_t epi_sleep_ns; // the epilogue warps poll their accumulator barrier this many ns apart (0 = spin)
+    int compact_one;       // routine compaction: 0 = every flagged list at once (default), 1 = one list per gap between tiles, 2 = split over two gaps
     int diag;              // tuning builds (-DMMALIGN_TUNING, MMALIGN_K1_DIAG): 1 = the epilogue hands every accumulator back
                            // unread, 2 = no operand loads after the ring's first fill; always 0 in the release build
 };
@@ -220,8 +221,12 @@ constexpr int kCompactMargin = 72;  // routine compaction when fewer than this m
 
 // Warp-cooperative compaction of the lists of the lanes that ask for it: keeps the best ~K'
 // entries and raises the lane's threshold tau to the smallest kept score.
+// `one`: at most one list per call (the routine compaction between two tiles: a warp that compacts several lists in
+// one go -- 6.5k cycles measured -- comes late to its next accumulator, and the accumulator's hand-back, i.e. the
+// tensor pipe, waits for the slowest of the epilogue warps; the lists left over keep their flag and take the next
+// gaps -- 72 free slots last for hundreds of tiles).
 template <int KPL>
-__device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, int kprime, bool need)
+__device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, int kprime, bool need, bool one = false)
 {
     constexpr int CAP = 32 * KPL;
     const int lane = threadIdx.x & 31;
@@ -234,6 +239,9 @@ __device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, i
         MMA_CHECK(cnt >= 0 && cnt <= CAP);  // a list never holds more than its capacity
         uint2 *L = reinterpret_cast<uint2 *>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_list), src));
         __syncwarp();
+#ifdef MMALIGN_PROFILE_EPI
+        const long long q0_ = clock64();
+#endif
         uint32_t h[KPL], c[KPL];  // ordered score key, column
         uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
 #pragma unroll
@@ -250,6 +258,9 @@ __device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, i
         }
         uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, hmin);
         uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, hmax);
+#ifdef MMALIGN_PROFILE_EPI
+        const long long q1_ = clock64();
+#endif
         int c_lo = cnt;  // #{key >= lo}
         // largest t with #{key >= t} >= kprime, stopping early once the count is within the slack
         while (lo < hi && c_lo > kprime + kSlack) {
@@ -261,6 +272,9 @@ __device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, i
             if (cc >= kprime) { lo = mid; c_lo = cc; } else hi = mid - 1u;
         }
         const uint32_t t = lo;
+#ifdef MMALIGN_PROFILE_EPI
+        const long long q2_ = clock64();
+#endif
         const bool drop_ties = c_lo > CAP - 64;  // a wall of equal scores: keep only what is above it
         int base = 0;
 #pragma unroll
@@ -273,7 +287,96 @@ __device__ __noinline__ void compact_lists(uint2 *my_list, int &n, float &tau, i
         __syncwarp();
         MMA_CHECK(base <= cnt && base <= CAP);
         if (lane == src) { n = base; tau = fmaxf(tau, f32_unordered(t)); }
+#ifdef MMALIGN_PROFILE_EPI
+        if (lane == 0) {
+            const long long q3_ = clock64();
+            atomicAdd(&g_epi_prof[12], (unsigned long long)(q1_ - q0_)); atomicAdd(&g_epi_prof[13], (unsigned long long)(q2_ - q1_));
+            atomicAdd(&g_epi_prof[14], (unsigned long long)(q3_ - q2_)); atomicAdd(&g_epi_prof[15], 1ull);
+        }
+#endif
+        if (one) break;
     }
+}
+
+// Split compaction (the routine case, lists of up to 256 entries).  Compacting a list takes ~4k cycles (load 1.7k,
+// bisection 1.1k, write-back 1.2k: tools/k1_epilogue_profile.py) against ~2.2k cycles of slack between two tiles, so
+// a warp that compacts arrives late at its next accumulator, and the accumulator's hand-back -- i.e. the tensor pipe
+// -- waits for the slowest of the epilogue warps; with eight (sixteen on CTA pairs) warps and 0.09 compactions per warp
+// and tile that is most tiles.  Split: the loads of ONE flagged list are issued in the gap after a tile and consumed in
+// the gap after the next one, so their latency runs under that tile's filtering.  What the owner appended in between
+// (behind the snapshot) is moved down behind the compacted entries.
+template <int KPL>
+__device__ __forceinline__ void compact_issue(const uint2 *my_list, int n, bool need, int &src, int &cnt, uint2 (&e)[KPL])
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned pending = __ballot_sync(0xFFFFFFFFu, need);
+    src = -1;
+    if (!pending) return;
+    src = __ffs(pending) - 1;
+    cnt = __shfl_sync(0xFFFFFFFFu, n, src);
+    const uint2 *L = reinterpret_cast<const uint2 *>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_list), src));
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) {
+        const int idx = q * 32 + lane;
+        e[q] = make_uint2(0u, 0u);
+        if (idx < cnt) e[q] = __ldcg(L + idx);
+    }
+}
+
+template <int KPL>
+__device__ __forceinline__ void compact_complete(uint2 *my_list, int &n, float &tau, int kprime, int src, int cnt,
+                                                 const uint2 (&e)[KPL])
+{
+    constexpr int CAP = 32 * KPL;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    uint2 *L = reinterpret_cast<uint2 *>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_list), src));
+    uint32_t h[KPL];
+    uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) {
+        h[q] = 0u;
+        if (q * 32 + lane < cnt) {
+            h[q] = f32_ordered(__uint_as_float(e[q].y));
+            hmin = min(hmin, h[q]);
+            hmax = max(hmax, h[q]);
+        }
+    }
+    uint32_t lo = __reduce_min_sync(0xFFFFFFFFu, hmin);
+    uint32_t hi = __reduce_max_sync(0xFFFFFFFFu, hmax);
+    int c_lo = cnt;
+    while (lo < hi && c_lo > kprime + kSlack) {  // (as compact_lists)
+        const uint32_t mid = lo + ((hi - lo + 1u) >> 1);
+        int cc = 0;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) cc += (h[q] >= mid);
+        cc = __reduce_add_sync(0xFFFFFFFFu, cc);
+        if (cc >= kprime) { lo = mid; c_lo = cc; } else hi = mid - 1u;
+    }
+    const uint32_t t = lo;
+    const bool drop_ties = c_lo > CAP - 64;
+    int base = 0;
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) {
+        const bool keep = drop_ties ? h[q] > t : h[q] >= t;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+        if (keep) L[base + __popc(m & lt_mask)] = e[q];
+        base += __popc(m);
+    }
+    __syncwarp();
+    MMA_CHECK(base <= cnt && base <= CAP);
+    if (lane == src) {
+        const float t_new = f32_unordered(t);
+        int w = base;
+        for (int q = cnt; q < n; ++q) {  // appended since the snapshot: a handful
+            const uint2 x = my_list[q];
+            if (__uint_as_float(x.y) > t_new) my_list[w++] = x;
+        }
+        n = w;
+        tau = fmaxf(tau, t_new);
+    }
+    __syncwarp();
 }
 
 __device__ __forceinline__ float max8(const uint32_t *v)
@@ -308,7 +411,7 @@ __device__ __noinline__ uint2 *append_group(uint32_t a0, uint32_t a1, uint32_t a
 #endif
 template <int KPL>
 __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t M, uint2 *list, int &n, float &tau,
-                                              int kprime, uint32_t col_base PC_PROF)
+                                              int kprime, uint32_t col_base, int &pend PC_PROF)
 {
     constexpr int CAP = 32 * KPL;
     EPI_T(p0_);
@@ -317,7 +420,10 @@ __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t
         for (int k = 0; k < 32; ++k)
             if (col0 + k >= M) v[k] = 0xFF800000u;  // -inf
     }
-    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) compact_lists<KPL>(list, n, tau, kprime, n > CAP - 32);
+    if (__any_sync(0xFFFFFFFFu, n > CAP - 32)) {  // (the first tiles of a sweep; a snapshot taken for a split compaction is stale now)
+        compact_lists<KPL>(list, n, tau, kprime, n > CAP - 32);
+        pend = -1;
+    }
     float g[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) g[q] = max8(v + 8 * q);
@@ -518,6 +624,8 @@ __device__ __forceinline__ void fused_body(const CUtensorMap &tmap_a, const CUte
             uint2 *const list = reinterpret_cast<uint2 *>(P.keys + list_id * CAP);  // this thread's candidate list
             float tau = P.tau_init;
             int n = 0;
+            int pend = -1, pend_cnt = 0;  // split compaction in flight: the lane whose list was snapshot, its length then
+            uint2 pend_e[KPL <= 8 ? KPL : 1];
             const int64_t row = rb * BM + r;
             for (int64_t t = t0; t < t1; ++t) {
                 EPI_T(w0_);
@@ -556,19 +664,19 @@ __device__ __forceinline__ void fused_body(const CUtensorMap &tmap_a, const CUte
                     tmem_ld_wait(va);
                     EPI_T(c1_);
                     tmem_ld32(taddr + 32, vb);
-                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
                     EPI_T(c2_);
                     tmem_ld_wait(vb);
                     EPI_T(c3_);
                     tmem_ld32(taddr + 64, va);
-                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
                     EPI_T(c4_);
                     tmem_ld_wait(va);
                     EPI_T(c5_);
                     tmem_ld32(taddr + 96, vb);
-                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
                     EPI_T(c6_);
                     tmem_ld_wait(vb);
@@ -576,14 +684,25 @@ __device__ __forceinline__ void fused_body(const CUtensorMap &tmap_a, const CUte
                     tc_fence_before();  // last read of this accumulator: hand it back to the MMA warp (every lane's loads
                     __syncwarp();       // have completed; one arrival per warp)
                     if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
-                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     // Routine compaction happens HERE, after the accumulator went back to the MMA warp, so that its
                     // global-memory latency is off the MMA critical path (the check inside process_chunk only fires
                     // when a single tile overflows the remaining room, i.e. in the first tiles of a sweep).
                     __syncwarp();
                     EPI_T(c8_);
-                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin)) {
-                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin);
+                    bool split = false;
+                    if constexpr (KPL <= 8) {
+                        if (P.compact_one == 2) {
+                            split = true;
+                            if (pend >= 0) {
+                                compact_complete<KPL>(list, n, tau, P.kprime, pend, pend_cnt, pend_e);
+                                EPI_ADD(5, 1);
+                            }
+                            compact_issue<KPL>(list, n, n > CAP - kCompactMargin, pend, pend_cnt, pend_e);
+                        }
+                    }
+                    if (!split && __any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin)) {
+                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin, P.compact_one != 0);
                         EPI_ADD(5, 1);
                     }
                     EPI_T(c9_);
@@ -596,6 +715,7 @@ __device__ __forceinline__ void fused_body(const CUtensorMap &tmap_a, const CUte
             }
             if (!P.dump && !P.skip_final) {  // leave at most K' + slack entries per list for the rescoring kernel
                 __syncwarp();
+                pend = -1;
                 if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
                     compact_lists<KPL>(list, n, tau, P.kprime, n > P.kprime + kSlack);
             }
@@ -808,6 +928,10 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
         const int r = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
+#ifdef MMALIGN_PROFILE_EPI
+        long long prof[12] = {};
+        const long long prof_t0 = clock64();
+#endif
         for (int64_t u = cluster_id; u < n_units; u += n_clusters) {
             const int64_t rb = 2 * (u % n_pairs) + rank;
             const int sp = (int)(u / n_pairs);
@@ -817,12 +941,14 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
             uint2 *const list = reinterpret_cast<uint2 *>(P.keys + list_id * CAP);
             float tau = P.tau_init;
             int n = 0;
+            int pend = -1, pend_cnt = 0;  // split compaction in flight: the lane whose list was snapshot, its length then
+            uint2 pend_e[KPL <= 8 ? KPL : 1];
             const int64_t row = rb * BM + r;
-#ifdef MMALIGN_PROFILE_EPI
-            long long prof[12] = {};
-#endif
             for (int64_t t = t0; t < t1; ++t) {
+                EPI_T(w0_);
                 mbar_wait_paused(bar_tfull + 8u * acc, acc_phase, P.epi_sleep_ns);
+                EPI_T(w1_);
+                EPI_ADD(0, w1_ - w0_);  // waiting for the tensor pipe
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
@@ -859,46 +985,74 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);
-                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
-                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
                     for (int k = 0; k < 32; ++k) { va[k] ^= 0x00000100u; vb[k] ^= 0x00000100u; }
-                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
-                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
                     if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
                         compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin);
                 } else {
                     uint32_t va[32], vb[32];
                     __syncwarp();
+                    EPI_T(c0_);
                     tmem_ld32(taddr, va);
                     tmem_ld_wait(va);
+                    EPI_T(c1_);
                     tmem_ld32(taddr + 32, vb);
-                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(va, col0, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
+                    EPI_T(c2_);
                     tmem_ld_wait(vb);
+                    EPI_T(c3_);
                     tmem_ld32(taddr + 64, va);
-                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(vb, col0 + 32, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
+                    EPI_T(c4_);
                     tmem_ld_wait(va);
+                    EPI_T(c5_);
                     tmem_ld32(taddr + 96, vb);
-                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(va, col0 + 64, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
+                    EPI_T(c6_);
                     tmem_ld_wait(vb);
+                    EPI_T(c7_);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);  // 2 x 8 arrivals free the accumulator for the pair
-                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base PC_PROF_ARG);
+                    process_chunk<KPL>(vb, col0 + 96, P.M, list, n, tau, P.kprime, P.col_base, pend PC_PROF_ARG);
                     __syncwarp();
-                    if (__any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin))
-                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin);
+                    EPI_T(c8_);
+                    bool split = false;
+                    if constexpr (KPL <= 8) {
+                        if (P.compact_one == 2) {
+                            split = true;
+                            if (pend >= 0) {
+                                compact_complete<KPL>(list, n, tau, P.kprime, pend, pend_cnt, pend_e);
+                                EPI_ADD(5, 1);
+                            }
+                            compact_issue<KPL>(list, n, n > CAP - kCompactMargin, pend, pend_cnt, pend_e);
+                        }
+                    }
+                    if (!split && __any_sync(0xFFFFFFFFu, n > CAP - kCompactMargin)) {
+                        compact_lists<KPL>(list, n, tau, P.kprime, n > CAP - kCompactMargin, P.compact_one != 0);
+                        EPI_ADD(5, 1);
+                    }
+                    EPI_T(c9_);
+                    EPI_ADD(1, (c1_ - c0_) + (c3_ - c2_) + (c5_ - c4_) + (c7_ - c6_));  // waiting for TMEM loads
+                    EPI_ADD(2, (c2_ - c1_) + (c4_ - c3_) + (c6_ - c5_) + (c8_ - c7_));  // filtering (incl. appends)
+                    EPI_ADD(3, c9_ - c8_);                                              // routine compaction
+                    EPI_ADD(4, 1);                                                      // tiles
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
             if (!P.dump && !P.skip_final) {
                 __syncwarp();
+                pend = -1;
                 if (__any_sync(0xFFFFFFFFu, n > P.kprime + kSlack))
                     compact_lists<KPL>(list, n, tau, P.kprime, n > P.kprime + kSlack);
             }
@@ -908,6 +1062,13 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                 P.count[list_id] = n;
             }
         }
+#ifdef MMALIGN_PROFILE_EPI
+        if (lane == 0) {
+            prof[6] = clock64() - prof_t0;
+            for (int q = 0; q < 12; ++q) if (q != 7) atomicAdd(&g_epi_prof[q], (unsigned long long)prof[q]);
+            atomicAdd(&g_epi_prof[7], 1ull);
+        }
+#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -1095,6 +1256,7 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
 #endif
     a.col_base = (uint32_t)col_base;
     a.epi_sleep_ns = (uint32_t)plan.epi_sleep_ns;
+    a.compact_one = plan.compact_one;
     const CUtensorMap &ta = *reinterpret_cast<const CUtensorMap *>(tmap_a);
     const CUtensorMap &tb = *reinterpret_cast<const CUtensorMap *>(tmap_b);
     lists.cap = plan.cap; lists.n_splits = plan.n_splits; lists.n_row_blocks = plan.n_row_blocks;

@@ -16,6 +16,7 @@ ap.add_argument("--D", type=int, default=512)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--variants", default="0,1,2,3")
 ap.add_argument("--pairs", type=int, default=0)
+ap.add_argument("--compact", type=int, default=-1, help="compact_one option (-1 = library default)")
 a = ap.parse_args()
 import torch
 pkg = importlib.import_module(PKG)
@@ -23,8 +24,28 @@ synthetic = importlib.import_module(PKG + ".synthetic")
 img, chk, _ = synthetic.make_torch(a.N, a.M, a.D, T=512, device="cuda")
 eng = pkg.AlignmentEngine(0)
 eng.set_option("cta_pairs", a.pairs)
+if a.compact >= 0:
+    eng.set_option("compact_one", a.compact)
 eng.set_images(img["emb"], img["key"], img["bbox"], None)
 eng.set_chunks(chk["emb"], chk["key"], chk["bbox"], chk["terms"], n_terms=512)
+import threading
+import pynvml
+pynvml.nvmlInit()
+_h = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+
+class Sampler(threading.Thread):  # SM clock and board power while a variant runs (NVML, every 20 ms)
+    def __init__(self):
+        super().__init__(daemon=True)
+        self.stop, self.mhz, self.watts = False, [], []
+
+    def run(self):
+        while not self.stop:
+            self.mhz.append(pynvml.nvmlDeviceGetClockInfo(_h, pynvml.NVML_CLOCK_SM))
+            self.watts.append(pynvml.nvmlDeviceGetPowerUsage(_h) / 1000.0)
+            time.sleep(0.02)
+
+
 names = {0: "whole kernel", 1: "no epilogue work", 2: "no operand loads", 3: "neither (tensor pipe + barriers)",
          4: "accumulator handed back right after its loads (pair kernel; lists not valid)",
          8: "no epilogue work in quadrant 1 (the warps that share the MMA warp's scheduler)", 16: "no epilogue work in quadrant 2"}
@@ -34,6 +55,8 @@ for v in [int(x) for x in a.variants.split(",")]:
     eng.fused_pass(["vanilla_clip"], **kw)
     torch.cuda.synchronize()
     ts = []
+    smp = Sampler()
+    smp.start()
     for rep in range(a.reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -41,7 +64,11 @@ for v in [int(x) for x in a.variants.split(",")]:
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
+    smp.stop = True
+    smp.join()
+    half = len(smp.mhz) // 2  # the second half of the run: the cap has settled
+    mhz, watts = sorted(smp.mhz[half:])[len(smp.mhz[half:]) // 2], sorted(smp.watts[half:])[len(smp.watts[half:]) // 2]
     ms = sum(ts[-3:]) / len(ts[-3:])
-    print(f"cta_pairs={a.pairs} diag={v} ({names[v]}): {ms:.2f} ms = {2.0 * a.N * a.M * a.D / ms / 1e9:.0f} TFLOP/s  "
-          f"(all reps: {', '.join(f'{t:.1f}' for t in ts)})", flush=True)
+    print(f"cta_pairs={a.pairs} compact={a.compact} diag={v} ({names[v]}): {ms:.2f} ms = {2.0 * a.N * a.M * a.D / ms / 1e9:.0f} TFLOP/s  "
+          f"(all reps: {', '.join(f'{t:.1f}' for t in ts)}); median SM clock {mhz} MHz, board power {watts:.0f} W", flush=True)
 eng.close()

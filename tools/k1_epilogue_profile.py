@@ -16,6 +16,8 @@ ap.add_argument("--N", type=int, default=8 * 148 * 128)
 ap.add_argument("--M", type=int, default=1_000_000)
 ap.add_argument("--D", type=int, default=512)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--compact", type=int, default=-1)
+ap.add_argument("--pairs", type=int, default=0, help="cta_pairs option of the engine (0, 1 = cta_group::2, 2 = B multicast)")
 a = ap.parse_args()
 os.environ.setdefault("MMALIGN_LIB", str(ROOT / PKG / "csrc" / "libmmalign_prof.so"))
 pkg = importlib.import_module(PKG)
@@ -23,6 +25,9 @@ synthetic = importlib.import_module(PKG + ".synthetic")
 L = pkg._native.load()
 img, chk, _ = synthetic.make_torch(a.N, a.M, a.D, T=512, device="cuda")
 eng = pkg.AlignmentEngine(0)
+eng.set_option("cta_pairs", a.pairs)
+if a.compact >= 0:
+    eng.set_option("compact_one", a.compact)
 eng.set_images(img["emb"], img["key"], img["bbox"], None)
 eng.set_chunks(chk["emb"], chk["key"], chk["bbox"], chk["terms"], n_terms=512)
 buf = (C.c_ulonglong * 16)()
@@ -48,5 +53,7 @@ for rep in range(a.reps):
           f"routine compaction {v[3] / tiles:.0f} ({v[5] / tiles:.3f} per tile), total {v[6] / tiles:.0f}; "
           f"warps {warps}, tiles/warp {tiles / warps:.0f}; per 32x32 chunk: maxima+vote {v[8] / tiles / 4:.0f} cycles, "
           f"P(chunk has a hit) {v[9] / tiles / 4:.3f}, 8-column groups with a hit per chunk {v[10] / tiles / 4:.3f}, "
-          f"hit path {v[11] / max(v[9], 1):.0f} cycles per chunk with a hit = {v[11] / max(v[10], 1):.0f} per group", flush=True)
+          f"hit path {v[11] / max(v[9], 1):.0f} cycles per chunk with a hit = {v[11] / max(v[10], 1):.0f} per group; "
+          f"per compacted list (all call sites): load {v[12] / max(v[15], 1):.0f}, bisection {v[13] / max(v[15], 1):.0f}, "
+          f"write-back {v[14] / max(v[15], 1):.0f} cycles; lists {v[15]}", flush=True)
 eng.close()
