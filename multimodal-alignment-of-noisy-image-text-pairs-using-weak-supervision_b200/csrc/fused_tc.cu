@@ -640,6 +640,19 @@ __device__ __forceinline__ void fused_body(const CUtensorMap &tmap_a, const CUte
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
+                } else if (K1_DIAG(32)) {  // (diagnosis: the accumulator is read, nothing is done with it)
+                    uint32_t va[32], vb[32];
+                    __syncwarp();
+                    tmem_ld32(taddr, va); tmem_ld32(taddr + 32, vb);
+                    tmem_ld_wait(va); tmem_ld_wait(vb);
+                    uint32_t x = va[0] ^ vb[31];
+                    tmem_ld32(taddr + 64, va); tmem_ld32(taddr + 96, vb);
+                    tmem_ld_wait(va); tmem_ld_wait(vb);
+                    x ^= va[5] ^ vb[7];
+                    if (x == 0x12345678u) n = 1;  // (keeps the loads)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8u * acc);
                 } else if (P.dump) {
 #pragma unroll 1
                     for (int ch = 0; ch < 4; ++ch) {
@@ -953,6 +966,19 @@ fused_score_topk_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const _
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * 128);
                 const int64_t col0 = t * BN + half * 128;
                 if (K1_DIAG(1)) {  // (diagnosis: the contraction alone)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);
+                } else if (K1_DIAG(32)) {  // (diagnosis: the accumulator is read, nothing is done with it)
+                    uint32_t va[32], vb[32];
+                    __syncwarp();
+                    tmem_ld32(taddr, va); tmem_ld32(taddr + 32, vb);
+                    tmem_ld_wait(va); tmem_ld_wait(vb);
+                    uint32_t x = va[0] ^ vb[31];
+                    tmem_ld32(taddr + 64, va); tmem_ld32(taddr + 96, vb);
+                    tmem_ld_wait(va); tmem_ld_wait(vb);
+                    x ^= va[5] ^ vb[7];
+                    if (x == 0x12345678u) n = 1;  // (keeps the loads)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_rank0(bar_tempty + 8u * acc);

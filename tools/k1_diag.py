@@ -48,7 +48,7 @@ class Sampler(threading.Thread):  # SM clock and board power while a variant run
 
 names = {0: "whole kernel", 1: "no epilogue work", 2: "no operand loads", 3: "neither (tensor pipe + barriers)",
          4: "accumulator handed back right after its loads (pair kernel; lists not valid)",
-         8: "no epilogue work in quadrant 1 (the warps that share the MMA warp's scheduler)", 16: "no epilogue work in quadrant 2"}
+         32: "TMEM loads only (no filter, no lists)", 8: "no epilogue work in quadrant 1 (the warps that share the MMA warp's scheduler)", 16: "no epilogue work in quadrant 2"}
 for v in [int(x) for x in a.variants.split(",")]:
     os.environ["MMALIGN_K1_DIAG"] = str(v)
     kw = dict(shard=(0, a.M), k_values=(1, 5, 10, 20), mrr_cutoff=100, weak_weight=(0.3, 0.2))
