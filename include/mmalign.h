@@ -148,9 +148,18 @@ int mmalign_set_chunks(mmalign_ctx *ctx, const float *emb, const uint64_t *page_
                        const double *bbox, const uint64_t *terms, int64_t m_local, int32_t D,
                        int32_t term_words, int64_t n_terms, int64_t col_offset);
 
-/* tunables of a context.  "piece_bytes": host embedding rows are uploaded in pieces of about this many bytes
- * (default 64 MiB; each piece announces itself, so preparation and the first contraction start behind the
- * first pieces instead of behind the whole table). */
+/* tunables of a context (none changes a result):
+ *   "piece_bytes"   host embedding rows are uploaded in pieces of about this many bytes (default 64 MiB; each piece
+ *                   announces itself, so preparation and the first contraction start behind the first pieces
+ *                   instead of behind the whole table)
+ *   "cta_pairs"     the fused kernel on clusters of two CTAs: 0 = one CTA per SM on its own (default),
+ *                   1 = tcgen05.mma.cta_group::2 (one M = 256 MMA per pair, half of B per CTA),
+ *                   2 = cta_group::1 MMAs per CTA over a B ring the pair fills together by TMA multicast
+ *   "k2_sms"        SMs left to the exact rescoring of slab s while slab s+1 is contracted (default 0: one after
+ *                   the other)
+ *   "compact_one"   routine compaction of the candidate lists: 0 = every flagged list at once (default), 1 = one
+ *                   list per gap between two tiles, 2 = split over two gaps
+ *   "epi_sleep_ns"  pause between the epilogue warps' polls of their accumulator barrier (default 0) */
 int mmalign_set_option(mmalign_ctx *ctx, const char *name, int64_t value);
 
 /* waits for every upload and preparation queued by set_images / set_chunks (after it, page-locked host

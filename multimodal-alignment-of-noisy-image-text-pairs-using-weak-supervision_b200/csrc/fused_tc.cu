@@ -1157,15 +1157,16 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     // tile; the room between those two marks is how many insertions one compaction buys.  Measured (K1 alone): 6 slots
     // of room (the 4-GPU share in 128-entry lists) cost 6.5 % against 64; 300 slots in 512-entry lists gain nothing.
     int room = 64;
+    bool room_forced = false;
 #ifdef MMALIGN_TUNING
-    if (const char *e = getenv("MMALIGN_CAP_ROOM")) room = atoi(e);
+    if (const char *e = getenv("MMALIGN_CAP_ROOM")) { room = atoi(e); room_forced = true; }
 #endif
     int need = p.kprime_list + kSlack + kCompactMargin + room;
     if (need > 512) need = p.kprime_list + kSlack + kCompactMargin + 32;
     // A few slots short of the full room is worth the next smaller capacity (half the keys per lane in every
     // compaction, half the list memory): 48 slots of room are accepted for it.
-    if (need > 256 && need - room + 48 <= 256) need = 256;
-    if (need > 128 && need - room + 48 <= 128) need = 128;
+    if (!room_forced && need > 256 && need - room + 48 <= 256) need = 256;
+    if (!room_forced && need > 128 && need - room + 48 <= 128) need = 128;
     if (need <= 128) p.cap = 128;
     else if (need <= 256) p.cap = 256;
     else if (need <= 512) p.cap = 512;
