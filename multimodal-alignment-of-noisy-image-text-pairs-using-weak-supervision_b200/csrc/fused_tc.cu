@@ -409,6 +409,9 @@ __device__ __noinline__ uint2 *append_group(uint32_t a0, uint32_t a1, uint32_t a
 #define PC_PROF
 #define PC_PROF_ARG
 #endif
+#ifdef MMALIGN_TUNING
+__device__ int g_hit_mode;  // tuning builds (MMALIGN_K1_HIT): 1 = a hit group appends its maximum only (one store, no call: lists NOT valid), 2 = hits are found but nothing is stored
+#endif
 template <int KPL>
 __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t M, uint2 *list, int &n, float &tau,
                                               int kprime, uint32_t col_base, int &pend PC_PROF)
@@ -438,6 +441,15 @@ __device__ __forceinline__ void process_chunk(uint32_t *v, int64_t col0, int64_t
         // of it instruction fetch).
         uint2 *wp = list + n;
         const uint32_t c0 = (uint32_t)col0 + col_base;
+#ifdef MMALIGN_TUNING
+        if (g_hit_mode) {  // (diagnosis: what a hit path of a few instructions would buy)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (g[q] > tau) { if (g_hit_mode == 1) *wp = make_uint2(c0 + 8 * q, __float_as_uint(g[q])); ++wp; }
+            n = (int)(wp - list);
+            return;
+        }
+#endif
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             if (__any_sync(0xFFFFFFFFu, g[q] > tau)) {
@@ -1280,6 +1292,10 @@ cudaError_t launch_fused(const Side &img, const Side &chk, const FusedPlan &plan
     if (const char *e = getenv("MMALIGN_TAU_INIT")) a.tau_init = (float)atof(e);
     a.skip_final = getenv("MMALIGN_SKIP_FINAL") != nullptr;
     if (const char *e = getenv("MMALIGN_K1_DIAG")) a.diag = atoi(e);
+    {
+        const int hm = getenv("MMALIGN_K1_HIT") ? atoi(getenv("MMALIGN_K1_HIT")) : 0;
+        cudaMemcpyToSymbolAsync(g_hit_mode, &hm, sizeof hm, 0, cudaMemcpyHostToDevice, st);
+    }
 #endif
     a.col_base = (uint32_t)col_base;
     a.epi_sleep_ns = (uint32_t)plan.epi_sleep_ns;
