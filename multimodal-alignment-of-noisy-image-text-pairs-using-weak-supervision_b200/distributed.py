@@ -196,9 +196,48 @@ class ShardedScorer:
             eng.rescore_after(event)
         eng.set_images(img["emb"], img["key"], img.get("bbox"), img.get("terms"))
 
+    def prefetch(self, img, chk):
+        """Streaming use (one load + run per batch of tables): start the upload of the NEXT step's host shards -- pinned
+        torch tensors -- into device staging buffers on a side stream, behind whatever the GPU is computing; the next
+        load() given the same objects picks the staged copies up instead of uploading.  Two sets of staging buffers
+        alternate, because the step in flight still reads the set its own load() was given."""
+        import torch
+        if self.device is None or torch.device(self.device).type != "cuda":
+            return
+        if getattr(self, "_pf_stream", None) is None:
+            self._pf_stream = torch.cuda.Stream(device=self.device)
+            self._pf_parity = 0
+        self._pf_parity ^= 1
+        staged = []
+        self._pf_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._pf_stream):
+            for side, d in (("img", img), ("chk", chk)):
+                o = {}
+                for f in self.FIELDS:
+                    x = self._as_tensor(d.get(f))
+                    if x is None:
+                        o[f] = None
+                        continue
+                    buf = self._buffer(("prefetch", self._pf_parity, side, f), tuple(x.shape), x.dtype, x)
+                    buf.copy_(x, non_blocking=True)
+                    o[f] = buf
+                staged.append(o)
+            ev = torch.cuda.Event()
+            ev.record(self._pf_stream)
+        self._prefetched = (id(img), id(chk), staged[0], staged[1], ev)
+
+    def _take_prefetched(self, img, chk):
+        pf = getattr(self, "_prefetched", None)
+        self._prefetched = None
+        if pf is None or pf[0] != id(img) or pf[1] != id(chk):
+            return img, chk
+        pf[4].synchronize()  # (the copy had the previous step's kernels to finish behind)
+        return pf[2], pf[3]
+
     def load(self, img, chk, *, N: int, M: int, n_terms: int = 0):
         """img: image rows slab_range(N, world, rank); chk: chunk rows shard_range(M, world, rank) -- dicts of
         emb / key / bbox / terms (CUDA or pinned host torch tensors, or numpy arrays)."""
+        img, chk = self._take_prefetched(img, chk)
         self.N, self.M = int(N), int(M)
         self.mode = self._mode(N) if self.world > 1 else "rows"
         if self.world > 1 and self.mode == "rows":
