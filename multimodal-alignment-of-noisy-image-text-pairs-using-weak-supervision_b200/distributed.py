@@ -88,6 +88,8 @@ class ShardedScorer:
         self.dist = dist
         self._full = {}
         self._side = None
+        self._prefetched = None  # (image ids, staged device copies, event) of the next step: prefetch()
+        self._pf_stream = None
         self.N = self.M = 0
         self.mode = "rows"
         self.MAX = getattr(getattr(dist, "ReduceOp", None), "MAX", "max") if dist is not None else "max"
@@ -204,7 +206,7 @@ class ShardedScorer:
         import torch
         if self.device is None or torch.device(self.device).type != "cuda":
             return
-        if getattr(self, "_pf_stream", None) is None:
+        if self._pf_stream is None:
             self._pf_stream = torch.cuda.Stream(device=self.device)
             self._pf_parity = 0
         self._pf_parity ^= 1
@@ -227,7 +229,7 @@ class ShardedScorer:
         self._prefetched = (id(img), id(chk), staged[0], staged[1], ev)
 
     def _take_prefetched(self, img, chk):
-        pf = getattr(self, "_prefetched", None)
+        pf = self._prefetched
         self._prefetched = None
         if pf is None or pf[0] != id(img) or pf[1] != id(chk):
             return img, chk

@@ -168,3 +168,52 @@ def test_fully_sharded_equals_oracle(pkg, oracle, synthetic, N, M, D, world):
         for si in range(4):
             for q, k in enumerate(ks):
                 assert r["hits"][si, q] == np.count_nonzero((o["pair_rank"][si] >= 1) & (o["pair_rank"][si] <= k))
+
+
+@pytest.mark.parametrize("world,contraction", [(1, "rows"), (2, "rows"), (3, "columns")])
+def test_prefetched_uploads_give_the_same_results(pkg, oracle, synthetic, world, contraction):
+    """Streaming use: while step s computes, ShardedScorer.prefetch copies the pinned host shards of step s+1 into device
+    staging buffers (two sets alternate); the next load() picks them up.  Three steps over two different corpora
+    (A, B, A): every step's results are the oracle's for ITS corpus."""
+    distributed = importlib.import_module(PKG_NAME + ".distributed")
+    N, M, D = 600, 5000, 128
+    ks, cutoff, lam = (1, 5, 10, 20), 100, (0.3, 0.2)
+    corpora = [synthetic.make_numpy(N, M, D, T=512, seed=s)[:2] for s in (81, 82)]
+    want = [oracle.evaluate(i, c, T=512, schema_mask=15, candidates="all", lam=(lam[0], lam[1], lam[0] + lam[1]),
+                            kmax=max(ks), cutoff=cutoff) for i, c in corpora]
+
+    def pinned(d, lo, hi):
+        out = {}
+        for k, v in d.items():
+            if v is None:
+                out[k] = None
+                continue
+            v = np.ascontiguousarray(v[lo:hi])
+            out[k] = torch.from_numpy(v.view(np.int64) if v.dtype == np.uint64 else v).pin_memory()
+        return out
+
+    def rank_main(rank, dist):
+        eng = pkg.AlignmentEngine(0)
+        sc = distributed.ShardedScorer(eng, world, rank, torch.device("cuda", 0), dist=dist if world > 1 else None,
+                                       contraction=contraction)
+        host = [(pinned(i, *distributed.slab_range(N, world, rank)), pinned(c, *distributed.shard_range(M, world, rank)))
+                for i, c in corpora]
+        got = []
+        for step, which in enumerate((0, 1, 0)):
+            assert (sc._prefetched is not None) == (step > 0)
+            sc.load(*host[which], N=N, M=M, n_terms=512)
+            assert sc._prefetched is None  # (load consumed what the previous step staged)
+            nxt = (1, 0, 1)[step]
+            sc.prefetch(*host[nxt])
+            r = sc.run(schemas=ALL4, k_values=ks, mrr_cutoff=cutoff, weak_weight=lam, host_outputs=True)
+            got.append({k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in r.items()})
+        eng.close()
+        return got
+    results = _run_ranks(world, rank_main)
+    for rank in range(world):
+        q0, q1 = distributed.slab_range(N, world, rank)
+        for step, which in enumerate((0, 1, 0)):
+            r, o = results[rank][step], want[which]
+            p0, p1 = o["pair_offsets"][q0], o["pair_offsets"][q1]
+            assert np.array_equal(r["topk_idx"], o["topk_idx"][:, q0:q1]) and np.array_equal(r["topk_score"], o["topk_score"][:, q0:q1])
+            assert np.array_equal(r["pair_rank"], o["pair_rank"][:, p0:p1]) and np.array_equal(r["pair_sim"], o["pair_sim"][p0:p1])
