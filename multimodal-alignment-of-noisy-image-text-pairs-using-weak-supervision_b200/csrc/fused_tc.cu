@@ -1130,9 +1130,12 @@ int fused_plan(int64_t N, int64_t M, int D, int kneed, int kprime_req, int sm_co
     if (p.pairs) p.n_row_blocks = (p.n_row_blocks + 1) & ~(int64_t)1;  // whole pairs; a phantom block's lists are never read
     const int64_t n_tiles = (M + BN - 1) / BN;
     // column splits: the fewest that keep the last wave of persistent CTAs >= 95 % full
+    // (up to 16 splits keep a row's 2 x splits lists within what the warp-per-row rescoring takes, rescore.cu; more only
+    // when they are needed to fill the GPU at all)
     int best = 1;
     double best_eff = 0.0;
     for (int s = 1; s <= 64 && s <= n_tiles; ++s) {
+        if (s == 17 && best_eff >= 0.85) break;
         const int64_t units = p.n_row_blocks * s;
         const int64_t waves = (units + sm_count - 1) / sm_count;
         const double eff = (double)units / (double)(waves * sm_count);
