@@ -17,6 +17,7 @@ ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--variants", default="0,1,2,3")
 ap.add_argument("--pairs", type=int, default=0)
 ap.add_argument("--compact", type=int, default=-1, help="compact_one option (-1 = library default)")
+ap.add_argument("--epi-sleep", type=int, default=-1, help="epi_sleep_ns option (-1 = library default)")
 a = ap.parse_args()
 import torch
 pkg = importlib.import_module(PKG)
@@ -26,6 +27,8 @@ eng = pkg.AlignmentEngine(0)
 eng.set_option("cta_pairs", a.pairs)
 if a.compact >= 0:
     eng.set_option("compact_one", a.compact)
+if a.epi_sleep >= 0:
+    eng.set_option("epi_sleep_ns", a.epi_sleep)
 eng.set_images(img["emb"], img["key"], img["bbox"], None)
 eng.set_chunks(chk["emb"], chk["key"], chk["bbox"], chk["terms"], n_terms=512)
 import threading
@@ -69,6 +72,6 @@ for v in [int(x) for x in a.variants.split(",")]:
     half = len(smp.mhz) // 2  # the second half of the run: the cap has settled
     mhz, watts = sorted(smp.mhz[half:])[len(smp.mhz[half:]) // 2], sorted(smp.watts[half:])[len(smp.watts[half:]) // 2]
     ms = sum(ts[-3:]) / len(ts[-3:])
-    print(f"cta_pairs={a.pairs} compact={a.compact} diag={v} ({names[v]}): {ms:.2f} ms = {2.0 * a.N * a.M * a.D / ms / 1e9:.0f} TFLOP/s  "
+    print(f"cta_pairs={a.pairs} compact={a.compact} epi_sleep={a.epi_sleep} diag={v} ({names[v]}): {ms:.2f} ms = {2.0 * a.N * a.M * a.D / ms / 1e9:.0f} TFLOP/s  "
           f"(all reps: {', '.join(f'{t:.1f}' for t in ts)}); median SM clock {mhz} MHz, board power {watts:.0f} W", flush=True)
 eng.close()
