@@ -45,3 +45,17 @@ def test_throttled_runs_are_rejected():
     assert b.clocks_rejected(dict(ok, reasons=["sw_thermal_slowdown"])) and b.clocks_rejected(dict(ok, reasons=["hw_slowdown"]))
     assert b.clocks_rejected({"sm_mhz": 900.0, "sm_max_mhz": 1965.0, "reasons": []})      # clock lock left behind
     assert not b.clocks_rejected({"sm_mhz": None, "sm_max_mhz": 1965.0, "reasons": ["no samples: x"]})
+
+
+def test_core_binding_is_optional():
+    """bench.py binds a rank to the cores NVML lists as local to its GPU; without NVML or a GPU it leaves the process alone."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod2", ROOT / "bench.py")
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    before = os.sched_getaffinity(0)
+    n = b.bind_to_gpu_cores(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before

@@ -295,3 +295,17 @@ def test_slab_range(pkg):
             r = [d.slab_range(N, G, k) for k in range(G)]
             assert r[0][0] == 0 and r[-1][1] == N and all(a[1] == b[0] for a, b in zip(r, r[1:]))
             assert all(a[0] % 128 == 0 or a[0] == N for a in r) and d.slab_size(N, G) * G >= N
+
+
+def test_prefetch_is_a_device_feature(pkg):
+    """ShardedScorer.prefetch stages the next step's pinned host shards on the GPU; without a CUDA device it does nothing
+    and load() takes its inputs as they are (the GPU side: tests/test_gpu_multirank.py::test_prefetched_uploads_*)."""
+    d = importlib.import_module(PKG_NAME + ".distributed")
+    sc = d.ShardedScorer(engine=None, world=1, rank=0, device=None)
+    img, chk = {"emb": np.zeros((2, 64), np.float32)}, {"emb": np.zeros((3, 64), np.float32)}
+    sc.prefetch(img, chk)
+    assert sc._prefetched is None
+    assert sc._take_prefetched(img, chk) == (img, chk)
+    other = {"emb": np.zeros((2, 64), np.float32)}
+    sc._prefetched = (id(other), id(chk), "staged images", "staged chunks", None)   # staged for other objects: ignored, dropped
+    assert sc._take_prefetched(img, chk) == (img, chk) and sc._prefetched is None
